@@ -1,0 +1,683 @@
+// plbm_api.cu -- the C ABI of libplbm_b200.so (include/plbm.h): handle lifecycle, property
+// derivation, step orchestration (iold/inew bookkeeping identical to the reference) and
+// host <-> device staging of the macroscopic fields.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "plbm_internal.h"
+
+namespace plbm {
+
+std::atomic<long long> g_launches{0};
+static thread_local std::string t_error;
+
+void set_error(const std::string& msg) { t_error = msg; }
+int cuda_fail(cudaError_t e, const char* what)
+{
+    t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return PLBM_ERR_CUDA;
+}
+
+namespace {
+
+int check(plbm_handle g)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    cudaError_t e = cudaSetDevice(g->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return PLBM_OK;
+}
+
+int need_props(plbm_handle g)
+{
+    if (!g->props_set) {
+        set_error("set_properties has not been called on this grid");
+        return PLBM_ERR_STATE;
+    }
+    return PLBM_OK;
+}
+
+bool valid_model(int m) { return m == PLBM_BGK || m == PLBM_TRT || m == PLBM_RR || m == PLBM_BGK_SPLIT; }
+
+void swap_lattices(Grid& g)
+{
+    int t = g.iold;
+    g.iold = g.inew;
+    g.inew = t;
+}
+
+// src/collision_trt.F90:30-34 lambda_d(omega, x), in working precision
+template <typename T> T lambda_d(T omega, T x) { return (T(4) - T(2) * omega) / (T(4) * x * omega + T(2) - omega); }
+
+template <typename T> CollideParams<T> collide_params(const Grid& g, int model)
+{
+    CollideParams<T> cp;
+    cp.omega = (T)g.omega;
+    cp.lambda_d = model == PLBM_TRT ? lambda_d<T>((T)g.omega, (T)g.trt_magic) : T(0);
+    return cp;
+}
+
+template <typename T> LbmArgs<T> lbm_args(const Grid& g, int src, int dst, int model)
+{
+    LbmArgs<T> a;
+    a.src = g.lat<T>(src);
+    a.dst = g.lat<T>(dst);
+    a.nx = g.nx;
+    a.ny = g.ny;
+    a.ld = g.ld;
+    a.x_begin = 0;
+    a.x_end = g.nx;
+    a.halo_lo = nullptr;
+    a.halo_hi = nullptr;
+    a.cp = collide_params<T>(g, model);
+    return a;
+}
+
+// DUGKS relaxation rates, src/periodic_dugks.F90:40-44, 53, 60, 68-71, 180-181
+template <typename T> void dugks_rates(const Grid& g, bool dugks, T& omega_full, T& omega_half, T& omega_face)
+{
+    const T tau_d = (T)g.tau / (T)g.dt;
+    omega_full = (T)g.omega;  // first kernel_bgk call uses grid%omega
+    T omega = T(1) / (tau_d + T(0.5));
+    if (dugks) omega = T(0.75) * omega;
+    omega_half = omega;
+    omega_face = T(1) / (T(4) * tau_d + T(1));
+}
+
+template <typename T> int set_properties_t(Grid& g, double nu_, double dt_, double magic_, int has_magic)
+{
+    // src/fvm_bardow.F90:242-269, all arithmetic in working precision
+    const T nu = (T)nu_, dt = (T)dt_;
+    const T csqr = T(1) / T(3);
+    const T invcsqr = T(1) / csqr;
+    const T tau = invcsqr * nu;
+    g.nu = nu;
+    g.dt = dt;
+    g.csqr = csqr;
+    g.tau = tau;
+    g.omega = dt / (tau + T(0.5) * dt);
+    g.trt_magic = has_magic ? (T)magic_ : (tau / dt) * (tau / dt);
+    g.props_set = true;
+    return PLBM_OK;
+}
+
+// Apply the deferred half-step collision of the last fused DUGKS step to lattice `inew`.
+int materialize_inew(Grid& g)
+{
+    if (!g.dugks_pending) return PLBM_OK;
+    g.dugks_pending = false;
+    if (g.prec == PLBM_F64) {
+        LbmArgs<double> a = lbm_args<double>(g, g.inew, g.inew, PLBM_BGK);
+        a.cp.omega = g.dugks_pending_omega;
+        return launch_lbm<double>(a, M_BGK_SPLIT, false, g.variant, g.stream);
+    }
+    LbmArgs<float> a = lbm_args<float>(g, g.inew, g.inew, PLBM_BGK);
+    a.cp.omega = (float)g.dugks_pending_omega;
+    return launch_lbm<float>(a, M_BGK_SPLIT, false, g.variant, g.stream);
+}
+
+template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
+{
+    g.dugks_pending = false;  // lattice inew is overwritten below
+    if (g.comm) return comm_lbm_steps<T>(g, model, collide_params<T>(g, model), nsteps);
+    for (int s = 0; s < nsteps; ++s) {
+        LbmArgs<T> a = lbm_args<T>(g, g.iold, g.inew, model);
+        int rc = launch_lbm<T>(a, model, true, g.variant, g.stream);
+        if (rc) return rc;
+        swap_lattices(g);
+    }
+    return PLBM_OK;
+}
+
+template <typename T> int step_fvm_t(Grid& g, int model, int nsteps)
+{
+    const CollideParams<T> cp = collide_params<T>(g, model);
+    g.dugks_pending = false;  // lattice inew is overwritten below
+    for (int s = 0; s < nsteps; ++s) {
+        int rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, model, cp, g.stream);
+        if (rc) return rc;
+        swap_lattices(g);
+    }
+    return PLBM_OK;
+}
+
+template <typename T> int step_dugks_t(Grid& g, bool dugks, int nsteps)
+{
+    T of, oh, oc;
+    dugks_rates<T>(g, dugks, of, oh, oc);
+    for (int s = 0; s < nsteps; ++s) {
+        int rc;
+        g.dugks_pending = false;  // lattice inew is overwritten below
+        if (g.variant == 1) {  // reference structure: collide pass + stream pass
+            rc = launch_dugks_collide<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), of, oh, g.stream);
+            if (rc) return rc;
+            rc = launch_dugks_stream<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, oc, dugks, g.stream);
+        } else {
+            // fused: lattice iold (ftilde^n) is left untouched, inew receives ftilde^{n+1}.
+            rc = launch_dugks_fused<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, of, oh, oc, dugks, g.stream);
+        }
+        if (rc) return rc;
+        swap_lattices(g);
+        if (g.variant != 1) {
+            g.dugks_pending = true;
+            g.dugks_pending_omega = (double)oh;
+        }
+    }
+    return PLBM_OK;
+}
+
+template <typename T> int upload_field(Grid& g, T* dev, const void* host)
+{
+    PLBM_CUDA(cudaMemcpyAsync(dev, host, sizeof(T) * (size_t)g.nx * g.ny, cudaMemcpyHostToDevice, g.stream));
+    return PLBM_OK;
+}
+template <typename T> int download_field(Grid& g, void* host, const T* dev)
+{
+    if (!host) return PLBM_OK;
+    PLBM_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * (size_t)g.nx * g.ny, cudaMemcpyDeviceToHost, g.stream));
+    return PLBM_OK;
+}
+
+template <typename T> int set_pdf_to_equilibrium_t(Grid& g, const void* rho, const void* ux, const void* uy)
+{
+    int rc;
+    if ((rc = upload_field<T>(g, g.rho<T>(), rho))) return rc;
+    if ((rc = upload_field<T>(g, g.ux<T>(), ux))) return rc;
+    if ((rc = upload_field<T>(g, g.uy<T>(), uy))) return rc;
+    return launch_init_eq<T>(g, g.lat<T>(g.iold), g.stream);
+}
+
+}  // namespace
+}  // namespace plbm
+
+using namespace plbm;
+
+#define DISPATCH(g, expr_d, expr_f) ((g)->prec == PLBM_F64 ? (expr_d) : (expr_f))
+
+extern "C" {
+
+const char* plbm_last_error(void) { return t_error.c_str(); }
+int plbm_version(void) { return 100; }
+long long plbm_launch_count(void) { return g_launches.load(); }
+
+int plbm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int plbm_alloc_grid_on(plbm_handle* out, int nx, int ny, int nf, int precision, int device)
+{
+    if (!out || nx < 1 || ny < 1 || (nf != 2 && nf != 3) || (precision != PLBM_F64 && precision != PLBM_F32)) {
+        set_error("alloc_grid: bad argument (need nx,ny >= 1, nf in {2,3}, precision in {F64,F32})");
+        return PLBM_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libplbm_b200 has no CPU fallback");
+        return PLBM_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("alloc_grid: device ordinal out of range");
+        return PLBM_ERR_ARG;
+    }
+    PLBM_CUDA(cudaSetDevice(device));
+    plbm_grid_s* g = new plbm_grid_s();
+    g->nx = nx;
+    g->ny = ny;
+    g->nx_global = nx;
+    // round the unit-stride dimension up to a multiple of 16 (src/fvm_bardow.F90:144-147)
+    g->ld = (ny + 15) / 16 * 16;
+    g->nf = nf;
+    g->prec = precision;
+    g->device = device;
+    g->inew = 1;
+    g->iold = 2;
+    g->imid = nf > 2 ? 3 : -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) g->sm_count = prop.multiProcessorCount;
+    const size_t es = g->esize();
+    const size_t nm = (size_t)nx * ny;
+    auto fail = [&](cudaError_t err, const char* what) {
+        int rc = cuda_fail(err, what);
+        plbm_dealloc_grid(g);
+        return rc;
+    };
+    for (int i = 0; i < nf; ++i) {
+        e = cudaMalloc(&g->f[i], g->lattice_elems() * es);
+        if (e != cudaSuccess) return fail(e, "cudaMalloc(lattice)");
+    }
+    if ((e = cudaMalloc(&g->mf, 3 * nm * es)) != cudaSuccess) return fail(e, "cudaMalloc(mf)");
+    if ((e = cudaMalloc(&g->aux, nm * es)) != cudaSuccess) return fail(e, "cudaMalloc(aux)");
+    if ((e = cudaMalloc(&g->aux2, nm * es)) != cudaSuccess) return fail(e, "cudaMalloc(aux2)");
+    g->npartial = 4 * g->sm_count;
+    if ((e = cudaMalloc(&g->partial, 32 * (size_t)g->npartial)) != cudaSuccess) return fail(e, "cudaMalloc(partial)");
+    if ((e = cudaMallocHost(&g->partial_host, 32 * (size_t)g->npartial)) != cudaSuccess) return fail(e, "cudaMallocHost");
+    if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    g->own_stream = true;
+    *out = g;
+    return PLBM_OK;
+}
+
+int plbm_alloc_grid(plbm_handle* out, int nx, int ny, int nf, int precision)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        dev = 0;
+    }
+    return plbm_alloc_grid_on(out, nx, ny, nf, precision, dev);
+}
+
+int plbm_dealloc_grid(plbm_handle g)
+{
+    if (!g) return PLBM_OK;
+    cudaSetDevice(g->device);
+    if (g->comm) comm_finalize(*g);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    for (int i = 0; i < 3; ++i)
+        if (g->f[i]) cudaFree(g->f[i]);
+    if (g->mf) cudaFree(g->mf);
+    if (g->aux) cudaFree(g->aux);
+    if (g->aux2) cudaFree(g->aux2);
+    if (g->partial) cudaFree(g->partial);
+    if (g->partial_host) cudaFreeHost(g->partial_host);
+    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+    return PLBM_OK;
+}
+
+int plbm_get_dims(plbm_handle g, int* nx, int* ny, int* ld, int* nf, int* precision)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    if (nx) *nx = g->nx;
+    if (ny) *ny = g->ny;
+    if (ld) *ld = g->ld;
+    if (nf) *nf = g->nf;
+    if (precision) *precision = g->prec;
+    return PLBM_OK;
+}
+
+int plbm_get_indices(plbm_handle g, int* iold, int* inew, int* imid)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    if (iold) *iold = g->iold;
+    if (inew) *inew = g->inew;
+    if (imid) *imid = g->imid;
+    return PLBM_OK;
+}
+
+int plbm_set_properties(plbm_handle g, double nu, double dt, double magic, int has_magic)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    if (!(dt > 0) || !(nu >= 0)) {
+        set_error("set_properties: need dt > 0 and nu >= 0");
+        return PLBM_ERR_ARG;
+    }
+    return DISPATCH(g, set_properties_t<double>(*g, nu, dt, magic, has_magic), set_properties_t<float>(*g, nu, dt, magic, has_magic));
+}
+
+int plbm_get_properties(plbm_handle g, double out[6])
+{
+    if (!g || !out) {
+        set_error("get_properties: null argument");
+        return PLBM_ERR_ARG;
+    }
+    int rc = need_props(g);
+    if (rc) return rc;
+    out[0] = g->nu;
+    out[1] = g->dt;
+    out[2] = g->tau;
+    out[3] = g->omega;
+    out[4] = g->trt_magic;
+    out[5] = g->csqr;
+    return PLBM_OK;
+}
+
+int plbm_set_omega(plbm_handle g, double omega)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    g->omega = g->prec == PLBM_F64 ? omega : (double)(float)omega;
+    return PLBM_OK;
+}
+
+int plbm_set_pdf_to_equilibrium(plbm_handle g, const void* rho, const void* ux, const void* uy)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (!rho || !ux || !uy) {
+        set_error("set_pdf_to_equilibrium: null field pointer");
+        return PLBM_ERR_ARG;
+    }
+    if ((rc = materialize_inew(*g))) return rc;
+    comm_invalidate_halo(*g);
+    rc = DISPATCH(g, set_pdf_to_equilibrium_t<double>(*g, rho, ux, uy), set_pdf_to_equilibrium_t<float>(*g, rho, ux, uy));
+    if (rc) return rc;
+    // the host buffers are borrowed for the call only
+    PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_perform_lbm_step(plbm_handle g, int collision, int nsteps)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    if (!valid_model(collision) || nsteps < 0) {
+        set_error("perform_lbm_step: bad collision id or nsteps");
+        return PLBM_ERR_ARG;
+    }
+    return DISPATCH(g, step_lbm_t<double>(*g, collision, nsteps), step_lbm_t<float>(*g, collision, nsteps));
+}
+
+int plbm_perform_step(plbm_handle g, int streaming, int collision, int nsteps)
+{
+    if (streaming == PLBM_STREAM_LBM) return plbm_perform_lbm_step(g, collision, nsteps);
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    if (streaming != PLBM_STREAM_FVM_BARDOW || !valid_model(collision) || nsteps < 0) {
+        set_error("perform_step: bad streaming/collision id or nsteps");
+        return PLBM_ERR_ARG;
+    }
+    if (g->comm) {
+        set_error("perform_step(fvm_bardow): slab decomposition not supported for this scheme");
+        return PLBM_ERR_ARG;
+    }
+    return DISPATCH(g, step_fvm_t<double>(*g, collision, nsteps), step_fvm_t<float>(*g, collision, nsteps));
+}
+
+int plbm_perform_dugks_step(plbm_handle g, int dugks, int nsteps)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    if (nsteps < 0) {
+        set_error("perform_dugks_step: bad nsteps");
+        return PLBM_ERR_ARG;
+    }
+    if (g->comm) {
+        set_error("perform_dugks_step: slab decomposition not supported for this scheme");
+        return PLBM_ERR_ARG;
+    }
+    return DISPATCH(g, step_dugks_t<double>(*g, dugks != 0, nsteps), step_dugks_t<float>(*g, dugks != 0, nsteps));
+}
+
+int plbm_lbm_stream(plbm_handle g)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (g->comm) {
+        set_error("lbm_stream: unfused entry points are single-GPU only");
+        return PLBM_ERR_ARG;
+    }
+    g->dugks_pending = false;  // lattice inew is overwritten
+    if (g->prec == PLBM_F64) return launch_lbm<double>(lbm_args<double>(*g, g->iold, g->inew, PLBM_BGK), M_NONE, true, g->variant, g->stream);
+    return launch_lbm<float>(lbm_args<float>(*g, g->iold, g->inew, PLBM_BGK), M_NONE, true, g->variant, g->stream);
+}
+
+int plbm_stream_fvm_bardow(plbm_handle g)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    g->dugks_pending = false;  // lattice inew is overwritten
+    if (g->prec == PLBM_F64)
+        return launch_fvm_bardow<double>(*g, g->lat<double>(g->iold), g->lat<double>(g->inew), (double)g->dt, M_NONE,
+                                         CollideParams<double>{0, 0}, g->stream);
+    return launch_fvm_bardow<float>(*g, g->lat<float>(g->iold), g->lat<float>(g->inew), (float)g->dt, M_NONE,
+                                    CollideParams<float>{0, 0}, g->stream);
+}
+
+int plbm_collide(plbm_handle g, int collision)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    if (!valid_model(collision)) {
+        set_error("collide: bad collision id");
+        return PLBM_ERR_ARG;
+    }
+    if ((rc = materialize_inew(*g))) return rc;
+    // in place on lattice inew, like collide_bgk/trt/rr
+    if (g->prec == PLBM_F64) return launch_lbm<double>(lbm_args<double>(*g, g->inew, g->inew, collision), collision, false, g->variant, g->stream);
+    return launch_lbm<float>(lbm_args<float>(*g, g->inew, g->inew, collision), collision, false, g->variant, g->stream);
+}
+
+int plbm_dugks_collide(plbm_handle g, int dugks)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    g->dugks_pending = false;  // lattice inew is overwritten
+    if (g->prec == PLBM_F64) {
+        double of, oh, oc;
+        dugks_rates<double>(*g, dugks != 0, of, oh, oc);
+        return launch_dugks_collide<double>(*g, g->lat<double>(g->iold), g->lat<double>(g->inew), of, oh, g->stream);
+    }
+    float of, oh, oc;
+    dugks_rates<float>(*g, dugks != 0, of, oh, oc);
+    return launch_dugks_collide<float>(*g, g->lat<float>(g->iold), g->lat<float>(g->inew), of, oh, g->stream);
+}
+
+int plbm_dugks_stream(plbm_handle g, int dugks)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    if (g->prec == PLBM_F64) {
+        double of, oh, oc;
+        dugks_rates<double>(*g, dugks != 0, of, oh, oc);
+        return launch_dugks_stream<double>(*g, g->lat<double>(g->iold), g->lat<double>(g->inew), (double)g->dt, oc, dugks != 0, g->stream);
+    }
+    float of, oh, oc;
+    dugks_rates<float>(*g, dugks != 0, of, oh, oc);
+    return launch_dugks_stream<float>(*g, g->lat<float>(g->iold), g->lat<float>(g->inew), (float)g->dt, oc, dugks != 0, g->stream);
+}
+
+int plbm_swap(plbm_handle g)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = materialize_inew(*g))) return rc;
+    swap_lattices(*g);
+    return PLBM_OK;
+}
+
+int plbm_update_macros(plbm_handle g, void* rho, void* ux, void* uy, int lagged)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    const int which = lagged ? g->inew : g->iold;
+    if (lagged && (rc = materialize_inew(*g))) return rc;
+    if (g->prec == PLBM_F64) {
+        if ((rc = launch_macros<double>(*g, g->lat<double>(which), g->stream))) return rc;
+        if ((rc = download_field<double>(*g, rho, g->rho<double>()))) return rc;
+        if ((rc = download_field<double>(*g, ux, g->ux<double>()))) return rc;
+        if ((rc = download_field<double>(*g, uy, g->uy<double>()))) return rc;
+    } else {
+        if ((rc = launch_macros<float>(*g, g->lat<float>(which), g->stream))) return rc;
+        if ((rc = download_field<float>(*g, rho, g->rho<float>()))) return rc;
+        if ((rc = download_field<float>(*g, ux, g->ux<float>()))) return rc;
+        if ((rc = download_field<float>(*g, uy, g->uy<float>()))) return rc;
+    }
+    if (rho || ux || uy) PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_vorticity(plbm_handle g, int order, void* omega)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (g->comm) {
+        set_error("vorticity: single-GPU only (gather the macroscopic fields first)");
+        return PLBM_ERR_ARG;
+    }
+    if (g->prec == PLBM_F64) {
+        if ((rc = launch_vorticity<double>(*g, order, g->ux<double>(), g->uy<double>(), (double*)g->aux, g->stream))) return rc;
+        if ((rc = download_field<double>(*g, omega, (double*)g->aux))) return rc;
+    } else {
+        if ((rc = launch_vorticity<float>(*g, order, g->ux<float>(), g->uy<float>(), (float*)g->aux, g->stream))) return rc;
+        if ((rc = download_field<float>(*g, omega, (float*)g->aux))) return rc;
+    }
+    if (omega) PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_vorticity_host(plbm_handle g, int order, const void* ux, const void* uy, void* omega)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (!ux || !uy || !omega) {
+        set_error("vorticity_host: null pointer");
+        return PLBM_ERR_ARG;
+    }
+    // stage through the device macroscopic fields (overwrites ux, uy)
+    if (g->prec == PLBM_F64) {
+        if ((rc = upload_field<double>(*g, g->ux<double>(), ux))) return rc;
+        if ((rc = upload_field<double>(*g, g->uy<double>(), uy))) return rc;
+    } else {
+        if ((rc = upload_field<float>(*g, g->ux<float>(), ux))) return rc;
+        if ((rc = upload_field<float>(*g, g->uy<float>(), uy))) return rc;
+    }
+    return plbm_vorticity(g, order, omega);
+}
+
+int plbm_diagnostics(plbm_handle g, double out[PLBM_DIAG_COUNT])
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (!out) {
+        set_error("diagnostics: null output");
+        return PLBM_ERR_ARG;
+    }
+    return DISPATCH(g, launch_diagnostics<double>(*g, out, g->stream), launch_diagnostics<float>(*g, out, g->stream));
+}
+
+int plbm_l2_sums(plbm_handle g, const void* uxa, const void* uya, double out[2])
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (!uxa || !uya || !out) {
+        set_error("l2_sums: null pointer");
+        return PLBM_ERR_ARG;
+    }
+    if (g->prec == PLBM_F64) {
+        if ((rc = upload_field<double>(*g, (double*)g->aux, uxa))) return rc;
+        if ((rc = upload_field<double>(*g, (double*)g->aux2, uya))) return rc;
+        return launch_l2_sums<double>(*g, (const double*)g->aux, (const double*)g->aux2, out, g->stream);
+    }
+    if ((rc = upload_field<float>(*g, (float*)g->aux, uxa))) return rc;
+    if ((rc = upload_field<float>(*g, (float*)g->aux2, uya))) return rc;
+    return launch_l2_sums<float>(*g, (const float*)g->aux, (const float*)g->aux2, out, g->stream);
+}
+
+int plbm_upload_f(plbm_handle g, int which, const void* host_f)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (which < 1 || which > g->nf || !host_f) {
+        set_error("upload_f: bad lattice index or null pointer");
+        return PLBM_ERR_ARG;
+    }
+    if (which == g->inew) g->dugks_pending = false;
+    else if ((rc = materialize_inew(*g))) return rc;
+    comm_invalidate_halo(*g);
+    PLBM_CUDA(cudaMemcpyAsync(g->f[which - 1], host_f, g->lattice_elems() * g->esize(), cudaMemcpyHostToDevice, g->stream));
+    PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_download_f(plbm_handle g, int which, void* host_f)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (which < 1 || which > g->nf || !host_f) {
+        set_error("download_f: bad lattice index or null pointer");
+        return PLBM_ERR_ARG;
+    }
+    if (which == g->inew && (rc = materialize_inew(*g))) return rc;
+    PLBM_CUDA(cudaMemcpyAsync(host_f, g->f[which - 1], g->lattice_elems() * g->esize(), cudaMemcpyDeviceToHost, g->stream));
+    PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_set_stream(plbm_handle g, void* cuda_stream)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    if (g->own_stream) {
+        cudaStreamDestroy(g->stream);
+        g->own_stream = false;
+    }
+    if (cuda_stream) {
+        g->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        PLBM_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+        g->own_stream = true;
+    }
+    return PLBM_OK;
+}
+
+int plbm_synchronize(plbm_handle g)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_set_variant(plbm_handle g, int variant)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return PLBM_ERR_ARG;
+    }
+    g->variant = variant;
+    return PLBM_OK;
+}
+
+int plbm_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+
+int plbm_comm_init(plbm_handle g, const void* id128, int rank, int nranks, int nx_global, int x_offset)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    return comm_init(*g, id128, rank, nranks, nx_global, x_offset);
+}
+
+int plbm_comm_finalize(plbm_handle g)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    return comm_finalize(*g);
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// plbm_comm.cu -- slab decomposition along the slow index across the GPUs of one box.
+//
+// The reference is single-process; this is new functionality whose correctness
+// is defined as "bitwise identical to the single-GPU result".  Rank r owns nx lines starting
+// at x_offset and forms a periodic ring with r-1 (lo) and r+1 (hi).  Pull streaming needs,
+// per step, the last line of the populations moving in +x (q = 1,5,8) from lo and the first
+// line of those moving in -x (q = 3,6,7) from hi: 3 x ld reals per direction.
+//
+// Per step (src -> dst), two streams:
+//   main : wait(halo[src]) -> boundary lines 0 and nx-1 -> pack dst boundary -> record(packed)
+//          -> interior lines 1 .. nx-2                       (overlaps the exchange)
+//   comm : wait(packed) -> grouped ncclSend x2 / ncclRecv x2 into halo[dst] -> record(halo[dst])
+// Halo buffers are double-buffered by step parity.  NCCL is resolved with dlopen at
+// comm_init time so the single-GPU library has no link-time dependency on it.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "plbm_internal.h"
+
+namespace plbm {
+
+namespace {
+struct NcclUniqueId {
+    char internal[128];
+};
+typedef void* ncclComm_t;
+typedef int ncclResult_t;
+constexpr int kNcclInt8 = 0;
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl()
+{
+    if (g_nccl.lib) return PLBM_OK;
+    // a process that already imported torch has its bundled libnccl.so.2 mapped: same soname
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names)
+        if ((lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) {
+        set_error(std::string("cannot load NCCL: ") + dlerror());
+        return PLBM_ERR_COMM;
+    }
+#define SYM(field, name)                                                   \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                           \
+    if (!g_nccl.field) {                                                   \
+        set_error(std::string("NCCL symbol missing: ") + name);            \
+        return PLBM_ERR_COMM;                                              \
+    }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = lib;
+    return PLBM_OK;
+}
+
+int nccl_fail(ncclResult_t r, const char* what)
+{
+    set_error(std::string("NCCL error: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?") + " in " + what);
+    return PLBM_ERR_COMM;
+}
+#define PLBM_NCCL(call)                                  \
+    do {                                                 \
+        ncclResult_t _r = (call);                        \
+        if (_r != 0) return nccl_fail(_r, #call);        \
+    } while (0)
+}  // namespace
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1, lo = 0, hi = 0;
+    cudaStream_t stream = nullptr;          // exchange stream
+    cudaEvent_t ev_packed = nullptr;        // send buffers ready (main -> comm)
+    cudaEvent_t ev_halo[2] = {nullptr, nullptr};  // halo[p] received (comm -> main)
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // halo[p] read by the boundary kernels (main -> comm)
+    void* send_lo = nullptr;                // line 0 of q = 3,6,7   -> rank lo
+    void* send_hi = nullptr;                // line nx-1 of q = 1,5,8 -> rank hi
+    void* halo_lo[2] = {nullptr, nullptr};  // from lo: q = 1,5,8
+    void* halo_hi[2] = {nullptr, nullptr};  // from hi: q = 3,6,7
+    size_t bytes = 0;
+    int parity = 0;        // halo slot holding the neighbours' lines of lattice `iold`
+    bool halo_valid = false;
+    int halo_of_lattice = 0;
+};
+
+int comm_unique_id(void* id128)
+{
+    if (!id128) {
+        set_error("comm_unique_id: null pointer");
+        return PLBM_ERR_ARG;
+    }
+    int rc = load_nccl();
+    if (rc) return rc;
+    NcclUniqueId id;
+    PLBM_NCCL(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+    return PLBM_OK;
+}
+
+int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, int x_offset)
+{
+    if (g.comm) {
+        set_error("comm_init: already initialised");
+        return PLBM_ERR_STATE;
+    }
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks || x_offset < 0 || x_offset + g.nx > nx_global) {
+        set_error("comm_init: bad argument");
+        return PLBM_ERR_ARG;
+    }
+    if (g.nx < 2 && nranks > 1) {
+        set_error("comm_init: every slab needs at least 2 lines");
+        return PLBM_ERR_ARG;
+    }
+    int rc = load_nccl();
+    if (rc) return rc;
+    Comm* c = new Comm();
+    c->rank = rank;
+    c->nranks = nranks;
+    c->lo = (rank + nranks - 1) % nranks;
+    c->hi = (rank + 1) % nranks;
+    c->bytes = 3 * (size_t)g.ld * g.esize();
+    NcclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) {
+        delete c;
+        return nccl_fail(r, "ncclCommInitRank");
+    }
+    PLBM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PLBM_CUDA(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    for (int p = 0; p < 2; ++p) {
+        PLBM_CUDA(cudaEventCreateWithFlags(&c->ev_halo[p], cudaEventDisableTiming));
+        PLBM_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[p], cudaEventDisableTiming));
+        PLBM_CUDA(cudaMalloc(&c->halo_lo[p], c->bytes));
+        PLBM_CUDA(cudaMalloc(&c->halo_hi[p], c->bytes));
+    }
+    PLBM_CUDA(cudaMalloc(&c->send_lo, c->bytes));
+    PLBM_CUDA(cudaMalloc(&c->send_hi, c->bytes));
+    g.comm = c;
+    g.nx_global = nx_global;
+    g.x_offset = x_offset;
+    return PLBM_OK;
+}
+
+int comm_finalize(Grid& g)
+{
+    Comm* c = g.comm;
+    if (!c) return PLBM_OK;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (g.stream) cudaStreamSynchronize(g.stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (int p = 0; p < 2; ++p) {
+        if (c->halo_lo[p]) cudaFree(c->halo_lo[p]);
+        if (c->halo_hi[p]) cudaFree(c->halo_hi[p]);
+        if (c->ev_halo[p]) cudaEventDestroy(c->ev_halo[p]);
+        if (c->ev_consumed[p]) cudaEventDestroy(c->ev_consumed[p]);
+    }
+    if (c->send_lo) cudaFree(c->send_lo);
+    if (c->send_hi) cudaFree(c->send_hi);
+    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    g.comm = nullptr;
+    g.nx_global = g.nx;
+    g.x_offset = 0;
+    return PLBM_OK;
+}
+
+void comm_invalidate_halo(Grid& g)
+{
+    if (g.comm) g.comm->halo_valid = false;
+}
+
+// Post the ring exchange of the packed boundary lines into halo slot p (on the comm stream).
+static int exchange(Grid& g, int p)
+{
+    Comm* c = g.comm;
+    PLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_packed, 0));
+    // do not overwrite halo[p] before the boundary kernels of two steps ago have read it
+    PLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_consumed[p], 0));
+    PLBM_NCCL(g_nccl.GroupStart());
+    // posting order matters when lo == hi (2 ranks): first message lands in the peer's halo_hi
+    PLBM_NCCL(g_nccl.Send(c->send_lo, c->bytes, kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Send(c->send_hi, c->bytes, kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv(c->halo_hi[p], c->bytes, kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv(c->halo_lo[p], c->bytes, kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.GroupEnd());
+    PLBM_CUDA(cudaEventRecord(c->ev_halo[p], c->stream));
+    return PLBM_OK;
+}
+
+template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps)
+{
+    Comm* c = g.comm;
+    int rc;
+    if (nsteps > 0 && (!c->halo_valid || c->halo_of_lattice != g.iold)) {
+        // first step after an initial condition / upload: exchange the boundary lines of `iold`
+        if ((rc = launch_halo_pack<T>(g, g.lat<T>(g.iold), (T*)c->send_lo, (T*)c->send_hi, g.stream))) return rc;
+        PLBM_CUDA(cudaEventRecord(c->ev_packed, g.stream));
+        if ((rc = exchange(g, c->parity))) return rc;
+        c->halo_valid = true;
+        c->halo_of_lattice = g.iold;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        const int p = c->parity;
+        LbmArgs<T> a;
+        a.src = g.lat<T>(g.iold);
+        a.dst = g.lat<T>(g.inew);
+        a.nx = g.nx;
+        a.ny = g.ny;
+        a.ld = g.ld;
+        a.halo_lo = (const T*)c->halo_lo[p];
+        a.halo_hi = (const T*)c->halo_hi[p];
+        a.cp = cp;
+        // boundary lines first: they need the neighbours' lines, and produce what must be sent
+        PLBM_CUDA(cudaStreamWaitEvent(g.stream, c->ev_halo[p], 0));
+        a.x_begin = 0;
+        a.x_end = 1;
+        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        a.x_begin = g.nx - 1;
+        a.x_end = g.nx;
+        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        PLBM_CUDA(cudaEventRecord(c->ev_consumed[p], g.stream));
+        if ((rc = launch_halo_pack<T>(g, a.dst, (T*)c->send_lo, (T*)c->send_hi, g.stream))) return rc;
+        PLBM_CUDA(cudaEventRecord(c->ev_packed, g.stream));
+        if ((rc = exchange(g, p ^ 1))) return rc;
+        // interior, overlapped with the exchange
+        a.x_begin = 1;
+        a.x_end = g.nx - 1;
+        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        // the send buffers are re-packed next step: the exchange must have consumed them by then.
+        // (the next pack is ordered after ev_halo[p^1], recorded after the sends completed.)
+        int t = g.iold;
+        g.iold = g.inew;
+        g.inew = t;
+        c->parity = p ^ 1;
+        c->halo_of_lattice = g.iold;
+    }
+    return PLBM_OK;
+}
+
+template int comm_lbm_steps<double>(Grid&, int, const CollideParams<double>&, int);
+template int comm_lbm_steps<float>(Grid&, int, const CollideParams<float>&, int);
+
+}  // namespace plbm

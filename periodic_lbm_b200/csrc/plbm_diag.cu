@@ -1,0 +1,250 @@
+// plbm_diag.cu -- initial condition, macroscopic moments, vorticity and the warp-shuffle
+// reductions for the moment / energy diagnostics (sm_100a).
+//
+//   set_pdf_to_equilibrium  src/fvm_bardow.F90:272-305
+//   update_macros_kernel    src/fvm_bardow.F90:356-388      (9 reads + 3 writes per node)
+//   vorticity_2nd / _4th    src/vorticity.f90:13-87         (4th-order weights as shipped)
+//   maxval/minval(hypot(ux,uy)), norm2(hypot(..))  app/main_taylor_green.f90:106,155,195-198
+#include "plbm_internal.h"
+
+namespace plbm {
+
+// ---- init / macros ---------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_init_eq(const T* __restrict__ rho, const T* __restrict__ ux,
+                                                 const T* __restrict__ uy, T* __restrict__ f, int nx, int ny, int ld)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = (int)(g / (size_t)ld);
+    const int y = (int)(g - (size_t)x * ld);
+    if (x >= nx || y >= ny) return;
+    const size_t m = (size_t)x * ny + y;
+    T feq[9];
+    equilibrium(rho[m], ux[m], uy[m], feq);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) f[((size_t)q * nx + x) * (size_t)ld + y] = feq[q];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_macros(const T* __restrict__ f, T* __restrict__ rho, T* __restrict__ ux,
+                                                T* __restrict__ uy, int nx, int ny, int ld)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = (int)(g / (size_t)ld);
+    const int y = (int)(g - (size_t)x * ld);
+    if (x >= nx || y >= ny) return;
+    T fs[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) fs[q] = f[((size_t)q * nx + x) * (size_t)ld + y];
+    T r, u, v;
+    macros(fs, r, u, v);
+    const size_t m = (size_t)x * ny + y;
+    rho[m] = r;
+    ux[m] = u;
+    uy[m] = v;
+}
+
+template <typename T> int launch_init_eq(const Grid& g, T* f, cudaStream_t s)
+{
+    const size_t n = (size_t)g.nx * g.ld;
+    k_init_eq<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g.rho<T>(), g.ux<T>(), g.uy<T>(), f, g.nx, g.ny, g.ld);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    return PLBM_OK;
+}
+
+template <typename T> int launch_macros(const Grid& g, const T* f, cudaStream_t s)
+{
+    const size_t n = (size_t)g.nx * g.ld;
+    k_macros<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, g.rho<T>(), g.ux<T>(), g.uy<T>(), g.nx, g.ny, g.ld);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    return PLBM_OK;
+}
+
+// ---- vorticity ---------------------------------------------------------------------------
+// Single-GPU periodic wrap in both directions (the multi-GPU slab path gathers macros first).
+template <typename T, int ORDER>
+__global__ void __launch_bounds__(256) k_vorticity(const T* __restrict__ ux, const T* __restrict__ uy,
+                                                   T* __restrict__ om, int nx, int ny)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = (int)(g / (size_t)ny);
+    const int y = (int)(g - (size_t)x * ny);
+    if (x >= nx) return;
+    auto wp = [](int i, int n) { return i >= n ? i - n : i; };
+    auto wm = [](int i, int n) { return i < 0 ? i + n : i; };
+    const int xp1 = wp(x + 1, nx), xm1 = wm(x - 1, nx), yp1 = wp(y + 1, ny), ym1 = wm(y - 1, ny);
+#define M(yy, xx) ((size_t)(xx) * ny + (yy))
+    T duydx, duxdy;
+    if (ORDER == 2) {
+        duydx = T(0.5) * (uy[M(y, xp1)] - uy[M(y, xm1)]);
+        duxdy = T(0.5) * (ux[M(yp1, x)] - ux[M(ym1, x)]);
+    } else {
+        const T t1 = T(1) / T(12), t2 = T(2) / T(3);
+        // mod(x+1,nx)+1 etc. on 1-based indices: +-2 neighbours (may wrap twice when n < 2)
+        const int xp2 = (x + 2) % nx, xm2 = (nx + x - 2 + nx) % nx, yp2 = (y + 2) % ny, ym2 = (ny + y - 2 + ny) % ny;
+        duydx = t1 * (uy[M(y, xp1)] - uy[M(y, xm1)]) + t2 * (uy[M(y, xm2)] - uy[M(y, xp2)]);
+        duxdy = t1 * (ux[M(yp1, x)] - ux[M(ym1, x)]) + t2 * (ux[M(ym2, x)] - ux[M(yp2, x)]);
+    }
+#undef M
+    om[(size_t)x * ny + y] = duydx - duxdy;
+}
+
+template <typename T> int launch_vorticity(const Grid& g, int order, const T* ux, const T* uy, T* out, cudaStream_t s)
+{
+    const size_t n = (size_t)g.nx * g.ny;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (order == 2)
+        k_vorticity<T, 2><<<nb, 256, 0, s>>>(ux, uy, out, g.nx, g.ny);
+    else if (order == 4)
+        k_vorticity<T, 4><<<nb, 256, 0, s>>>(ux, uy, out, g.nx, g.ny);
+    else {
+        set_error("vorticity: order must be 2 or 4");
+        return PLBM_ERR_ARG;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    return PLBM_OK;
+}
+
+// ---- reductions ---------------------------------------------------------------------------
+// Two-stage and deterministic: each block reduces its grid-stride share with warp shuffles and
+// writes one partial per quantity; the (few hundred) partials are combined on the host in a
+// fixed order.  Accumulation is in double for both precisions.
+struct Red4 {
+    double a, b, c, d;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// MODE 0: a = max |u|, b = min |u|, c = sum rho, d = 1/2 sum rho |u|^2
+// MODE 1: a = sum |u-ua|^2, b = sum |ua|^2   (p0 = uxa, p1 = uya)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) k_reduce(const T* __restrict__ rho, const T* __restrict__ ux,
+                                                const T* __restrict__ uy, const T* __restrict__ p0,
+                                                const T* __restrict__ p1, size_t n, Red4* __restrict__ partial)
+{
+    double a = MODE == 0 ? 0.0 : 0.0, b = MODE == 0 ? 1e300 : 0.0, c = 0.0, d = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double u = (double)ux[i], v = (double)uy[i];
+        if (MODE == 0) {
+            const double sp = hypot(u, v);
+            a = fmax(a, sp);
+            b = fmin(b, sp);
+            const double r = (double)rho[i];
+            c += r;
+            d += 0.5 * r * (u * u + v * v);
+        } else {
+            const double ua = (double)p0[i], va = (double)p1[i];
+            a += (u - ua) * (u - ua) + (v - va) * (v - va);
+            b += ua * ua + va * va;
+        }
+    }
+    if (MODE == 0) {
+        a = warp_max(a);
+        b = warp_min(b);
+        c = warp_sum(c);
+        d = warp_sum(d);
+    } else {
+        a = warp_sum(a);
+        b = warp_sum(b);
+    }
+    __shared__ Red4 sm[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sm[w] = Red4{a, b, c, d};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Red4 r = sm[0];
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+            if (MODE == 0) {
+                r.a = fmax(r.a, sm[i].a);
+                r.b = fmin(r.b, sm[i].b);
+                r.c += sm[i].c;
+                r.d += sm[i].d;
+            } else {
+                r.a += sm[i].a;
+                r.b += sm[i].b;
+            }
+        }
+        partial[blockIdx.x] = r;
+    }
+}
+
+template <typename T, int MODE>
+static int reduce_impl(Grid& g, const T* p0, const T* p1, Red4& out, cudaStream_t s)
+{
+    const size_t n = (size_t)g.nx * g.ny;
+    int nb = (int)((n + 255) / 256);
+    if (nb > g.npartial) nb = g.npartial;
+    k_reduce<T, MODE><<<nb, 256, 0, s>>>(g.rho<T>(), g.ux<T>(), g.uy<T>(), p0, p1, n, static_cast<Red4*>(g.partial));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    PLBM_CUDA(cudaMemcpyAsync(g.partial_host, g.partial, sizeof(Red4) * nb, cudaMemcpyDeviceToHost, s));
+    PLBM_CUDA(cudaStreamSynchronize(s));
+    const Red4* h = static_cast<const Red4*>(g.partial_host);
+    out = h[0];
+    for (int i = 1; i < nb; ++i) {
+        if (MODE == 0) {
+            out.a = h[i].a > out.a ? h[i].a : out.a;
+            out.b = h[i].b < out.b ? h[i].b : out.b;
+            out.c += h[i].c;
+            out.d += h[i].d;
+        } else {
+            out.a += h[i].a;
+            out.b += h[i].b;
+        }
+    }
+    return PLBM_OK;
+}
+
+template <typename T> int launch_diagnostics(Grid& g, double out[PLBM_DIAG_COUNT], cudaStream_t s)
+{
+    Red4 r{};
+    int rc = reduce_impl<T, 0>(g, nullptr, nullptr, r, s);
+    if (rc) return rc;
+    out[PLBM_DIAG_MAX_SPEED] = r.a;
+    out[PLBM_DIAG_MIN_SPEED] = r.b;
+    out[PLBM_DIAG_SUM_RHO] = r.c;
+    out[PLBM_DIAG_KINETIC] = r.d;
+    return PLBM_OK;
+}
+
+template <typename T> int launch_l2_sums(Grid& g, const T* uxa, const T* uya, double out[2], cudaStream_t s)
+{
+    Red4 r{};
+    int rc = reduce_impl<T, 1>(g, uxa, uya, r, s);
+    if (rc) return rc;
+    out[0] = r.a;
+    out[1] = r.b;
+    return PLBM_OK;
+}
+
+#define INST(T)                                                                                   \
+    template int launch_init_eq<T>(const Grid&, T*, cudaStream_t);                                \
+    template int launch_macros<T>(const Grid&, const T*, cudaStream_t);                           \
+    template int launch_vorticity<T>(const Grid&, int, const T*, const T*, T*, cudaStream_t);     \
+    template int launch_diagnostics<T>(Grid&, double[PLBM_DIAG_COUNT], cudaStream_t);             \
+    template int launch_l2_sums<T>(Grid&, const T*, const T*, double[2], cudaStream_t);
+INST(double)
+INST(float)
+#undef INST
+
+}  // namespace plbm

@@ -1,0 +1,103 @@
+// plbm_internal.h -- grid state and launcher prototypes shared by the translation units of
+// libplbm_b200.so.  Not part of the public ABI (that is include/plbm.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/plbm.h"
+#include "plbm_math.cuh"
+
+namespace plbm {
+
+extern std::atomic<long long> g_launches;  // kernels launched through the library
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define PLBM_CUDA(call)                                          \
+    do {                                                         \
+        cudaError_t _e = (call);                                 \
+        if (_e != cudaSuccess) return plbm::cuda_fail(_e, #call); \
+    } while (0)
+
+struct Comm;  // multi-GPU ring (plbm_comm.cu)
+
+// Device-resident mirror of the reference's `lattice_grid` (src/fvm_bardow.F90:37-69).
+struct Grid {
+    int nx = 0, ny = 0, ld = 0, nf = 2;
+    int prec = PLBM_F64;
+    int device = 0;
+    void* f[3] = {nullptr, nullptr, nullptr};  // PDF lattices, each f(ld,nx,0:8)
+    void* mf = nullptr;                        // rho, ux, uy: 3 x (ny,nx)
+    void* aux = nullptr;                       // scratch field (ny,nx): vorticity / analytic upload
+    void* aux2 = nullptr;
+    void* partial = nullptr;                   // reduction partials (device)
+    void* partial_host = nullptr;              // pinned host mirror
+    int npartial = 0;
+    int iold = 2, inew = 1, imid = -1;         // 1-based like the reference
+    // properties in working precision, widened to double for storage
+    double nu = 0, dt = 0, tau = 0, omega = 0, trt_magic = 0, csqr = 0;
+    bool props_set = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int variant = 0;
+    int sm_count = 148;
+    Comm* comm = nullptr;
+    // After a fused DUGKS step lattice `inew` still holds ftilde^n, whereas the reference leaves
+    // fbar^{+,n} = BGK(ftilde^n, omega_half) there (what the lagged update_macros reads).  The
+    // half-step collision is applied lazily, in place, the first time somebody looks at `inew`.
+    bool dugks_pending = false;
+    double dugks_pending_omega = 0;
+    // slab decomposition (single GPU: nx_global == nx, x_offset == 0)
+    int nx_global = 0, x_offset = 0;
+
+    size_t lattice_elems() const { return (size_t)ld * nx * 9; }
+    size_t esize() const { return prec == PLBM_F64 ? 8 : 4; }
+    template <typename T> T* lat(int which) const { return static_cast<T*>(f[which - 1]); }
+    template <typename T> T* rho() const { return static_cast<T*>(mf); }
+    template <typename T> T* ux() const { return static_cast<T*>(mf) + (size_t)nx * ny; }
+    template <typename T> T* uy() const { return static_cast<T*>(mf) + 2 * (size_t)nx * ny; }
+};
+
+// Arguments of the fused pull-stream + collide kernel family (plbm_lbm.cu).
+template <typename T> struct LbmArgs {
+    const T* src;
+    T* dst;
+    int nx, ny, ld;        // lines in this slab, rows, leading dimension
+    int x_begin, x_end;    // lines updated by this launch
+    // halo lines from the ring neighbours, [3][ld] each: slots (q=1,5,8) in lo, (q=3,6,7)
+    // in hi; nullptr = periodic self-wrap by index arithmetic (single GPU)
+    const T* halo_lo;
+    const T* halo_hi;
+    CollideParams<T> cp;
+};
+
+// ---- launchers (all asynchronous on `s`) -------------------------------------------------
+template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream_pdfs, int variant, cudaStream_t s);
+template <typename T> int launch_init_eq(const Grid& g, T* f, cudaStream_t s);
+template <typename T> int launch_macros(const Grid& g, const T* f, cudaStream_t s);
+template <typename T> int launch_vorticity(const Grid& g, int order, const T* ux, const T* uy, T* out, cudaStream_t s);
+template <typename T> int launch_diagnostics(Grid& g, double out[PLBM_DIAG_COUNT], cudaStream_t s);
+template <typename T> int launch_l2_sums(Grid& g, const T* uxa, const T* uya, double out[2], cudaStream_t s);
+template <typename T>
+int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s);
+template <typename T> int launch_dugks_collide(const Grid& g, T* fold, T* fnew, T omega_full, T omega_half, cudaStream_t s);
+template <typename T> int launch_dugks_stream(const Grid& g, const T* ft, T* fp, T dt, T omega_face, bool dugks, cudaStream_t s);
+template <typename T>
+int launch_dugks_fused(const Grid& g, const T* fin, T* fout, T dt, T omega_full, T omega_half, T omega_face, bool dugks,
+                       cudaStream_t s);
+template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s);
+
+// multi-GPU ring exchange (plbm_comm.cu)
+int comm_unique_id(void* id128);
+int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, int x_offset);
+int comm_finalize(Grid& g);
+void comm_invalidate_halo(Grid& g);  // the lattices were modified behind the ring's back
+template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps);
+
+}  // namespace plbm
+
+struct plbm_grid_s : plbm::Grid {};

@@ -1,0 +1,313 @@
+// plbm_math.cuh -- per-node D2Q9 arithmetic (device), sm_100a.
+//
+// Each function evaluates one node exactly as the reference's Fortran does: same pairing
+// of the moment sums, same left-to-right products, one reciprocal + two multiplies for the
+// velocity.  The library is compiled with -fmad=false, so every add/mul/div below is an
+// individually rounded IEEE operation and results are bit-identical to the non-FMA CPU
+// build of the reference (gfortran -O3 on baseline x86-64).
+//
+// Reference sources (relative to the reference root):
+//   equilibrium            src/fvm_bardow.F90:99-126
+//   bgk_kernel             src/collision_bgk.F90:35-82
+//   kernel_bgk / bgk_cache src/periodic_dugks.F90:80-169, src/collision_bgk.F90:84-176
+//   trt_naive              src/collision_trt.F90:13-34, 64-160
+//   rr_kernel_naive        src/collision_regularized.F90:40-202
+//   update_ew / update_ns  src/periodic_dugks.F90:310-434
+//   update_macros_kernel   src/fvm_bardow.F90:356-388
+#pragma once
+#include <cuda_runtime.h>
+
+namespace plbm {
+
+// D2Q9 velocity set, src/fvm_bardow.F90:87-88
+__host__ __device__ constexpr int cxi(int q) { return q == 1 || q == 5 || q == 8 ? 1 : (q == 3 || q == 6 || q == 7 ? -1 : 0); }
+__host__ __device__ constexpr int cyi(int q) { return q == 2 || q == 5 || q == 6 ? 1 : (q == 4 || q == 7 || q == 8 ? -1 : 0); }
+
+enum Model : int { M_NONE = -1, M_BGK = 0, M_TRT = 1, M_RR = 2, M_BGK_SPLIT = 3 };
+
+template <typename T> struct K {
+    // evaluated in working precision, like the Fortran `parameter`s with _wp literals
+    static __host__ __device__ constexpr T w0() { return T(4) / T(9); }
+    static __host__ __device__ constexpr T ws() { return T(1) / T(9); }
+    static __host__ __device__ constexpr T wd() { return T(1) / T(36); }
+    static __host__ __device__ constexpr T csqr() { return T(1) / T(3); }
+    static __host__ __device__ constexpr T one_third() { return T(1) / T(3); }
+};
+
+// Collision parameters, precomputed on the host in working precision.
+template <typename T> struct CollideParams {
+    T omega;     // grid%omega              (BGK, RR, split BGK; lambda_even for TRT)
+    T lambda_d;  // lambda_d(omega, magic)  (TRT only)
+};
+
+// rho, ux, uy with the collision kernels' summation order (f0 added last).
+template <typename T> __device__ __forceinline__ void moments(const T (&f)[9], T& rho, T& ux, T& uy)
+{
+    rho = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
+    T invrho = T(1) / rho;
+    ux = invrho * (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3]));
+    uy = invrho * (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4]));
+}
+
+// update_macros_kernel order: f0 added first (bitwise the same sum, kept literal).
+template <typename T> __device__ __forceinline__ void macros(const T (&f)[9], T& rho, T& ux, T& uy)
+{
+    rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4])));
+    T invrho = T(1) / rho;
+    ux = invrho * (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3]));
+    uy = invrho * (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4]));
+}
+
+template <typename T> __device__ __forceinline__ void equilibrium(T rho, T ux, T uy, T (&feq)[9])
+{
+    const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd();
+    T uxx = ux * ux;
+    T uyy = uy * uy;
+    T indp = T(1) - T(1.5) * (uxx + uyy);
+    feq[0] = w0 * rho * (indp);
+    feq[1] = ws * rho * (indp + T(3) * ux + T(4.5) * uxx);
+    feq[2] = ws * rho * (indp + T(3) * uy + T(4.5) * uyy);
+    feq[3] = ws * rho * (indp - T(3) * ux + T(4.5) * uxx);
+    feq[4] = ws * rho * (indp - T(3) * uy + T(4.5) * uyy);
+    T uxpy = ux + uy;
+    feq[5] = wd * rho * (indp + T(3) * uxpy + T(4.5) * uxpy * uxpy);
+    feq[7] = wd * rho * (indp - T(3) * uxpy + T(4.5) * uxpy * uxpy);
+    T uxmy = ux - uy;
+    feq[6] = wd * rho * (indp - T(3) * uxmy + T(4.5) * uxmy * uxmy);
+    feq[8] = wd * rho * (indp + T(3) * uxmy + T(4.5) * uxmy * uxmy);
+}
+
+template <typename T> __device__ __forceinline__ void collide_bgk(T (&f)[9], T omega)
+{
+    T omegabar = T(1) - omega;
+    T rho, ux, uy, feq[9];
+    moments(f, rho, ux, uy);
+    equilibrium(rho, ux, uy, feq);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) f[q] = omegabar * f[q] + omega * feq[q];
+}
+
+// Re-associated BGK of kernel_bgk / bgk_kernel_cache (numerically different from collide_bgk).
+template <typename T> __device__ __forceinline__ void collide_bgk_split(T (&f)[9], T omega)
+{
+    const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd();
+    T omegabar = T(1) - omega;
+    T omega_w0 = T(3) * omega * w0;
+    T omega_ws = T(3) * omega * ws;
+    T omega_wd = T(3) * omega * wd;
+    T rho, ux, uy;
+    moments(f, rho, ux, uy);
+    T indp = K<T>::one_third() - T(0.5) * (ux * ux + uy * uy);
+
+    f[0] = omegabar * f[0] + omega_w0 * rho * indp;
+    T vel_trm_13 = indp + T(1.5) * ux * ux;
+    f[1] = omegabar * f[1] + omega_ws * rho * (vel_trm_13 + ux);
+    f[3] = omegabar * f[3] + omega_ws * rho * (vel_trm_13 - ux);
+    T vel_trm_24 = indp + T(1.5) * uy * uy;
+    f[2] = omegabar * f[2] + omega_ws * rho * (vel_trm_24 + uy);
+    f[4] = omegabar * f[4] + omega_ws * rho * (vel_trm_24 - uy);
+    T velxpy = ux + uy;
+    T vel_trm_57 = indp + T(1.5) * velxpy * velxpy;
+    f[5] = omegabar * f[5] + omega_wd * rho * (vel_trm_57 + velxpy);
+    f[7] = omegabar * f[7] + omega_wd * rho * (vel_trm_57 - velxpy);
+    T velxmy = ux - uy;
+    T vel_trm_68 = indp + T(1.5) * velxmy * velxmy;
+    f[6] = omegabar * f[6] + omega_wd * rho * (vel_trm_68 - velxmy);
+    f[8] = omegabar * f[8] + omega_wd * rho * (vel_trm_68 + velxmy);
+}
+
+// DUGKS face relaxation: moments of all nine face values, relax only the flux carriers.
+// EW = true: update_ew (1,3,5,7,6,8); EW = false: update_ns (2,4,5,7,6,8).
+template <typename T, bool EW> __device__ __forceinline__ void face_relax(T (&f)[9], T omega)
+{
+    const T ws = K<T>::ws(), wd = K<T>::wd();
+    T omegabar = T(1) - omega;
+    T omega_ws = T(3) * omega * ws;
+    T omega_wd = T(3) * omega * wd;
+    T rho, ux, uy;
+    moments(f, rho, ux, uy);
+    T indp = K<T>::one_third() - T(0.5) * (ux * ux + uy * uy);
+    if (EW) {
+        T vel_trm_13 = indp + T(1.5) * ux * ux;
+        f[1] = omegabar * f[1] + omega_ws * rho * (vel_trm_13 + ux);
+        f[3] = omegabar * f[3] + omega_ws * rho * (vel_trm_13 - ux);
+    } else {
+        T vel_trm_24 = indp + T(1.5) * uy * uy;
+        f[2] = omegabar * f[2] + omega_ws * rho * (vel_trm_24 + uy);
+        f[4] = omegabar * f[4] + omega_ws * rho * (vel_trm_24 - uy);
+    }
+    T velxpy = ux + uy;
+    T vel_trm_57 = indp + T(1.5) * velxpy * velxpy;
+    f[5] = omegabar * f[5] + omega_wd * rho * (vel_trm_57 + velxpy);
+    f[7] = omegabar * f[7] + omega_wd * rho * (vel_trm_57 - velxpy);
+    T velxmy = ux - uy;
+    T vel_trm_68 = indp + T(1.5) * velxmy * velxmy;
+    f[6] = omegabar * f[6] + omega_wd * rho * (vel_trm_68 - velxmy);
+    f[8] = omegabar * f[8] + omega_wd * rho * (vel_trm_68 + velxmy);
+}
+
+// Two-relaxation-time, incompressible equilibrium (velocity = momentum).
+template <typename T> __device__ __forceinline__ void collide_trt(T (&f)[9], T lambda_e, T lambda_d)
+{
+    const T t0 = T(4) / T(9);
+    const T t1x2 = (T(1) / T(9)) * T(2);
+    const T t2x2 = (T(1) / T(36)) * T(2);
+    const T inv2csq2 = T(1) / (T(2) * (T(1) / T(3)) * (T(1) / T(3)));
+    const T fac1 = t1x2 * inv2csq2;
+    const T fac2 = t2x2 * inv2csq2;
+
+    T lambda_e_scaled = T(0.5) * lambda_e;
+    T lambda_d_scaled = T(0.5) * lambda_d;
+
+    T vC = f[0], vE = f[1], vN = f[2], vW = f[3], vS = f[4];
+    T vNE = f[5], vNW = f[6], vSW = f[7], vSE = f[8];
+
+    T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
+    T velX = (((vNE - vSW) + (vSE - vNW)) + (vE - vW));
+    T velY = (((vNE - vSW) + (vNW - vSE)) + (vN - vS));
+    T velX2 = velX * velX;
+    T velY2 = velY * velY;
+    T feq_common = rho - T(1.5) * (velX2 + velY2);
+
+    f[0] = vC * (T(1) - lambda_e) + lambda_e * t0 * feq_common;
+
+    T velXPY = velX + velY;
+    T sym_NE_SW = lambda_e_scaled * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common);
+    T asym_NE_SW = lambda_d_scaled * (vNE - vSW - T(3) * t2x2 * velXPY);
+    f[5] = vNE - sym_NE_SW - asym_NE_SW;
+    f[7] = vSW - sym_NE_SW + asym_NE_SW;
+
+    T velXMY = velX - velY;
+    T sym_SE_NW = lambda_e_scaled * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common);
+    T asym_SE_NW = lambda_d_scaled * (vSE - vNW - T(3) * t2x2 * velXMY);
+    f[8] = vSE - sym_SE_NW - asym_SE_NW;
+    f[6] = vNW - sym_SE_NW + asym_SE_NW;
+
+    T sym_N_S = lambda_e_scaled * (vN + vS - fac1 * velY2 - t1x2 * feq_common);
+    T asym_N_S = lambda_d_scaled * (vN - vS - T(3) * t1x2 * velY);
+    f[2] = vN - sym_N_S - asym_N_S;
+    f[4] = vS - sym_N_S + asym_N_S;
+
+    T sym_E_W = lambda_e_scaled * (vE + vW - fac1 * velX2 - t1x2 * feq_common);
+    T asym_E_W = lambda_d_scaled * (vE - vW - T(3) * t1x2 * velX);
+    f[1] = vE - sym_E_W - asym_E_W;
+    f[3] = vW - sym_E_W + asym_E_W;
+}
+
+// Recursive-regularized collision with 3rd/4th-order Hermite equilibrium.
+template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T omega)
+{
+    const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd(), csqr = K<T>::csqr();
+    T omega_w0 = w0 * (T(1) - omega);
+    T omega_ws = ws * (T(1) - omega);
+    T omega_wd = wd * (T(1) - omega);
+
+    T vC = f[0], vE = f[1], vN = f[2], vW = f[3], vS = f[4];
+    T vNE = f[5], vNW = f[6], vSW = f[7], vSE = f[8];
+    T feq[9];
+
+    T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
+    T invrho = T(1) / rho;
+    T ux = invrho * (((vNE - vSW) + (vSE - vNW)) + (vE - vW));
+    T uy = invrho * (((vNE - vSW) + (vNW - vSE)) + (vN - vS));
+
+    T uxx = ux * ux;
+    T uyy = uy * uy;
+    T uxxy = uxx * uy;
+    T uyyx = uyy * ux;
+    T uxxyy = uxx * uyy;
+
+    T indp0 = T(1) - T(1.5) * (uxx + uyy);
+    T indps = indp0 - T(4.5) * uxxyy;
+    T indpd = indp0 + T(9) * uxxyy;
+    indp0 = indp0 + T(2.25) * uxxyy;
+
+    feq[0] = w0 * rho * indp0;
+    feq[1] = ws * rho * (indps + T(3) * ux + T(4.5) * (uxx - uyyx));
+    feq[3] = ws * rho * (indps - T(3) * ux + T(4.5) * (uxx + uyyx));
+    feq[2] = ws * rho * (indps + T(3) * uy + T(4.5) * (uyy - uxxy));
+    feq[4] = ws * rho * (indps - T(3) * uy + T(4.5) * (uyy + uxxy));
+
+    vC = vC - feq[0];
+    vE = vE - feq[1];
+    vN = vN - feq[2];
+    vW = vW - feq[3];
+    vS = vS - feq[4];
+
+    T axx = csqr * (T(2) * (vE + vW) - (vN + vS) - vC);
+    T ayy = csqr * (T(2) * (vN + vS) - (vE + vW) - vC);
+
+    T u3p = uxxy + uyyx;
+    T uxpy = ux + uy;
+    T indp57 = indpd + T(4.5) * uxpy * uxpy;
+    feq[5] = wd * rho * (indp57 + T(3) * uxpy + T(9) * u3p);
+    feq[7] = wd * rho * (indp57 - T(3) * uxpy - T(9) * u3p);
+
+    T u3m = uxxy - uyyx;
+    T uxmy = ux - uy;
+    T indp68 = indpd + T(4.5) * uxmy * uxmy;
+    feq[6] = wd * rho * (indp68 - T(3) * uxmy + T(9) * u3m);
+    feq[8] = wd * rho * (indp68 + T(3) * uxmy - T(9) * u3m);
+
+    vNE = vNE - feq[5];
+    vNW = vNW - feq[6];
+    vSW = vSW - feq[7];
+    vSE = vSE - feq[8];
+
+    T tmp = T(2) * csqr * (vNE + vNW + vSW + vSE);
+    axx = axx + tmp;
+    ayy = ayy + tmp;
+    T axy = ((vNE + vSW) - (vNW + vSE));
+
+    T axxy = T(2) * ux * axy + uy * axx;
+    T ayyx = T(2) * uy * axy + ux * ayy;
+    T axxyy = T(2) * (ux * ayyx + uy * axxy) - uxx * ayy - uyy * axx - T(4) * ux * uy * axy;
+
+    indp0 = -T(1.5) * (axx + ayy);
+    indps = indp0 - T(4.5) * axxyy;
+    indpd = T(9) * axxyy - T(2) * indp0;
+    indp0 = indp0 + T(2.25) * axxyy;
+
+    vC = indp0;
+    vE = indps + T(4.5) * (axx - ayyx);
+    vW = indps + T(4.5) * (axx + ayyx);
+    vN = indps + T(4.5) * (ayy - axxy);
+    vS = indps + T(4.5) * (ayy + axxy);
+    vNE = indpd + T(9) * (axxy + ayyx + axy);
+    vSW = indpd - T(9) * (axxy + ayyx - axy);
+    vNW = indpd + T(9) * (axxy - ayyx - axy);
+    vSE = indpd - T(9) * (axxy - ayyx + axy);
+
+    f[0] = feq[0] + omega_w0 * vC;
+    f[1] = feq[1] + omega_ws * vE;
+    f[2] = feq[2] + omega_ws * vN;
+    f[3] = feq[3] + omega_ws * vW;
+    f[4] = feq[4] + omega_ws * vS;
+    f[5] = feq[5] + omega_wd * vNE;
+    f[6] = feq[6] + omega_wd * vNW;
+    f[7] = feq[7] + omega_wd * vSW;
+    f[8] = feq[8] + omega_wd * vSE;
+}
+
+template <typename T, int MODEL> __device__ __forceinline__ void collide(T (&f)[9], const CollideParams<T>& p)
+{
+    if (MODEL == M_BGK) collide_bgk(f, p.omega);
+    else if (MODEL == M_TRT) collide_trt(f, p.omega, p.lambda_d);
+    else if (MODEL == M_RR) collide_rr(f, p.omega);
+    else if (MODEL == M_BGK_SPLIT) collide_bgk_split(f, p.omega);
+}
+
+// 2nd-order, half-step back-traced face reconstruction of one population from its 3x3
+// neighbourhood: src/fvm_bardow.F90:449-473 == src/periodic_dugks.F90:238-263.
+template <typename T>
+__device__ __forceinline__ void faces(T fc, T fe, T fn, T fw, T fs, T fne, T fnw, T fsw, T fse, T cxq, T cyq,
+                                      T& cfw, T& cfn, T& cfe, T& cfs)
+{
+    const T p2 = T(0.5), p8 = T(0.125);
+    cfw = p2 * (fc + fw) - p2 * cxq * (fc - fw) - p8 * cyq * (fnw + fn - fsw - fs);
+    cfn = p2 * (fc + fn) - p2 * cyq * (fn - fc) - p8 * cxq * (fne + fe - fnw - fw);
+    cfe = p2 * (fc + fe) - p2 * cxq * (fe - fc) - p8 * cyq * (fne + fn - fse - fs);
+    cfs = p2 * (fc + fs) - p2 * cyq * (fc - fs) - p8 * cxq * (fse + fe - fsw - fw);
+}
+
+}  // namespace plbm

@@ -1,0 +1,211 @@
+// plbm_plugin.cu -- the reference's C plugin seam (sim/lbm.h:13-19) implemented on the GPU.
+//
+// Exports c_plbm_{init,step,vars,free,norm} with the exact signatures of the reference's
+// `slbm` plugin (sim/sim_slbm.F90:135-205), so the reference's loader
+// `SimPlugin("./libplbm_b200.so")` (sim/cases.py:13-66, name = "plbm") works unmodified, plus
+// c_plbm_step_n to batch steps without one ctypes round trip per step.
+//
+// Semantics follow sim/sim.F90: populations are stored DDF-shifted (f - w), arrays are
+// x-fastest (nx,ny), the `rho` argument of init carries PRESSURE (rho = rho0 + p/cs^2,
+// sim/sim.F90:181-199), one step is collide -> push-stream -> periodic fold
+// (sim/sim_slbm.F90:80-110; sim/sim.F90:404-505, 568-624).  On the device the halo ring of the
+// reference is replaced by periodic index arithmetic in the scatter; results are identical.
+#include <cmath>
+#include <cstdio>
+
+#include "plbm_internal.h"
+
+namespace plbm {
+namespace {
+
+struct SimState {
+    int nx, ny;
+    double *f1, *f2;   // [9][ny][nx], DDF-shifted
+    double *rho, *u;   // device staging for vars(): rho[ny][nx], u[2][ny][nx]
+    cudaStream_t stream;
+};
+
+__device__ __forceinline__ void sim_equilibrium(double rho, double ux, double uy, double (&feq)[9])
+{
+    const double w0 = 4.0 / 9.0, ws = 1.0 / 9.0, wd = 1.0 / 36.0, rho0 = 1.0;
+    const double w[9] = {w0, ws, ws, ws, ws, wd, wd, wd, wd};
+    double uxx = ux * ux, uyy = uy * uy;
+    double uxpy = ux + uy, uxmy = ux - uy;
+    double indp = -1.5 * (uxx + uyy);
+    feq[0] = w0 * rho * (indp);
+    feq[1] = ws * rho * (indp + 3.0 * ux + 4.5 * uxx);
+    feq[2] = ws * rho * (indp + 3.0 * uy + 4.5 * uyy);
+    feq[3] = ws * rho * (indp - 3.0 * ux + 4.5 * uxx);
+    feq[4] = ws * rho * (indp - 3.0 * uy + 4.5 * uyy);
+    feq[5] = wd * rho * (indp + 3.0 * uxpy + 4.5 * uxpy * uxpy);
+    feq[7] = wd * rho * (indp - 3.0 * uxpy + 4.5 * uxpy * uxpy);
+    feq[6] = wd * rho * (indp - 3.0 * uxmy + 4.5 * uxmy * uxmy);
+    feq[8] = wd * rho * (indp + 3.0 * uxmy + 4.5 * uxmy * uxmy);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) feq[k] = feq[k] + w[k] * (rho - rho0);
+}
+
+// lbm_eqinit, sim/sim.F90:181-199
+__global__ void k_sim_init(const double* __restrict__ p, const double* __restrict__ u, double* __restrict__ f, int nx, int ny)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const double csqr = 1.0 / 3.0, rho0 = 1.0;
+    double rho = rho0 + p[m] / csqr;
+    double feq[9];
+    sim_equilibrium(rho, u[m], u[n + m], feq);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k * n + m] = feq[k];
+}
+
+// lbm_collide_and_stream_fused (push) + lbm_periodic_bc_push, sim/sim.F90:404-505, 568-624
+__global__ void __launch_bounds__(256) k_sim_step(const double* __restrict__ fsrc, double* __restrict__ fdst, int nx, int ny,
+                                                  double omega)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int j = (int)(m / nx), i = (int)(m - (size_t)j * nx);
+    const double rho0 = 1.0;
+    double f[9], feq[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = fsrc[k * n + m];
+    double rho = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
+    rho = rho + rho0;
+    double ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) / rho;
+    double uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / rho;
+    sim_equilibrium(rho, ux, uy, feq);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        int id = i + cxi(k), jd = j + cyi(k);
+        id = id < 0 ? nx - 1 : (id >= nx ? 0 : id);
+        jd = jd < 0 ? ny - 1 : (jd >= ny ? 0 : jd);
+        fdst[k * n + (size_t)jd * nx + id] = omega * (feq[k] - f[k]) + f[k];
+    }
+}
+
+// lbm_macros, sim/sim.F90:148-179
+__global__ void k_sim_macros(const double* __restrict__ fsrc, double* __restrict__ rho, double* __restrict__ u, int nx, int ny)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    double f[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = fsrc[k * n + m];
+    double r = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
+    r = r + 1.0;
+    rho[m] = r;
+    u[m] = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) / r;
+    u[n + m] = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / r;
+}
+
+void sim_destroy(SimState* s)
+{
+    if (!s) return;
+    if (s->f1) cudaFree(s->f1);
+    if (s->f2) cudaFree(s->f2);
+    if (s->rho) cudaFree(s->rho);
+    if (s->u) cudaFree(s->u);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+}  // namespace
+}  // namespace plbm
+
+using namespace plbm;
+
+extern "C" {
+
+// void *siminit(int nx, int ny, double dt, double *rho, double *u, double *sigma, void *params)
+// Returns NULL on failure (the reference `error stop`s); see plbm_last_error().
+void* c_plbm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    (void)params;
+    if (nx < 1 || ny < 1 || !rho || !u) {
+        set_error("c_plbm_init: bad argument");
+        return nullptr;
+    }
+    if (dt != 1.0) {  // sim/sim_slbm.F90:48-51
+        set_error("Standard LBM only supports dt = 1.0!");
+        return nullptr;
+    }
+    if (sigma) {  // sim/sim_slbm.F90:65-70
+        set_error("c_plbm_init: non-equilibrium initialisation is not implemented (NotImplementedError in the reference)");
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libplbm_b200 has no CPU fallback");
+        return nullptr;
+    }
+    SimState* s = new SimState{nx, ny, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const size_t n = (size_t)nx * ny;
+    bool ok = cudaMalloc(&s->f1, 9 * n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->f2, 9 * n * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&s->rho, n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->u, 2 * n * sizeof(double)) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(s->rho, rho, n * sizeof(double), cudaMemcpyHostToDevice, s->stream) == cudaSuccess &&
+         cudaMemcpyAsync(s->u, u, 2 * n * sizeof(double), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    if (ok) {
+        k_sim_init<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->rho, s->u, s->f1, nx, ny);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        ok = cudaStreamSynchronize(s->stream) == cudaSuccess;
+    }
+    if (!ok) {
+        cuda_fail(cudaGetLastError(), "c_plbm_init");
+        sim_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+void c_plbm_step_n(void* sim, double omega, int n)
+{
+    SimState* s = static_cast<SimState*>(sim);
+    if (!s) return;
+    const size_t nn = (size_t)s->nx * s->ny;
+    for (int it = 0; it < n; ++it) {
+        k_sim_step<<<(unsigned)((nn + 255) / 256), 256, 0, s->stream>>>(s->f1, s->f2, s->nx, s->ny, omega);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        double* t = s->f1;
+        s->f1 = s->f2;
+        s->f2 = t;
+    }
+}
+
+// void simstep(void *sim, double omega)
+void c_plbm_step(void* sim, double omega) { c_plbm_step_n(sim, omega, 1); }
+
+// void simvars(void *sim, double *rho, double *u)
+void c_plbm_vars(void* sim, double* rho, double* u)
+{
+    SimState* s = static_cast<SimState*>(sim);
+    if (!s || !rho || !u) return;
+    const size_t n = (size_t)s->nx * s->ny;
+    k_sim_macros<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->f1, s->rho, s->u, s->nx, s->ny);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaMemcpyAsync(rho, s->rho, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(u, s->u, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) cuda_fail(cudaGetLastError(), "c_plbm_vars");
+}
+
+// void simfree(void *sim)
+void c_plbm_free(void* sim) { sim_destroy(static_cast<SimState*>(sim)); }
+
+// c_slbm_norm (sim/sim_slbm.F90:198-205): norm2(u - ua) / norm2(ua) over nx*ny host values.
+// Host arrays in, scalar out: evaluated on the host like the reference does.
+double c_plbm_norm(int nx, int ny, const double* u, const double* ua)
+{
+    const size_t n = (size_t)nx * ny;
+    double a = 0.0, b = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        a += (u[i] - ua[i]) * (u[i] - ua[i]);
+        b += ua[i] * ua[i];
+    }
+    return std::sqrt(a) / std::sqrt(b);
+}
+
+}  // extern "C"

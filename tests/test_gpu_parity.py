@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA library (through its C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: fp64 AND fp32 results are BIT-IDENTICAL to the oracle (the library is compiled with
+-fmad=false and evaluates every node in the reference's operation order), which is stronger than
+the north-star tolerance (1e-12 relative fp64, 1e-5 fp32).
+"""
+import numpy as np
+import pytest
+
+from conftest import random_state
+from oracle.oracle import Oracle, OracleGrid, padded_ld, taylor_green_setup
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 64), (67, 53), (16, 130), (5, 3), (128, 256), (2, 2)]
+PRECS = ["f64", "f32"]
+
+
+def make_pair(plbm, nx, ny, prec, nu=0.02, dt=1.0, magic=0.25, seed=None):
+    """Oracle grid + device grid holding the same random lattice in `iold`."""
+    og = OracleGrid(nx, ny, prec)
+    og.set_properties(nu, dt, magic)
+    f0 = random_state(og.o, nx, ny) if seed is None else random_state(og.o, nx, ny, seed=seed)
+    og.lattice(og.iold)[...] = f0
+    og.lattice(og.inew)[...] = 0
+    g = plbm.alloc_grid(nx, ny, precision=prec)
+    plbm.set_properties(g, nu, dt, magic)
+    g.upload_f(g.iold, np.nan_to_num(f0, nan=0.0))
+    g.upload_f(g.inew, np.zeros_like(f0))
+    return og, g
+
+
+def assert_same_lattice(g, og, which_g, which_o, ny):
+    got = g.download_f(which_g)[:, :, :ny]
+    want = og.lattice(which_o)[:, :, :ny]
+    assert np.array_equal(got, want), f"max abs diff {np.abs(got - want).max():.3e}"
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_properties_match_oracle(plbm, prec):
+    o = Oracle(prec)
+    for nu, dt, magic in [(0.02, 1.0, 0.25), (0.0036950, 0.05542, None), (1.8919, 1.0, 0.25)]:
+        want = o.set_properties(nu, dt, magic)
+        g = plbm.alloc_grid(8, 8, precision=prec)
+        plbm.set_properties(g, nu, dt, magic)
+        assert g.tau == want["tau"] and g.omega == want["omega"] and g.trt_magic == want["trt_magic"] and g.csqr == want["csqr"]
+        plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_set_pdf_to_equilibrium_and_macros(plbm, nx, ny, prec):
+    o = Oracle(prec)
+    rng = np.random.default_rng(7)
+    rho = (0.9 + 0.2 * rng.random((nx, ny))).astype(o.dtype)
+    ux = (0.1 * (rng.random((nx, ny)) - 0.5)).astype(o.dtype)
+    uy = (0.1 * (rng.random((nx, ny)) - 0.5)).astype(o.dtype)
+    f = o.alloc_f(nx, ny)
+    o.set_pdf_to_equilibrium(rho, ux, uy, f)
+    g = plbm.alloc_grid(nx, ny, precision=prec)
+    g.rho[:], g.ux[:], g.uy[:] = rho, ux, uy
+    plbm.set_pdf_to_equilibrium(g)
+    assert np.array_equal(g.download_f(g.iold)[:, :, :ny], f[:, :, :ny])
+    plbm.update_macros(g, lagged=False)
+    r2, u2, v2 = o.update_macros(f, ny)
+    assert np.array_equal(g.rho, r2) and np.array_equal(g.ux, u2) and np.array_equal(g.uy, v2)
+    plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_unfused_stream_then_collide_entries(plbm, nx, ny, prec):
+    """lbm_stream, collide_bgk/trt/rr as separate calls + swap == oracle, bitwise."""
+    for coll, ocoll in ((plbm.collide_bgk, Oracle.BGK), (plbm.collide_trt, Oracle.TRT), (plbm.collide_rr, Oracle.RR),
+                        (plbm.collide_bgk_split, Oracle.BGK_SPLIT)):
+        og, g = make_pair(plbm, nx, ny, prec)
+        plbm.lbm_stream(g)
+        og.o.lbm_stream(og.lattice(og.iold), og.lattice(og.inew), ny)
+        assert_same_lattice(g, og, g.inew, og.inew, ny)
+        coll(g)
+        p = og.props
+        if ocoll == Oracle.BGK:
+            og.o.collide_bgk(og.lattice(og.inew), ny, p["omega"])
+        elif ocoll == Oracle.TRT:
+            og.o.collide_trt(og.lattice(og.inew), ny, p["omega"], p["trt_magic"])
+        elif ocoll == Oracle.RR:
+            og.o.collide_rr(og.lattice(og.inew), ny, p["omega"])
+        else:
+            og.o.kernel_bgk(og.lattice(og.inew), ny, p["omega"])
+        assert_same_lattice(g, og, g.inew, og.inew, ny)
+        plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_fused_lbm_steps(plbm, nx, ny, prec, variant):
+    """perform_lbm_step (fused kernel), 7 steps, every collision model, every load variant."""
+    for coll, ocoll in ((plbm.collide_bgk, Oracle.BGK), (plbm.collide_trt, Oracle.TRT), (plbm.collide_rr, Oracle.RR),
+                        (plbm.collide_bgk_split, Oracle.BGK_SPLIT)):
+        og, g = make_pair(plbm, nx, ny, prec)
+        g.set_variant(variant)
+        g.collision, g.streaming = coll, plbm.lbm_stream
+        plbm.perform_lbm_step(g, 7)
+        og.run(Oracle.SCHEME_LBM, ocoll, 7)
+        assert (g.iold, g.inew) == (og.iold, og.inew)
+        assert_same_lattice(g, og, g.iold, og.iold, ny)
+        assert_same_lattice(g, og, g.inew, og.inew, ny)  # the lagged lattice too
+        plbm.update_macros(g)  # lagged, like the reference
+        r, u, v = og.update_macros(lagged=True)
+        assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v)
+        plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", [(64, 64), (67, 67), (5, 5), (130, 130)])
+def test_fvm_bardow_steps(plbm, nx, ny, prec):
+    """perform_step with stream_fvm_bardow + collide_bgk (what app/main_vortex.f90 runs)."""
+    og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+    g.collision, g.streaming = plbm.collide_bgk, plbm.stream_fvm_bardow
+    plbm.perform_step(g, 5)
+    og.run(Oracle.SCHEME_FVM_BARDOW, Oracle.BGK, 5)
+    assert_same_lattice(g, og, g.iold, og.iold, ny)
+    # unfused entry point
+    plbm.stream_fvm_bardow(g)
+    og.o.stream_fvm_bardow(og.lattice(og.iold), og.lattice(og.inew), ny, og.props["dt"])
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("dugks", [True, False])
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", [(64, 64), (67, 53), (5, 3), (34, 130)])
+def test_dugks_steps(plbm, nx, ny, prec, variant, dugks):
+    """perform_dugks_step: fused kernel (variant 0) and reference-structured two-pass (variant 1)."""
+    og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+    g.set_variant(variant)
+    g.dugks = dugks
+    plbm.perform_dugks_step(g, 5)
+    og.run(Oracle.SCHEME_DUGKS if dugks else Oracle.SCHEME_DUGKS_OFF, Oracle.BGK, 5)
+    assert (g.iold, g.inew) == (og.iold, og.inew)
+    assert_same_lattice(g, og, g.iold, og.iold, ny)
+    # lattice inew must hold fbar^+ of the last step, exactly what the reference leaves there
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    plbm.update_macros(g)
+    r, u, v = og.update_macros(lagged=True)
+    assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v)
+    # stepping on after the lazy materialisation must still agree
+    plbm.perform_dugks_step(g, 2)
+    og.run(Oracle.SCHEME_DUGKS if dugks else Oracle.SCHEME_DUGKS_OFF, Oracle.BGK, 2)
+    assert_same_lattice(g, og, g.iold, og.iold, ny)
+    plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_dugks_unfused_entries(plbm, prec):
+    nx, ny = 40, 48
+    og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+    p = og.props
+    plbm.dugks_collide(g)
+    og.o.dugks_collide(og.lattice(og.iold), og.lattice(og.inew), ny, p["omega"], p["tau"], p["dt"], True)
+    assert_same_lattice(g, og, g.iold, og.iold, ny)
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    plbm.dugks_stream(g)
+    og.o.dugks_stream(og.lattice(og.iold), og.lattice(og.inew), ny, p["tau"], p["dt"], True)
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("nx,ny", [(64, 64), (67, 53), (5, 3)])
+def test_vorticity(plbm, nx, ny, prec, order):
+    o = Oracle(prec)
+    rng = np.random.default_rng(3)
+    ux = rng.standard_normal((nx, ny)).astype(o.dtype)
+    uy = rng.standard_normal((nx, ny)).astype(o.dtype)
+    want = o.vorticity(ux, uy, order)
+    got = (plbm.vorticity_2nd if order == 2 else plbm.vorticity_4th)(ux, uy)
+    assert np.array_equal(got, want)
+
+
+def test_diagnostics_reductions(plbm):
+    n = 96
+    og = OracleGrid(n, n)
+    o = og.o
+    s = taylor_green_setup(o, n, dt=1.0)
+    p, ux, uy = o.taylor_green_eval(n, n, s["kx"], s["ky"], s["umax"], s["td"], 0.0)
+    g = plbm.alloc_grid(n, n)
+    plbm.set_properties(g, s["nu"], s["dt"], 0.25)
+    g.rho[:], g.ux[:], g.uy[:] = p * 3.0 + 1.0, ux, uy
+    plbm.set_pdf_to_equilibrium(g)
+    d = g.diagnostics()
+    sp = np.hypot(ux, uy)
+    # hypot differs by at most an ulp between libm and the CUDA math library
+    assert abs(d["max_speed"] - sp.max()) <= 4e-16 * sp.max() and abs(d["min_speed"] - sp.min()) <= 4e-16 * sp.max()
+    assert abs(d["sum_rho"] - g.rho.sum()) / g.rho.sum() < 1e-13
+    ke = 0.5 * (g.rho * (ux**2 + uy**2)).sum()
+    assert abs(d["kinetic_energy"] - ke) / ke < 1e-12
+    # analytic TG kinetic energy at t=0: 1/4 N umax^2 (rho ~ 1)
+    assert abs(d["kinetic_energy"] - 0.25 * n * n * float(s["umax"]) ** 2) / ke < 1e-3
+    _, uxa, uya = o.taylor_green_eval(n, n, s["kx"], s["ky"], s["umax"], s["td"], 100.0)
+    want = float(o.l2_norm(ux, uy, uxa, uya))
+    assert abs(g.l2_error(uxa, uya) - want) / want < 1e-12
+    plbm.dealloc_grid(g)
+
+
+def test_cases_match_oracle(plbm):
+    for prec, dt in (("f64", np.float64), ("f32", np.float32)):
+        o = Oracle(prec)
+        s = taylor_green_setup(o, 48, dt=1.0)
+        tp = plbm.taylor_green_params(48, dt=1.0, dtype=dt)
+        a = o.taylor_green_eval(48, 48, s["kx"], s["ky"], s["umax"], s["td"], dt(17.0))
+        b = tp["case"].eval(17.0)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        vp = plbm.vortex_params(40, dtype=dt)
+        c = vp["case"]
+        a = o.vortex_eval(40, 40, c.U0, c.xc, c.yc, c.Rc, c.eps)
+        b = c.eval(40, 40)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_sim_plugin_seam(plbm):
+    """c_plbm_{init,step,vars,free,norm} against the DDF-shifted oracle of sim/sim.F90."""
+    nx, ny, steps, omega = 48, 40, 25, 1.7
+    o = Oracle("f64")
+    rng = np.random.default_rng(11)
+    p = 1e-3 * rng.standard_normal((ny, nx))
+    u = 0.05 * rng.standard_normal((2, ny, nx))
+    f1 = np.zeros((9, ny + 2, nx + 2))
+    f2 = np.zeros_like(f1)
+    P = lambda a: a.ctypes.data  # noqa: E731
+    o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
+    f2[...] = f1
+    for _ in range(steps):
+        o._sim_step(nx, ny, P(f1), P(f2), omega)
+        o._sim_bc(nx, ny, P(f2))
+        f1, f2 = f2, f1
+    rho_w, u_w, v_w = np.zeros((ny, nx)), np.zeros((ny, nx)), np.zeros((ny, nx))
+    o._sim_macros(nx, ny, P(f1), P(rho_w), P(u_w), P(v_w))
+
+    sim = plbm.SimPlugin()
+    sim.init((nx, ny), 1.0, p, u)
+    for _ in range(5):
+        sim.step(omega)
+    sim.step(omega, n=steps - 5)
+    rho, uu = sim.vars()
+    assert np.array_equal(rho, rho_w) and np.array_equal(uu[0], u_w) and np.array_equal(uu[1], v_w)
+    assert abs(sim.norm(uu[0], u_w + 1e-3) - np.sqrt(((uu[0] - u_w - 1e-3) ** 2).sum() / ((u_w + 1e-3) ** 2).sum())) < 1e-12
+    sim.free()
+    with pytest.raises(plbm.PlbmError):
+        plbm.SimPlugin().init((nx, ny), 0.5, p, u)  # "Standard LBM only supports dt = 1.0!"
+
+
+def test_error_paths(plbm):
+    with pytest.raises(plbm.PlbmError):
+        plbm.alloc_grid(0, 8)
+    g = plbm.alloc_grid(8, 8)
+    g.collision, g.streaming = plbm.collide_bgk, plbm.lbm_stream
+    with pytest.raises(plbm.PlbmError):  # set_properties not called
+        plbm.perform_lbm_step(g, 1)
+    plbm.dealloc_grid(g)
