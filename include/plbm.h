@@ -137,7 +137,8 @@ int plbm_upload_f(plbm_handle grid, int which, const void* host_f);
 int plbm_download_f(plbm_handle grid, int which, void* host_f);
 
 /* ---- execution control ---------------------------------------------------------------- */
-/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = library stream */
+/* run on a caller-owned cudaStream_t (e.g. a torch stream); NULL = back to a library-owned
+ * stream.  To use the legacy default stream pass cudaStreamLegacy ((void*)1), not 0. */
 int plbm_set_stream(plbm_handle grid, void* cuda_stream);
 int plbm_synchronize(plbm_handle grid);
 /* kernels launched by this process through the library since load (for bench accounting) */
@@ -151,6 +152,9 @@ int plbm_set_variant(plbm_handle grid, int variant);
 double plbm_case_tg_decay_time(int precision, double kx, double ky, double nu);
 int plbm_case_taylor_green(int precision, int nx, int ny, double kx, double ky, double umax, double td,
                            double t, void* p, void* ux, void* uy);
+/* same, for the nx lines of a slab whose first line is global line x0 (multi-GPU ICs) */
+int plbm_case_taylor_green_slab(int precision, int nx, int x0, int ny, double kx, double ky, double umax,
+                                double td, double t, void* p, void* ux, void* uy);
 /* vortex_case_t%eval (src/benchmarks/barotropic_vortex_case.F90:34-83) */
 int plbm_case_vortex(int precision, int nx, int ny, double U0, double xc, double yc, double Rc, double eps,
                      double rho0, double csqr, void* rho, void* ux, void* uy);

@@ -1,0 +1,34 @@
+/*
+ * plbm_sim_plugin.h -- the reference's C plugin seam (sim/lbm.h:13-19) as exported by
+ * libplbm_b200.so.  The reference loader (sim/cases.py:13-66) derives the symbol prefix from
+ * the library file name, lib<name>.so -> c_<name>_{init,step,vars,free,norm}; with <name> =
+ * "plbm" these are the concrete prototypes of the reference's `slbm` plugin
+ * (sim/sim_slbm.F90:135-205).  Arrays are Fortran-contiguous rho(nx,ny), u(nx,ny,2) (x
+ * fastest); `rho` carries PRESSURE on input (rho = 1 + p/cs^2, sim/sim.F90:181-199); dt must
+ * be 1 (sim/sim_slbm.F90:48-51).  c_plbm_init returns NULL on failure instead of `error stop`
+ * (message via plbm_last_error()).
+ */
+#ifndef PLBM_SIM_PLUGIN_H
+#define PLBM_SIM_PLUGIN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* void *siminit(int nx, int ny, double dt, double *rho, double *u, double *sigma, void *params) */
+void* c_plbm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params);
+/* void simstep(void *sim, double omega): collide -> push-stream -> periodic fold, once */
+void c_plbm_step(void* sim, double omega);
+/* extension: n steps per call (the reference pays one ctypes round trip per step) */
+void c_plbm_step_n(void* sim, double omega, int n);
+/* void simvars(void *sim, double *rho, double *u) */
+void c_plbm_vars(void* sim, double* rho, double* u);
+/* void simfree(void *sim) */
+void c_plbm_free(void* sim);
+/* c_slbm_norm (sim/sim_slbm.F90:198-205): norm2(u - ua) / norm2(ua) over nx*ny host values */
+double c_plbm_norm(int nx, int ny, const double* u, const double* ua);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLBM_SIM_PLUGIN_H */

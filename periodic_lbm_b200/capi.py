@@ -58,6 +58,7 @@ SIGNATURES = {
     "plbm_comm_finalize": (_I, [_H]),
     "plbm_case_tg_decay_time": (_D, [_I, _D, _D, _D]),
     "plbm_case_taylor_green": (_I, [_I, _I, _I, _D, _D, _D, _D, _D, _P, _P, _P]),
+    "plbm_case_taylor_green_slab": (_I, [_I, _I, _I, _I, _D, _D, _D, _D, _D, _P, _P, _P]),
     "plbm_case_vortex": (_I, [_I, _I, _I, _D, _D, _D, _D, _D, _D, _D, _P, _P, _P]),
     # sim/lbm.h plugin seam
     "c_plbm_init": (_P, [_I, _I, _D, _P, _P, _P, _P]),

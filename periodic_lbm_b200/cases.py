@@ -42,11 +42,13 @@ class TaylorGreen:
     def decay_time(self):
         return self.td
 
-    def eval(self, t):
-        """-> p, ux, uy as (nx, ny) arrays (Fortran (ny,nx))."""
-        p, ux, uy = (np.empty((self.nx, self.ny), dtype=self.dtype) for _ in range(3))
-        check(lib.plbm_case_taylor_green(_prec(self.dtype), self.nx, self.ny, float(self.kx), float(self.ky),
-                                         float(self.umax), float(self.td), float(self.dtype(t)), _ptr(p), _ptr(ux), _ptr(uy)),
+    def eval(self, t, x_offset=0, nx_local=None, out=None):
+        """-> p, ux, uy as (nx, ny) arrays (Fortran (ny,nx)).  x_offset/nx_local select the lines of
+        one slab of the global grid; `out` may supply three preallocated (e.g. pinned) arrays."""
+        nxl = self.nx if nx_local is None else nx_local
+        p, ux, uy = out if out is not None else (np.empty((nxl, self.ny), dtype=self.dtype) for _ in range(3))
+        check(lib.plbm_case_taylor_green_slab(_prec(self.dtype), nxl, int(x_offset), self.ny, float(self.kx), float(self.ky),
+                                              float(self.umax), float(self.td), float(self.dtype(t)), _ptr(p), _ptr(ux), _ptr(uy)),
               "case_taylor_green")
         return p, ux, uy
 

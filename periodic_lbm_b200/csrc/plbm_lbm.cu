@@ -144,10 +144,12 @@ template <typename T, int MODEL, bool STREAM> static int launch_v(const LbmArgs<
 {
     constexpr int VMAX = 16 / (int)sizeof(T);  // 128-bit vectors: 2 x fp64, 4 x fp32
     const bool vec_ok = (a.ny % VMAX) == 0;
-    // variant 0 (default) = vector + shuffle; 1 = vector + element loads; 2 = scalar
+    // variant 0 (default) = 128-bit vectors, element loads for the six y-shifted populations
+    // (measured fastest on B200: ~1.05x the measured copy bandwidth, profiles/);
+    // variant 1 = 128-bit vectors + warp shuffle of the aligned vector; 2 = scalar (1 node/thread)
     if (!vec_ok || variant == 2) return launch_one<T, MODEL, STREAM, 1, 0>(a, s);
-    if (variant == 1) return launch_one<T, MODEL, STREAM, VMAX, 0>(a, s);
-    return launch_one<T, MODEL, STREAM, VMAX, 1>(a, s);
+    if (variant == 1) return launch_one<T, MODEL, STREAM, VMAX, 1>(a, s);
+    return launch_one<T, MODEL, STREAM, VMAX, 0>(a, s);
 }
 
 template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream_pdfs, int variant, cudaStream_t s)

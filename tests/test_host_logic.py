@@ -1,0 +1,130 @@
+"""Host-side logic that needs no GPU: slab partitioning, driver recipes, scalar helpers, and the
+multi-rank halo protocol (world_size 2 over gloo, oracle as the per-slab compute)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, OracleGrid, padded_ld, taylor_green_setup, taylor_green_steps_to_tmax
+
+
+def test_slab_partition_covers_grid():
+    from periodic_lbm_b200.slab import Q_FROM_HI, Q_FROM_LO, halo_message_bytes, slab_of
+    from periodic_lbm_b200.lattice import cx
+
+    for nxg, n in [(32768, 8), (100, 3), (17, 4), (16, 8)]:
+        slabs = [slab_of(r, n, nxg) for r in range(n)]
+        assert slabs[0].x_offset == 0 and slabs[-1].x_end == nxg
+        assert all(a.x_end == b.x_offset for a, b in zip(slabs, slabs[1:]))
+        assert max(s.nx_local for s in slabs) - min(s.nx_local for s in slabs) <= 1
+        assert all(s.lo == (s.rank - 1) % n and s.hi == (s.rank + 1) % n for s in slabs)
+    with pytest.raises(ValueError):
+        slab_of(0, 8, 15)
+    assert [q for q in range(9) if cx[q] == 1] == list(Q_FROM_LO)
+    assert [q for q in range(9) if cx[q] == -1] == sorted(Q_FROM_HI)
+    assert halo_message_bytes(32768, 8) == 786432
+
+
+def test_driver_recipe_matches_oracle_recipe():
+    import periodic_lbm_b200 as p
+
+    for dtype, prec in ((np.float64, "f64"), (np.float32, "f32")):
+        o = Oracle(prec)
+        s = taylor_green_setup(o, 64, dt_over_tau=5.0)
+        t = p.taylor_green_params(64, dt_over_tau=5.0, dtype=dtype)
+        for k in ("umax", "nu", "tau", "dt", "kx", "tmax"):
+            assert t[k] == s[k], k
+        assert t["nsteps"] == s["nsteps_cap"] and t["case"].td == s["td"]
+        assert p.steps_until(t["tmax"], t["dt"], t["nsteps"], dtype) == taylor_green_steps_to_tmax(o, s)
+    assert p.steps_until(np.float64(9731.422537830847), 1.0, 10704) == (9732, 9732.0)
+
+
+def test_trt_scalar_helpers():
+    import periodic_lbm_b200 as p
+
+    o = Oracle("f64")
+    for om, x in [(1.95, 0.25), (0.5, 3.0 / 16.0), (1.0, 1.0 / 12.0)]:
+        assert p.lambda_d(om, x) == o.lambda_d(om, x)
+        ld = p.lambda_d(om, x)
+        assert abs(p.magic_number(om, ld) - x) < 1e-15  # magic_number inverts lambda_d
+        assert p.magic_number(om, ld) == o.magic_number(om, ld)
+
+
+# ---------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
+    """One rank of the ring: owns a slab, exchanges the three-population halo lines with gloo, and
+    advances its slab with the ORACLE kernels on a halo-extended copy.  This exercises exactly the
+    protocol libplbm_b200's NCCL ring implements (which lines, which populations, which neighbour,
+    double buffering by step parity) without a GPU."""
+    import torch
+    import torch.distributed as dist
+
+    from periodic_lbm_b200.slab import Q_FROM_HI, Q_FROM_LO, slab_of
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = Oracle("f64")
+    sl = slab_of(rank, world, nxg)
+    ld = padded_ld(ny)
+    rng = np.random.default_rng(5)
+    fglob = np.zeros((9, nxg, ld))
+    fglob[:, :, :ny] = 0.1 + 0.01 * rng.random((9, nxg, ny))
+    f = fglob[:, sl.x_offset:sl.x_end].copy()
+    nxl = sl.nx_local
+    for _ in range(steps):
+        send_lo = torch.from_numpy(f[list(Q_FROM_HI), 0].copy())    # my first line of q=3,6,7 -> rank lo (its halo_hi)
+        send_hi = torch.from_numpy(f[list(Q_FROM_LO), -1].copy())   # my last line of q=1,5,8  -> rank hi (its halo_lo)
+        halo_lo, halo_hi = torch.empty_like(send_hi), torch.empty_like(send_lo)
+        ops = [dist.P2POp(dist.isend, send_lo, sl.lo), dist.P2POp(dist.isend, send_hi, sl.hi),
+               dist.P2POp(dist.irecv, halo_hi, sl.hi), dist.P2POp(dist.irecv, halo_lo, sl.lo)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        ext = np.zeros((9, nxl + 2, ld))
+        ext[:, 1:-1] = f
+        ext[list(Q_FROM_LO), 0] = halo_lo.numpy()
+        ext[list(Q_FROM_HI), -1] = halo_hi.numpy()
+        dst = np.zeros_like(ext)
+        o.lbm_stream(ext, dst, ny)  # periodic wrap of the extended slab only pollutes the two halo lines
+        fn = np.ascontiguousarray(dst[:, 1:-1])
+        {0: lambda: o.collide_bgk(fn, ny, 1.7), 2: lambda: o.collide_rr(fn, ny, 1.7)}[coll]()
+        f = fn
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (sl.x_offset, f))
+    if rank == 0:
+        full = np.concatenate([g[1] for g in sorted(gathered, key=lambda t: t[0])], axis=1)
+        # single-domain oracle
+        a, b = fglob.copy(), np.zeros_like(fglob)
+        for _ in range(steps):
+            o.lbm_stream(a, b, ny)
+            {0: lambda: o.collide_bgk(b, ny, 1.7), 2: lambda: o.collide_rr(b, ny, 1.7)}[coll]()
+            a, b = b, a
+        out.put(bool(np.array_equal(full[:, :, :ny], a[:, :, :ny])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nxg,ny,coll", [(2, 12, 10, 0), (2, 9, 16, 2), (3, 11, 7, 0)])
+def test_slab_halo_protocol_world_size_n_gloo(world, nxg, ny, coll):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, nxg, ny, 6, coll, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    ok = q.get(timeout=120)
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert ok, "slab-decomposed run differs from the single-domain run"

@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import periodic_lbm_b200 as p  # noqa: E402
 
 PEAK = 6540.8
+STREAM = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean 'library-owned stream'
 try:
     PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
@@ -20,7 +21,7 @@ except Exception:
 
 def run(nx, ny, prec, scheme, coll, variant, steps, warmup=3, dugks=True):
     g = p.alloc_grid(nx, ny, precision=prec)
-    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    g.set_stream(STREAM.cuda_stream)
     tp = p.taylor_green_params(nx, dt=1.0, dtype=g.dtype)
     if scheme == "lbm":
         p.set_properties(g, tp["nu"], 1.0, 0.25)
@@ -46,9 +47,9 @@ def run(nx, ny, prec, scheme, coll, variant, steps, warmup=3, dugks=True):
     step(warmup)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(STREAM)
     step(steps)
-    e1.record()
+    e1.record(STREAM)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     mlups = nx * ny / ms * 1e-3
