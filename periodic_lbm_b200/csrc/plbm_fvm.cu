@@ -1,99 +1,245 @@
 // plbm_fvm.cu -- finite-volume streaming on the D2Q9 lattice: Bardow's scheme and DUGKS (sm_100a).
 //
-//   fvm_bardow_kernel            src/fvm_bardow.F90:410-507
-//   dugks_collide (+copy_field)  src/periodic_dugks.F90:46-77, 441-486
-//   kernel_bgk                   src/periodic_dugks.F90:80-169
+//   fvm_bardow_kernel             src/fvm_bardow.F90:410-507
+//   dugks_collide (+copy_field)   src/periodic_dugks.F90:46-77, 441-486
+//   kernel_bgk                    src/periodic_dugks.F90:80-169
 //   kernel_stream (+update_ew/ns) src/periodic_dugks.F90:190-438
 //
-// Every population reads its own 3x3 neighbourhood (9x reuse), so these kernels stage a
-// (TY+2) x (TX+2) tile of each population in shared memory with a one-cell periodic halo;
-// the fused DUGKS kernel additionally recomputes the half-step collision on the halo so a
-// whole step costs one read and one write of the state (144 B fp64 per node) instead of the
-// reference's three passes.
+// Every population reads its own 3x3 neighbourhood (9x reuse), so the step kernels stage a
+// (FY+2) x (FX+2) tile of all nine populations in shared memory with a one-cell periodic halo.
+// The fused DUGKS kernel additionally recomputes the half-step collision on the halo, so a whole
+// step costs one read and one write of the state (144 B fp64 per node) instead of the reference's
+// three passes (432 B by the author's own accounting, sim/standard_lbm.F90:331).
+//
+// Bit parity forbids sharing a face value between the two cells it separates: the reference
+// evaluates it twice with a different order of the two subtractions (cfe of x vs cfw of x+1),
+// so each node computes its own four faces exactly like the Fortran.  Terms multiplied by
+// cx = 0 or cy = 0 are exact zeros and are skipped (x - 0 == x).
 #include "plbm_internal.h"
 
 namespace plbm {
 
 __device__ __forceinline__ int wrap_p1(int i, int n) { return i + 1 == n ? 0 : i + 1; }
 __device__ __forceinline__ int wrap_m1(int i, int n) { return i == 0 ? n - 1 : i - 1; }
-__device__ __forceinline__ int pmod(int i, int n) { i %= n; return i < 0 ? i + n : i; }
-
-// ---------------------------------------------------------------------------------------
-// Tile geometry: TY rows (unit stride, threadIdx.x) x TX lines (threadIdx.y).
-constexpr int TY = 64;
-constexpr int TX = 4;
-constexpr int SY = TY + 2;  // tile + halo
-constexpr int SX = TX + 2;
-
-// Load the (SY x SX) halo tile of population q of `f` into sm[sx][sy]; periodic in x and y.
-// With a slab decomposition the x-neighbours beyond the slab are not available here: the
-// FVM/DUGKS kernels are single-GPU (nx == nx_global).
-template <typename T, typename F>
-__device__ __forceinline__ void for_tile(int x0, int y0, int nx, int ny, F&& fn)
+__device__ __forceinline__ int pmod(int i, int n)
 {
-    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < SX * SY; i += blockDim.x * blockDim.y) {
-        const int sx = i / SY, sy = i - sx * SY;
-        // tiles may overhang the grid when nx % TX or ny % TY != 0: wrap whatever is outside
-        const int x = pmod(x0 + sx - 1, nx), y = pmod(y0 + sy - 1, ny);
-        fn(sx, sy, x, y);
-    }
+    i %= n;
+    return i < 0 ? i + n : i;
 }
 
 // ---------------------------------------------------------------------------------------
-// stream_fvm_bardow fused with the collision that perform_step applies right after it.
-template <typename T, int MODEL>
-__global__ void __launch_bounds__(TY* TX) k_fvm_bardow(const T* __restrict__ fold, T* __restrict__ fnew, int nx, int ny,
-                                                        int ld, T dt, CollideParams<T> cp)
+// Tile geometry of the fused kernels: FY rows (unit stride, threadIdx.x) x FX lines (threadIdx.y).
+constexpr int FY = 32, FX = 8;
+constexpr int GY = FY + 2, GX = FX + 2;  // with halo: 34 x 10 = 340 nodes
+constexpr int PITCH = GY + 1;            // odd pitch: neighbouring lines fall in different banks
+constexpr int NHALO = GX * GY - FX * FY; // 84 ring nodes
+
+// West/East faces of population Q from the shared tile; c points at the centre node, neighbours
+// are at c[dx * PITCH + dy].  hx = p2*cxq, ey = p8*cyq (products formed left to right like the
+// Fortran `p2*cxq*(...)`).
+template <typename T, int Q> __device__ __forceinline__ void faces_ew(const T* c, T hx, T ey, T& cfw, T& cfe)
 {
-    __shared__ T sm[SX][SY + 1];
-    const int x0 = blockIdx.y * TX, y0 = blockIdx.x * TY;
+    constexpr int CX = cxi(Q), CY = cyi(Q);
+    const T p2 = T(0.5);
+    const T fc = c[0], fw = c[-PITCH], fe = c[PITCH];
+    cfw = p2 * (fc + fw);
+    cfe = p2 * (fc + fe);
+    if (CX != 0) {
+        cfw = cfw - hx * (fc - fw);
+        cfe = cfe - hx * (fe - fc);
+    }
+    if (CY != 0) {
+        const T fn = c[1], fs = c[-1];
+        const T fnw = c[-PITCH + 1], fsw = c[-PITCH - 1], fne = c[PITCH + 1], fse = c[PITCH - 1];
+        cfw = cfw - ey * (fnw + fn - fsw - fs);
+        cfe = cfe - ey * (fne + fn - fse - fs);
+    }
+}
+
+// North/South faces; hy = p2*cyq, ex = p8*cxq.
+template <typename T, int Q> __device__ __forceinline__ void faces_ns(const T* c, T hy, T ex, T& cfn, T& cfs)
+{
+    constexpr int CX = cxi(Q), CY = cyi(Q);
+    const T p2 = T(0.5);
+    const T fc = c[0], fn = c[1], fs = c[-1];
+    cfn = p2 * (fc + fn);
+    cfs = p2 * (fc + fs);
+    if (CY != 0) {
+        cfn = cfn - hy * (fn - fc);
+        cfs = cfs - hy * (fc - fs);
+    }
+    if (CX != 0) {
+        const T fe = c[PITCH], fw = c[-PITCH];
+        const T fne = c[PITCH + 1], fnw = c[-PITCH + 1], fse = c[PITCH - 1], fsw = c[-PITCH - 1];
+        cfn = cfn - ex * (fne + fe - fnw - fw);
+        cfs = cfs - ex * (fse + fe - fsw - fw);
+    }
+}
+
+template <typename T, bool DUGKS, int Q>
+__device__ __forceinline__ void ew_pop(const T* c0, T dt, T (&cfw)[9], T (&cfe)[9])
+{
+    const T cxq = dt * T(cxi(Q)), cyq = dt * T(cyi(Q));
+    faces_ew<T, Q>(c0 + Q * (GX * PITCH), T(0.5) * cxq, T(0.125) * cyq, cfw[Q], cfe[Q]);
+}
+template <typename T, bool DUGKS, int Q>
+__device__ __forceinline__ void ns_pop(const T* c0, T dt, T (&cfn)[9], T (&cfs)[9])
+{
+    const T cxq = dt * T(cxi(Q)), cyq = dt * T(cyi(Q));
+    faces_ns<T, Q>(c0 + Q * (GX * PITCH), T(0.5) * cyq, T(0.125) * cxq, cfn[Q], cfs[Q]);
+}
+
+// Flux update of one node from the shared tile of fbar (DUGKS) or f^n (Bardow):
+//   fp(q) = fp(q) - cxq*(cfe - cfw) - cyq*(cfn - cfs)        (src/periodic_dugks.F90:297)
+// evaluated as two passes (east/west, then north/south) so only two face sets are live.
+template <typename T, bool DUGKS> __device__ __forceinline__ void flux_update(const T* c0, T dt, T omega_face, T (&fp)[9])
+{
+    {
+        T cfw[9], cfe[9];
+        if (DUGKS) ew_pop<T, DUGKS, 0>(c0, dt, cfw, cfe);  // rest population: faces only feed the moments
+        ew_pop<T, DUGKS, 1>(c0, dt, cfw, cfe);
+        ew_pop<T, DUGKS, 3>(c0, dt, cfw, cfe);
+        ew_pop<T, DUGKS, 5>(c0, dt, cfw, cfe);
+        ew_pop<T, DUGKS, 6>(c0, dt, cfw, cfe);
+        ew_pop<T, DUGKS, 7>(c0, dt, cfw, cfe);
+        ew_pop<T, DUGKS, 8>(c0, dt, cfw, cfe);
+        if (DUGKS) {
+            ew_pop<T, DUGKS, 2>(c0, dt, cfw, cfe);
+            ew_pop<T, DUGKS, 4>(c0, dt, cfw, cfe);
+            face_relax<T, true>(cfw, omega_face);
+            face_relax<T, true>(cfe, omega_face);
+        }
+#pragma unroll
+        for (int q = 1; q < 9; ++q)
+            if (cxi(q) != 0) fp[q] = fp[q] - (dt * T(cxi(q))) * (cfe[q] - cfw[q]);
+    }
+    {
+        T cfn[9], cfs[9];
+        if (DUGKS) ns_pop<T, DUGKS, 0>(c0, dt, cfn, cfs);
+        ns_pop<T, DUGKS, 2>(c0, dt, cfn, cfs);
+        ns_pop<T, DUGKS, 4>(c0, dt, cfn, cfs);
+        ns_pop<T, DUGKS, 5>(c0, dt, cfn, cfs);
+        ns_pop<T, DUGKS, 6>(c0, dt, cfn, cfs);
+        ns_pop<T, DUGKS, 7>(c0, dt, cfn, cfs);
+        ns_pop<T, DUGKS, 8>(c0, dt, cfn, cfs);
+        if (DUGKS) {
+            ns_pop<T, DUGKS, 1>(c0, dt, cfn, cfs);
+            ns_pop<T, DUGKS, 3>(c0, dt, cfn, cfs);
+            face_relax<T, false>(cfn, omega_face);
+            face_relax<T, false>(cfs, omega_face);
+        }
+#pragma unroll
+        for (int q = 1; q < 9; ++q)
+            if (cyi(q) != 0) fp[q] = fp[q] - (dt * T(cyi(q))) * (cfn[q] - cfs[q]);
+    }
+}
+
+// MODE_DUGKS : fin = ftilde^n -> fout = ftilde^{n+1}   (perform_dugks_step, -DDUGKS or not)
+// MODE_BARDOW: fin = f^n      -> fout = collide(stream_fvm_bardow(f^n))   (perform_step)
+//   stage 1: every thread parks its own node in the shared tile (DUGKS: after the half-step
+//            collision fbar^+, keeping the full-step collision ftilde^+ in registers); the first
+//            84 threads also fill the periodic halo ring (DUGKS: recomputing fbar^+ there).
+//   stage 2: faces from the tile, face relaxation (DUGKS), flux update, collision (Bardow), store.
+// fbar^+ of the previous step (what the reference leaves in lattice `inew`, read by the lagged
+// update_macros) is not stored: it is recomputed on demand from fin, bit-identically.
+enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2 };
+
+template <typename T, int MODE, int MODEL>
+__global__ void __launch_bounds__(FY* FX, 2)
+    k_fv_fused(const T* __restrict__ fin, T* __restrict__ fout, int nx, int ny, int ld, T dt, T omega_full, T omega_half,
+               T omega_face, CollideParams<T> cp)
+{
+    extern __shared__ unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);  // sm[q][sx][sy], pitch PITCH
+    const int x0 = blockIdx.y * FX, y0 = blockIdx.x * FY;
     const int tx = threadIdx.y, ty = threadIdx.x;
+    const int tid = tx * FY + ty;
+    constexpr bool IS_DUGKS = MODE != MODE_BARDOW;
+
+    // own node (tiles may overhang the grid: wrap, the result is discarded)
     const int x = x0 + tx, y = y0 + ty;
     const bool active = x < nx && y < ny;
-    T f[9];
-
-    if (active) f[0] = fold[(size_t)x * ld + y];  // rest population: plain copy (:429)
+    T fp[9];
+    {
+        const int xs = active ? x : pmod(x, nx), ys = active ? y : pmod(y, ny);
+        T b[9];
 #pragma unroll
-    for (int q = 1; q < 9; ++q) {
-        const T* fq = fold + (size_t)q * nx * (size_t)ld;
-        __syncthreads();
-        for_tile<T>(x0, y0, nx, ny, [&](int sx, int sy, int gx, int gy) { sm[sx][sy] = fq[(size_t)gx * ld + gy]; });
-        __syncthreads();
-        const T cxq = dt * T(cxi(q)), cyq = dt * T(cyi(q));
-        const int cxs = tx + 1, cys = ty + 1;
-        const T fc = sm[cxs][cys], fe = sm[cxs + 1][cys], fw = sm[cxs - 1][cys];
-        const T fn = sm[cxs][cys + 1], fs = sm[cxs][cys - 1];
-        const T fne = sm[cxs + 1][cys + 1], fnw = sm[cxs - 1][cys + 1];
-        const T fsw = sm[cxs - 1][cys - 1], fse = sm[cxs + 1][cys - 1];
-        T cfw, cfn, cfe, cfs;
-        faces(fc, fe, fn, fw, fs, fne, fnw, fsw, fse, cxq, cyq, cfw, cfn, cfe, cfs);
-        f[q] = fc - cxq * (cfe - cfw) - cyq * (cfn - cfs);
+        for (int q = 0; q < 9; ++q) fp[q] = b[q] = fin[((size_t)q * nx + xs) * (size_t)ld + ys];
+        if (IS_DUGKS) {
+            collide_bgk_split(b, omega_half);
+            collide_bgk_split(fp, omega_full);
+        }
+        T* c = sm + (tx + 1) * PITCH + (ty + 1);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c[q * (GX * PITCH)] = b[q];
     }
-    if (!active) return;
-    if (MODEL != M_NONE) collide<T, MODEL>(f, cp);
+    // halo ring: 2 full lines (sx = 0, GX-1) and 2 x FX edge cells (sy = 0, GY-1)
+    if (tid < NHALO) {
+        int sx, sy;
+        if (tid < 2 * GY) {
+            sx = tid < GY ? 0 : GX - 1;
+            sy = tid < GY ? tid : tid - GY;
+        } else {
+            const int k = tid - 2 * GY;
+            sx = 1 + (k >> 1);
+            sy = (k & 1) ? GY - 1 : 0;
+        }
+        const int xs = pmod(x0 + sx - 1, nx), ys = pmod(y0 + sy - 1, ny);
+        T b[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) fnew[((size_t)q * nx + x) * (size_t)ld + y] = f[q];
+        for (int q = 0; q < 9; ++q) b[q] = fin[((size_t)q * nx + xs) * (size_t)ld + ys];
+        if (IS_DUGKS) collide_bgk_split(b, omega_half);
+        T* c = sm + sx * PITCH + sy;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c[q * (GX * PITCH)] = b[q];
+    }
+    __syncthreads();
+    if (!active) return;
+
+    const T* c0 = sm + (tx + 1) * PITCH + (ty + 1);
+    flux_update<T, MODE == MODE_DUGKS>(c0, dt, omega_face, fp);
+    if (MODE == MODE_BARDOW && MODEL != M_NONE) collide<T, MODEL>(fp, cp);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) fout[((size_t)q * nx + x) * (size_t)ld + y] = fp[q];
 }
 
-template <typename T>
-int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s)
+template <typename T, int MODE, int MODEL>
+static int launch_fv(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T oc, const CollideParams<T>& cp, cudaStream_t s)
 {
-    dim3 block(TY, TX), grid((g.ny + TY - 1) / TY, (g.nx + TX - 1) / TX);
-    switch (model) {
-    case M_NONE: k_fvm_bardow<T, M_NONE><<<grid, block, 0, s>>>(fold, fnew, g.nx, g.ny, g.ld, dt, cp); break;
-    case M_BGK: k_fvm_bardow<T, M_BGK><<<grid, block, 0, s>>>(fold, fnew, g.nx, g.ny, g.ld, dt, cp); break;
-    case M_TRT: k_fvm_bardow<T, M_TRT><<<grid, block, 0, s>>>(fold, fnew, g.nx, g.ny, g.ld, dt, cp); break;
-    case M_RR: k_fvm_bardow<T, M_RR><<<grid, block, 0, s>>>(fold, fnew, g.nx, g.ny, g.ld, dt, cp); break;
-    case M_BGK_SPLIT: k_fvm_bardow<T, M_BGK_SPLIT><<<grid, block, 0, s>>>(fold, fnew, g.nx, g.ny, g.ld, dt, cp); break;
-    default: set_error("fvm_bardow: unknown collision model"); return PLBM_ERR_ARG;
-    }
+    dim3 block(FY, FX), grid((g.ny + FY - 1) / FY, (g.nx + FX - 1) / FX);
+    const size_t smem = sizeof(T) * 9 * GX * PITCH;  // 25.2 KB fp64: below the 48 KB default, no opt-in needed
+    k_fv_fused<T, MODE, MODEL><<<grid, block, smem, s>>>(fin, fout, g.nx, g.ny, g.ld, dt, of, oh, oc, cp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
 }
 
+template <typename T>
+int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s)
+{
+    switch (model) {
+    case M_NONE: return launch_fv<T, MODE_BARDOW, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    case M_BGK: return launch_fv<T, MODE_BARDOW, M_BGK>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    case M_TRT: return launch_fv<T, MODE_BARDOW, M_TRT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    case M_RR: return launch_fv<T, MODE_BARDOW, M_RR>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    case M_BGK_SPLIT: return launch_fv<T, MODE_BARDOW, M_BGK_SPLIT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    }
+    set_error("fvm_bardow: unknown collision model");
+    return PLBM_ERR_ARG;
+}
+
+template <typename T>
+int launch_dugks_fused(const Grid& g, const T* fin, T* fout, T dt, T omega_full, T omega_half, T omega_face, bool dugks,
+                       cudaStream_t s)
+{
+    const CollideParams<T> cp{T(0), T(0)};
+    if (dugks) return launch_fv<T, MODE_DUGKS, M_NONE>(g, fin, fout, dt, omega_full, omega_half, omega_face, cp, s);
+    return launch_fv<T, MODE_DUGKS_OFF, M_NONE>(g, fin, fout, dt, omega_full, omega_half, omega_face, cp, s);
+}
+
 // ---------------------------------------------------------------------------------------
-// dugks_collide: fnew = BGK(fold, omega_full) ; fold = BGK(fold, omega_half)   (one pass)
+// The reference's separately public DUGKS procedures (two passes over global memory).
+// dugks_collide: fnew = BGK(fold, omega_full) ; fold = BGK(fold, omega_half)
 template <typename T>
 __global__ void __launch_bounds__(256) k_dugks_collide(T* __restrict__ fold, T* __restrict__ fnew, int nx, int ny, int ld,
                                                        T omega_full, T omega_half)
@@ -123,35 +269,7 @@ template <typename T> int launch_dugks_collide(const Grid& g, T* fold, T* fnew, 
     return PLBM_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// Shared body of kernel_stream for one node: given a functor nb(q, dx, dy) returning
-// fbar^+ of population q at the (dx,dy) neighbour, compute the four faces of all nine
-// populations, relax them (DUGKS) and return the flux update of fp[1..8].
-template <typename T, bool DUGKS, typename NB>
-__device__ __forceinline__ void dugks_node(NB&& nb, T dt, T omega_face, T (&fp)[9])
-{
-    T cfw[9], cfn[9], cfe[9], cfs[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) {
-        const T cxq = dt * T(cxi(q)), cyq = dt * T(cyi(q));
-        const T fc = nb(q, 0, 0), fe = nb(q, 1, 0), fn = nb(q, 0, 1), fw = nb(q, -1, 0), fs = nb(q, 0, -1);
-        const T fne = nb(q, 1, 1), fnw = nb(q, -1, 1), fsw = nb(q, -1, -1), fse = nb(q, 1, -1);
-        faces(fc, fe, fn, fw, fs, fne, fnw, fsw, fse, cxq, cyq, cfw[q], cfn[q], cfe[q], cfs[q]);
-    }
-    if (DUGKS) {
-        face_relax<T, true>(cfw, omega_face);
-        face_relax<T, true>(cfe, omega_face);
-        face_relax<T, false>(cfn, omega_face);
-        face_relax<T, false>(cfs, omega_face);
-    }
-#pragma unroll
-    for (int q = 1; q < 9; ++q) {
-        const T cxq = dt * T(cxi(q)), cyq = dt * T(cyi(q));
-        fp[q] = fp[q] - cxq * (cfe[q] - cfw[q]) - cyq * (cfn[q] - cfs[q]);
-    }
-}
-
-// dugks_stream as a separate entry (ft = fbar^+ in global memory, fp updated in place).
+// dugks_stream: ft = fbar^+ (global memory), fp updated in place for q = 1..8.
 template <typename T, bool DUGKS>
 __global__ void __launch_bounds__(256) k_dugks_stream(const T* __restrict__ ft, T* __restrict__ fp_, int nx, int ny, int ld,
                                                       T dt, T omega_face)
@@ -162,13 +280,26 @@ __global__ void __launch_bounds__(256) k_dugks_stream(const T* __restrict__ ft, 
     if (x >= nx || y >= ny) return;
     const int xs[3] = {wrap_m1(x, nx), x, wrap_p1(x, nx)};
     const int ys[3] = {wrap_m1(y, ny), y, wrap_p1(y, ny)};
-    T fp[9];
+    T cfw[9], cfn[9], cfe[9], cfs[9];
 #pragma unroll
-    for (int q = 1; q < 9; ++q) fp[q] = fp_[((size_t)q * nx + x) * (size_t)ld + y];
-    auto nb = [&](int q, int dx, int dy) -> T { return ft[((size_t)q * nx + xs[dx + 1]) * (size_t)ld + ys[dy + 1]]; };
-    dugks_node<T, DUGKS>(nb, dt, omega_face, fp);
+    for (int q = 0; q < 9; ++q) {
+        const T cxq = dt * T(cxi(q)), cyq = dt * T(cyi(q));
+        auto nb = [&](int dx, int dy) -> T { return ft[((size_t)q * nx + xs[dx + 1]) * (size_t)ld + ys[dy + 1]]; };
+        faces(nb(0, 0), nb(1, 0), nb(0, 1), nb(-1, 0), nb(0, -1), nb(1, 1), nb(-1, 1), nb(-1, -1), nb(1, -1), cxq, cyq, cfw[q],
+              cfn[q], cfe[q], cfs[q]);
+    }
+    if (DUGKS) {
+        face_relax<T, true>(cfw, omega_face);
+        face_relax<T, true>(cfe, omega_face);
+        face_relax<T, false>(cfn, omega_face);
+        face_relax<T, false>(cfs, omega_face);
+    }
 #pragma unroll
-    for (int q = 1; q < 9; ++q) fp_[((size_t)q * nx + x) * (size_t)ld + y] = fp[q];
+    for (int q = 1; q < 9; ++q) {
+        const T cxq = dt * T(cxi(q)), cyq = dt * T(cyi(q));
+        const size_t i = ((size_t)q * nx + x) * (size_t)ld + y;
+        fp_[i] = fp_[i] - cxq * (cfe[q] - cfw[q]) - cyq * (cfn[q] - cfs[q]);
+    }
 }
 
 template <typename T>
@@ -180,69 +311,6 @@ int launch_dugks_stream(const Grid& g, const T* ft, T* fp, T dt, T omega_face, b
         k_dugks_stream<T, true><<<nb, 256, 0, s>>>(ft, fp, g.nx, g.ny, g.ld, dt, omega_face);
     else
         k_dugks_stream<T, false><<<nb, 256, 0, s>>>(ft, fp, g.nx, g.ny, g.ld, dt, omega_face);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    PLBM_CUDA(cudaGetLastError());
-    return PLBM_OK;
-}
-
-// ---------------------------------------------------------------------------------------
-// Fused DUGKS step: fin = ftilde^n  ->  fout = ftilde^{n+1}.
-//   stage 1: every thread of the (SY x SX) halo tile reads the nine populations of one node,
-//            applies the half-step collision (fbar^+) and parks it in shared memory; the
-//            interior threads also keep the full-step collision (ftilde^+) in registers.
-//   stage 2: interior threads reconstruct faces from the shared tile, relax, update, store.
-// fbar^+ of the previous step (what the reference leaves in lattice `inew`, read by the
-// lagged update_macros) is not stored: it is recomputed on demand from fin, bit-identically.
-constexpr int FY = 32, FX = 8;         // interior tile of the fused kernel
-constexpr int GY = FY + 2, GX = FX + 2;  // with halo: 34 x 10 = 340 nodes
-
-template <typename T, bool DUGKS>
-__global__ void __launch_bounds__(FY* FX) k_dugks_fused(const T* __restrict__ fin, T* __restrict__ fout, int nx, int ny,
-                                                         int ld, T dt, T omega_full, T omega_half, T omega_face)
-{
-    extern __shared__ unsigned char smem_raw[];
-    T(*sm)[GX][GY + 1] = reinterpret_cast<T(*)[GX][GY + 1]>(smem_raw);  // sm[q][sx][sy]
-    const int x0 = blockIdx.y * FX, y0 = blockIdx.x * FY;
-    const int tid = threadIdx.y * FY + threadIdx.x;
-
-    for (int i = tid; i < GX * GY; i += FX * FY) {
-        const int sx = i / GY, sy = i - sx * GY;
-        const int x = pmod(x0 + sx - 1, nx), y = pmod(y0 + sy - 1, ny);
-        T b[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) b[q] = fin[((size_t)q * nx + x) * (size_t)ld + y];
-        collide_bgk_split(b, omega_half);
-#pragma unroll
-        for (int q = 0; q < 9; ++q) sm[q][sx][sy] = b[q];
-    }
-    __syncthreads();
-
-    const int x = x0 + threadIdx.y, y = y0 + threadIdx.x;
-    if (x >= nx || y >= ny) return;
-    T fp[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) fp[q] = fin[((size_t)q * nx + x) * (size_t)ld + y];
-    collide_bgk_split(fp, omega_full);
-    const int cxs = threadIdx.y + 1, cys = threadIdx.x + 1;
-    auto nb = [&](int q, int dx, int dy) -> T { return sm[q][cxs + dx][cys + dy]; };
-    dugks_node<T, DUGKS>(nb, dt, omega_face, fp);
-#pragma unroll
-    for (int q = 0; q < 9; ++q) fout[((size_t)q * nx + x) * (size_t)ld + y] = fp[q];
-}
-
-template <typename T>
-int launch_dugks_fused(const Grid& g, const T* fin, T* fout, T dt, T omega_full, T omega_half, T omega_face, bool dugks,
-                       cudaStream_t s)
-{
-    dim3 block(FY, FX), grid((g.ny + FY - 1) / FY, (g.nx + FX - 1) / FX);
-    const size_t smem = sizeof(T) * 9 * GX * (GY + 1);
-    if (dugks) {
-        PLBM_CUDA(cudaFuncSetAttribute(k_dugks_fused<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dugks_fused<T, true><<<grid, block, smem, s>>>(fin, fout, g.nx, g.ny, g.ld, dt, omega_full, omega_half, omega_face);
-    } else {
-        PLBM_CUDA(cudaFuncSetAttribute(k_dugks_fused<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dugks_fused<T, false><<<grid, block, smem, s>>>(fin, fout, g.nx, g.ny, g.ld, dt, omega_full, omega_half, omega_face);
-    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;

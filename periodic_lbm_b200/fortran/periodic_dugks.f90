@@ -1,0 +1,41 @@
+!> Drop-in replacement of the reference module `periodic_dugks` (src/periodic_dugks.F90:9-12).
+!! grid%dugks selects the -DDUGKS branch (default) or the macro-less default build of the reference.
+module periodic_dugks
+   use, intrinsic :: iso_c_binding
+   use fvm_bardow, only: lattice_grid, sync_indices
+   use plbm_c
+   implicit none
+   private
+   public :: perform_dugks_step
+   public :: dugks_stream
+   public :: dugks_collide
+contains
+
+   subroutine perform_dugks_step(grid)
+      type(lattice_grid), intent(inout) :: grid
+      logical :: fused
+      call plbm_check(plbm_set_omega(grid%dev, real(grid%omega,c_double)), "set_omega")
+      fused = .true.
+      if (associated(grid%collision)) fused = fused .and. associated(grid%collision, dugks_collide)
+      if (associated(grid%streaming)) fused = fused .and. associated(grid%streaming, dugks_stream)
+      if (fused) then
+         call plbm_check(plbm_perform_dugks_step(grid%dev, merge(1_c_int, 0_c_int, grid%dugks), 1_c_int), "perform_dugks_step")
+      else
+         call grid%collision()
+         call grid%streaming()
+         call plbm_check(plbm_swap(grid%dev), "swap")
+      end if
+      call sync_indices(grid)
+   end subroutine
+
+   subroutine dugks_collide(grid)
+      class(lattice_grid), intent(inout) :: grid
+      call plbm_check(plbm_dugks_collide(grid%dev, merge(1_c_int, 0_c_int, grid%dugks)), "dugks_collide")
+   end subroutine
+
+   subroutine dugks_stream(grid)
+      class(lattice_grid), intent(inout) :: grid
+      call plbm_check(plbm_dugks_stream(grid%dev, merge(1_c_int, 0_c_int, grid%dugks)), "dugks_stream")
+   end subroutine
+
+end module periodic_dugks
