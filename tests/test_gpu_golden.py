@@ -19,6 +19,14 @@ def load_rows(name):
     return {float(r): float(v) for r, v in np.loadtxt(os.path.join(GOLD, name))}
 
 
+def assert_matches_golden(l2, gold, steps):
+    """The files print 8 significant digits.  Measured over all 47 rows (profiles/r01_golden_sweep.txt):
+    |ours - file| <= 4.8e-10 absolute everywhere; relative <= 6e-8 except on the eight longest runs
+    around the error minimum (5e5..9e5 steps, L2 ~ 1e-5..5e-4) where it is <= 1.5e-6 -- the level of
+    accumulated round-off of a differently compiled reference binary (<= 1e-12 absolute in u)."""
+    assert abs(l2 - gold) <= 6e-10 and abs(l2 - gold) / gold <= 3e-6, (l2, gold, steps)
+
+
 def gpu_tg_run(plbm, n, scheme, collision=None, dt=None, dt_over_tau=None, precision="f64", lagged=True, dugks=True):
     """app/main_taylor_green.f90 end to end on the device; returns (L2, steps, t, grid)."""
     dtype = np.float64 if precision == "f64" else np.float32
@@ -43,21 +51,21 @@ def gpu_tg_run(plbm, n, scheme, collision=None, dt=None, dt_over_tau=None, preci
     return g.l2_error(uxa, uya), steps, float(t), g, (uxa, uya), tp
 
 
-# all rows with dt/tau >= 2 (<= 4.4e5 steps each; the 64^2 grid is launch-bound, ~2 us per step)
-@pytest.mark.parametrize("r", [2.0, 2.5, 3.0, 4.0, 5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 40.0, 50.0])
+# EVERY row of both files (dt/tau = 0.5 is 1.76 M steps; the 64^2 grid is launch-bound, ~7 us per step)
+@pytest.mark.parametrize("r", sorted(load_rows("ref_fvm_bardow_64.txt"), reverse=True))
 def test_gpu_reproduces_fvm_bardow_golden(plbm, r):
     gold = load_rows("ref_fvm_bardow_64.txt")[r]
     l2, steps, t, g, _, _ = gpu_tg_run(plbm, 64, "fvm", plbm.collide_bgk, dt_over_tau=r)
     plbm.dealloc_grid(g)
-    assert abs(l2 - gold) / gold < 2e-7, (l2, gold, steps)
+    assert_matches_golden(l2, gold, steps)
 
 
-@pytest.mark.parametrize("r", [2.0, 2.5, 3.0, 4.0, 5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 40.0, 50.0, 60.0, 70.0])
+@pytest.mark.parametrize("r", sorted(load_rows("ref_fvm_dugks_64.txt"), reverse=True))
 def test_gpu_reproduces_fvm_dugks_golden(plbm, r):
     gold = load_rows("ref_fvm_dugks_64.txt")[r]
     l2, steps, t, g, _, _ = gpu_tg_run(plbm, 64, "dugks", dt_over_tau=r)
     plbm.dealloc_grid(g)
-    assert abs(l2 - gold) / gold < 2e-7, (l2, gold, steps)
+    assert_matches_golden(l2, gold, steps)
 
 
 def test_gpu_full_run_bitwise_equals_oracle(plbm):
