@@ -138,7 +138,11 @@ template <typename T> int step_fvm_t(Grid& g, int model, int nsteps)
     const CollideParams<T> cp = collide_params<T>(g, model);
     g.dugks_pending = false;  // lattice inew is overwritten below
     for (int s = 0; s < nsteps; ++s) {
-        int rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, model, cp, g.stream);
+        int rc;
+        if (g.variant == 0 && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
+            rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), 2, model, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
+        else
+            rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, model, cp, g.stream);
         if (rc) return rc;
         swap_lattices(g);
     }
@@ -156,8 +160,12 @@ template <typename T> int step_dugks_t(Grid& g, bool dugks, int nsteps)
             rc = launch_dugks_collide<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), of, oh, g.stream);
             if (rc) return rc;
             rc = launch_dugks_stream<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, oc, dugks, g.stream);
+        } else if (g.variant == 0 && g.tmap_ok) {
+            // fused, TMA-pipelined: lattice iold (ftilde^n) is left untouched, inew receives ftilde^{n+1}.
+            rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), dugks ? 0 : 1, M_NONE, (T)g.dt, of, oh, oc,
+                                  CollideParams<T>{T(0), T(0)}, g.stream);
         } else {
-            // fused: lattice iold (ftilde^n) is left untouched, inew receives ftilde^{n+1}.
+            // fused, plain loads (variant 2, or no TMA descriptor)
             rc = launch_dugks_fused<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, of, oh, oc, dugks, g.stream);
         }
         if (rc) return rc;
@@ -265,6 +273,7 @@ int plbm_alloc_grid_on(plbm_handle* out, int nx, int ny, int nf, int precision, 
     if ((e = cudaMallocHost(&g->partial_host, 32 * (size_t)g->npartial)) != cudaSuccess) return fail(e, "cudaMallocHost");
     if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     g->own_stream = true;
+    make_tensor_maps(*g);
     *out = g;
     return PLBM_OK;
 }

@@ -16,6 +16,7 @@
 // so each node computes its own four faces exactly like the Fortran.  Terms multiplied by
 // cx = 0 or cy = 0 are exact zeros and are skipped (x - 0 == x).
 #include "plbm_internal.h"
+#include "plbm_fv.cuh"
 
 namespace plbm {
 
@@ -33,106 +34,6 @@ constexpr int FY = 32, FX = 8;
 constexpr int GY = FY + 2, GX = FX + 2;  // with halo: 34 x 10 = 340 nodes
 constexpr int PITCH = GY + 1;            // odd pitch: neighbouring lines fall in different banks
 constexpr int NHALO = GX * GY - FX * FY; // 84 ring nodes
-
-// West/East faces of population Q from the shared tile; c points at the centre node, neighbours
-// are at c[dx * PITCH + dy].  hx = p2*cxq, ey = p8*cyq (products formed left to right like the
-// Fortran `p2*cxq*(...)`).
-template <typename T, int Q> __device__ __forceinline__ void faces_ew(const T* c, T hx, T ey, T& cfw, T& cfe)
-{
-    constexpr int CX = cxi(Q), CY = cyi(Q);
-    const T p2 = T(0.5);
-    const T fc = c[0], fw = c[-PITCH], fe = c[PITCH];
-    cfw = p2 * (fc + fw);
-    cfe = p2 * (fc + fe);
-    if (CX != 0) {
-        cfw = cfw - hx * (fc - fw);
-        cfe = cfe - hx * (fe - fc);
-    }
-    if (CY != 0) {
-        const T fn = c[1], fs = c[-1];
-        const T fnw = c[-PITCH + 1], fsw = c[-PITCH - 1], fne = c[PITCH + 1], fse = c[PITCH - 1];
-        cfw = cfw - ey * (fnw + fn - fsw - fs);
-        cfe = cfe - ey * (fne + fn - fse - fs);
-    }
-}
-
-// North/South faces; hy = p2*cyq, ex = p8*cxq.
-template <typename T, int Q> __device__ __forceinline__ void faces_ns(const T* c, T hy, T ex, T& cfn, T& cfs)
-{
-    constexpr int CX = cxi(Q), CY = cyi(Q);
-    const T p2 = T(0.5);
-    const T fc = c[0], fn = c[1], fs = c[-1];
-    cfn = p2 * (fc + fn);
-    cfs = p2 * (fc + fs);
-    if (CY != 0) {
-        cfn = cfn - hy * (fn - fc);
-        cfs = cfs - hy * (fc - fs);
-    }
-    if (CX != 0) {
-        const T fe = c[PITCH], fw = c[-PITCH];
-        const T fne = c[PITCH + 1], fnw = c[-PITCH + 1], fse = c[PITCH - 1], fsw = c[-PITCH - 1];
-        cfn = cfn - ex * (fne + fe - fnw - fw);
-        cfs = cfs - ex * (fse + fe - fsw - fw);
-    }
-}
-
-template <typename T, bool DUGKS, int Q>
-__device__ __forceinline__ void ew_pop(const T* c0, T dt, T (&cfw)[9], T (&cfe)[9])
-{
-    const T cxq = dt * T(cxi(Q)), cyq = dt * T(cyi(Q));
-    faces_ew<T, Q>(c0 + Q * (GX * PITCH), T(0.5) * cxq, T(0.125) * cyq, cfw[Q], cfe[Q]);
-}
-template <typename T, bool DUGKS, int Q>
-__device__ __forceinline__ void ns_pop(const T* c0, T dt, T (&cfn)[9], T (&cfs)[9])
-{
-    const T cxq = dt * T(cxi(Q)), cyq = dt * T(cyi(Q));
-    faces_ns<T, Q>(c0 + Q * (GX * PITCH), T(0.5) * cyq, T(0.125) * cxq, cfn[Q], cfs[Q]);
-}
-
-// Flux update of one node from the shared tile of fbar (DUGKS) or f^n (Bardow):
-//   fp(q) = fp(q) - cxq*(cfe - cfw) - cyq*(cfn - cfs)        (src/periodic_dugks.F90:297)
-// evaluated as two passes (east/west, then north/south) so only two face sets are live.
-template <typename T, bool DUGKS> __device__ __forceinline__ void flux_update(const T* c0, T dt, T omega_face, T (&fp)[9])
-{
-    {
-        T cfw[9], cfe[9];
-        if (DUGKS) ew_pop<T, DUGKS, 0>(c0, dt, cfw, cfe);  // rest population: faces only feed the moments
-        ew_pop<T, DUGKS, 1>(c0, dt, cfw, cfe);
-        ew_pop<T, DUGKS, 3>(c0, dt, cfw, cfe);
-        ew_pop<T, DUGKS, 5>(c0, dt, cfw, cfe);
-        ew_pop<T, DUGKS, 6>(c0, dt, cfw, cfe);
-        ew_pop<T, DUGKS, 7>(c0, dt, cfw, cfe);
-        ew_pop<T, DUGKS, 8>(c0, dt, cfw, cfe);
-        if (DUGKS) {
-            ew_pop<T, DUGKS, 2>(c0, dt, cfw, cfe);
-            ew_pop<T, DUGKS, 4>(c0, dt, cfw, cfe);
-            face_relax<T, true>(cfw, omega_face);
-            face_relax<T, true>(cfe, omega_face);
-        }
-#pragma unroll
-        for (int q = 1; q < 9; ++q)
-            if (cxi(q) != 0) fp[q] = fp[q] - (dt * T(cxi(q))) * (cfe[q] - cfw[q]);
-    }
-    {
-        T cfn[9], cfs[9];
-        if (DUGKS) ns_pop<T, DUGKS, 0>(c0, dt, cfn, cfs);
-        ns_pop<T, DUGKS, 2>(c0, dt, cfn, cfs);
-        ns_pop<T, DUGKS, 4>(c0, dt, cfn, cfs);
-        ns_pop<T, DUGKS, 5>(c0, dt, cfn, cfs);
-        ns_pop<T, DUGKS, 6>(c0, dt, cfn, cfs);
-        ns_pop<T, DUGKS, 7>(c0, dt, cfn, cfs);
-        ns_pop<T, DUGKS, 8>(c0, dt, cfn, cfs);
-        if (DUGKS) {
-            ns_pop<T, DUGKS, 1>(c0, dt, cfn, cfs);
-            ns_pop<T, DUGKS, 3>(c0, dt, cfn, cfs);
-            face_relax<T, false>(cfn, omega_face);
-            face_relax<T, false>(cfs, omega_face);
-        }
-#pragma unroll
-        for (int q = 1; q < 9; ++q)
-            if (cyi(q) != 0) fp[q] = fp[q] - (dt * T(cyi(q))) * (cfn[q] - cfs[q]);
-    }
-}
 
 // MODE_DUGKS : fin = ftilde^n -> fout = ftilde^{n+1}   (perform_dugks_step, -DDUGKS or not)
 // MODE_BARDOW: fin = f^n      -> fout = collide(stream_fvm_bardow(f^n))   (perform_step)
@@ -197,7 +98,7 @@ __global__ void __launch_bounds__(FY* FX, 2)
     if (!active) return;
 
     const T* c0 = sm + (tx + 1) * PITCH + (ty + 1);
-    flux_update<T, MODE == MODE_DUGKS>(c0, dt, omega_face, fp);
+    flux_update<T, MODE == MODE_DUGKS, PITCH, GX * PITCH>(c0, dt, omega_face, fp);
     if (MODE == MODE_BARDOW && MODEL != M_NONE) collide<T, MODEL>(fp, cp);
 #pragma unroll
     for (int q = 0; q < 9; ++q) fout[((size_t)q * nx + x) * (size_t)ld + y] = fp[q];

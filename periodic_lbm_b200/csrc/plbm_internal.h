@@ -51,6 +51,10 @@ struct Grid {
     // half-step collision is applied lazily, in place, the first time somebody looks at `inew`.
     bool dugks_pending = false;
     double dugks_pending_omega = 0;
+    // TMA descriptors (CUtensorMap, 128 B each) of the lattices viewed as a (ny, nx, 9) tensor with
+    // a (FY+2, FX+2, 9) box: used by the pipelined FVM/DUGKS tile kernel (plbm_fvm_tma.cu)
+    alignas(64) unsigned char tmap[3][128];
+    bool tmap_ok = false;
     // slab decomposition (single GPU: nx_global == nx, x_offset == 0)
     int nx_global = 0, x_offset = 0;
 
@@ -89,6 +93,11 @@ template <typename T> int launch_dugks_stream(const Grid& g, const T* ft, T* fp,
 template <typename T>
 int launch_dugks_fused(const Grid& g, const T* fin, T* fout, T dt, T omega_full, T omega_half, T omega_face, bool dugks,
                        cudaStream_t s);
+// TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice
+int make_tensor_maps(Grid& g);
+template <typename T>
+int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode, int model, T dt, T omega_full, T omega_half,
+                  T omega_face, const CollideParams<T>& cp, cudaStream_t s);
 template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s);
 
 // multi-GPU ring exchange (plbm_comm.cu)

@@ -65,9 +65,14 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--what", default="lbm")
+    ap.add_argument("--case", default="", help="scheme,prec,coll,variant  e.g. dugks,f64,bgk,0 (runs only this)")
     a = ap.parse_args()
     n = a.n
     rows = []
+    if a.case:
+        scheme, prec, coll, variant = a.case.split(",")
+        print(json.dumps(run(n, n, prec, scheme, coll, int(variant), a.steps)), flush=True)
+        sys.exit(0)
     if "lbm" in a.what:
         for prec in ("f64", "f32"):
             for coll in ("bgk", "trt", "rr"):
