@@ -39,6 +39,8 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (ny_fast, nx_slow_per_gpu, collision, precision, description)
     "c5_bgk_f64_slab": (32768, 4096, "bgk", "f64", "C5 D2Q9 BGK fp64 Taylor-Green, y-slab weak scaling, 32768 x 4096 lines per GPU"),
+    # strong scaling of the full C5 grid: nx_slow_per_gpu = 32768 / N (154.6 GB of PDFs on one GPU)
+    "c5_bgk_f64_strong": (32768, -32768, "bgk", "f64", "C5 D2Q9 BGK fp64 Taylor-Green 32768 x 32768, y-slab STRONG scaling"),
     "c3_rr_f64_8192": (8192, 8192, "rr", "f64", "C3 D2Q9 recursive-regularized fp64 Taylor-Green 8192 x 8192 per GPU"),
     "c3_rr_f32_8192": (8192, 8192, "rr", "f32", "C3 D2Q9 recursive-regularized fp32 Taylor-Green 8192 x 8192 per GPU"),
     "c2_trt_f64_1024": (1024, 1024, "trt", "f64", "C2 D2Q9 TRT fp64 1024 x 1024 per GPU"),
@@ -125,6 +127,11 @@ def cpu_reference_mlups(ny, collision, precision, seconds_budget, steps=None, wa
     nx = min(CPU_SAMPLE_LINES, ny)
     og = OracleGrid(nx, ny, precision, omp=True)
     o = og.o
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it)
+    try:
+        o.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        o.set_num_threads(os.cpu_count() or 1)
     cores = o.num_threads()
     s = taylor_green_setup(o, ny, dt=1.0)
     og.set_properties(s["nu"], s["dt"], magic=0.25)
@@ -153,6 +160,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     ny, nxl, collision, precision, desc = WORKLOADS[args.workload]
+    nxl = abs(nxl)
     steps = args.steps if args.steps else None
     # keep the whole run within a few minutes: cap the number of timed steps
     mlups, cores, sample, ms, steps = cpu_reference_mlups(ny, collision, precision, 20.0, steps=min(steps, 100) if steps else None,
@@ -160,7 +168,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "MLUPS", "value": round(mlups, 2), "unit": "MLUPS (1e6 lattice updates/s)",
         "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": round(ms, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+        "scaling": "strong" if WORKLOADS[args.workload][1] < 0 else "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "ny_fast": ny, "nx_slow_per_gpu": nxl, "collision": collision,
                    "note": "CPU run does not use the GPUs; value does not scale with n_gpus"},
         "cpu_baseline": {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample,
@@ -192,6 +200,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ny, nxl, collision, precision, desc = WORKLOADS[args.workload]
+    strong = nxl < 0
+    if strong:  # fixed global grid, split over the ranks
+        nxl = -nxl // world
     nx_global = nxl * world
     dtype = np.float64 if precision == "f64" else np.float32
     stream = torch.cuda.Stream()
@@ -302,7 +313,7 @@ def run_ours(args):
         tr = ncu_traffic_per_lup(args.workload)
         line = {
             "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS (1e6 lattice updates/s)", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": precision,
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "ny_fast": ny, "nx_slow_per_gpu": nxl, "nx_slow_global": nx_global,
                        "collision": collision, "lattice": "D2Q9, two lattices, SoA f(ld,nx,0:8)", "halo": "1 line x 3 populations per direction per step (NCCL send/recv)" if world > 1 else "none (periodic index wrap)",

@@ -99,6 +99,10 @@ int plbm_set_pdf_to_equilibrium(plbm_handle grid, const void* rho, const void* u
 int plbm_perform_lbm_step(plbm_handle grid, int collision, int nsteps);
 /* perform_step (src/fvm_bardow.F90:307-320) with streaming = stream_fvm_bardow. */
 int plbm_perform_step(plbm_handle grid, int streaming, int collision, int nsteps);
+/* perform_triple_step (src/fvm_bardow.F90:322-340), needs nf = 3: like perform_step but the
+ * streamed, pre-collision PDFs are kept in lattice `iold` before the indices rotate
+ * (iold, inew, imid) <- (inew, imid, iold). */
+int plbm_perform_triple_step(plbm_handle grid, int streaming, int collision, int nsteps);
 /* perform_dugks_step (src/periodic_dugks.F90:25-38): dugks_collide + dugks_stream + swap.
  * dugks != 0 selects the -DDUGKS branch (half-step + face relaxation), 0 the default
  * build (degenerates to Bardow's scheme). */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "plbm_set_pdf_to_equilibrium": (_I, [_H, _P, _P, _P]),
     "plbm_perform_lbm_step": (_I, [_H, _I, _I]),
     "plbm_perform_step": (_I, [_H, _I, _I, _I]),
+    "plbm_perform_triple_step": (_I, [_H, _I, _I, _I]),
     "plbm_perform_dugks_step": (_I, [_H, _I, _I]),
     "plbm_lbm_stream": (_I, [_H]),
     "plbm_stream_fvm_bardow": (_I, [_H]),

@@ -3,6 +3,7 @@
 // host <-> device staging of the macroscopic fields.
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "plbm_internal.h"
@@ -106,6 +107,15 @@ template <typename T> int set_properties_t(Grid& g, double nu_, double dt_, doub
 }
 
 // Apply the deferred half-step collision of the last fused DUGKS step to lattice `inew`.
+// scratch fields, allocated on first use
+int need_aux(Grid& g, int count)
+{
+    const size_t bytes = (size_t)g.nx * g.ny * g.esize();
+    if (!g.aux) PLBM_CUDA(cudaMalloc(&g.aux, bytes));
+    if (count > 1 && !g.aux2) PLBM_CUDA(cudaMalloc(&g.aux2, bytes));
+    return PLBM_OK;
+}
+
 int materialize_inew(Grid& g)
 {
     if (!g.dugks_pending) return PLBM_OK;
@@ -174,6 +184,35 @@ template <typename T> int step_dugks_t(Grid& g, bool dugks, int nsteps)
             g.dugks_pending = true;
             g.dugks_pending_omega = (double)oh;
         }
+    }
+    return PLBM_OK;
+}
+
+// perform_triple_step (src/fvm_bardow.F90:322-340): stream iold -> inew; copy inew -> iold (keep the
+// pre-collision PDFs); collide inew; rotate (iold, inew, imid) <- (inew, imid, iold).
+template <typename T> int step_triple_t(Grid& g, int streaming, int model, int nsteps)
+{
+    g.dugks_pending = false;
+    const CollideParams<T> cp = collide_params<T>(g, model);
+    for (int s = 0; s < nsteps; ++s) {
+        int rc;
+        if (streaming == PLBM_STREAM_LBM) {
+            // fused: post-collision -> inew, pre-collision -> the spare lattice (imid); the spare and
+            // the source then trade places so that index `iold` ends up holding the pre-collision copy
+            LbmArgs<T> a = lbm_args<T>(g, g.iold, g.inew, model);
+            a.pre = g.lat<T>(g.imid);
+            if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+            std::swap(g.f[g.iold - 1], g.f[g.imid - 1]);
+            for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.imid - 1][b]);
+        } else {
+            if ((rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, M_NONE, cp, g.stream))) return rc;
+            PLBM_CUDA(cudaMemcpyAsync(g.f[g.iold - 1], g.f[g.inew - 1], g.lattice_elems() * g.esize(), cudaMemcpyDeviceToDevice, g.stream));
+            if ((rc = launch_lbm<T>(lbm_args<T>(g, g.inew, g.inew, model), model, false, g.variant, g.stream))) return rc;
+        }
+        const int t = g.iold;
+        g.iold = g.inew;
+        g.inew = g.imid;
+        g.imid = t;
     }
     return PLBM_OK;
 }
@@ -266,8 +305,8 @@ int plbm_alloc_grid_on(plbm_handle* out, int nx, int ny, int nf, int precision, 
         if (e != cudaSuccess) return fail(e, "cudaMalloc(lattice)");
     }
     if ((e = cudaMalloc(&g->mf, 3 * nm * es)) != cudaSuccess) return fail(e, "cudaMalloc(mf)");
-    if ((e = cudaMalloc(&g->aux, nm * es)) != cudaSuccess) return fail(e, "cudaMalloc(aux)");
-    if ((e = cudaMalloc(&g->aux2, nm * es)) != cudaSuccess) return fail(e, "cudaMalloc(aux2)");
+    // aux / aux2 (vorticity output, analytic fields) are allocated on first use: a 32768^2 fp64 grid
+    // fills the GPU with its two lattices + macroscopic fields (180.4 GB of 192 GB)
     g->npartial = 4 * g->sm_count;
     if ((e = cudaMalloc(&g->partial, 32 * (size_t)g->npartial)) != cudaSuccess) return fail(e, "cudaMalloc(partial)");
     if ((e = cudaMallocHost(&g->partial_host, 32 * (size_t)g->npartial)) != cudaSuccess) return fail(e, "cudaMallocHost");
@@ -418,6 +457,26 @@ int plbm_perform_step(plbm_handle g, int streaming, int collision, int nsteps)
     return DISPATCH(g, step_fvm_t<double>(*g, collision, nsteps), step_fvm_t<float>(*g, collision, nsteps));
 }
 
+int plbm_perform_triple_step(plbm_handle g, int streaming, int collision, int nsteps)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if ((rc = need_props(g))) return rc;
+    if (g->nf < 3) {
+        set_error("perform_triple_step: the grid was allocated with nf = 2");
+        return PLBM_ERR_STATE;
+    }
+    if ((streaming != PLBM_STREAM_LBM && streaming != PLBM_STREAM_FVM_BARDOW) || !valid_model(collision) || nsteps < 0) {
+        set_error("perform_triple_step: bad streaming/collision id or nsteps");
+        return PLBM_ERR_ARG;
+    }
+    if (g->comm) {
+        set_error("perform_triple_step: slab decomposition not supported for this orchestrator");
+        return PLBM_ERR_ARG;
+    }
+    return DISPATCH(g, step_triple_t<double>(*g, streaming, collision, nsteps), step_triple_t<float>(*g, streaming, collision, nsteps));
+}
+
 int plbm_perform_dugks_step(plbm_handle g, int dugks, int nsteps)
 {
     int rc = check(g);
@@ -548,6 +607,7 @@ int plbm_vorticity(plbm_handle g, int order, void* omega)
         set_error("vorticity: single-GPU only (gather the macroscopic fields first)");
         return PLBM_ERR_ARG;
     }
+    if ((rc = need_aux(*g, 1))) return rc;
     if (g->prec == PLBM_F64) {
         if ((rc = launch_vorticity<double>(*g, order, g->ux<double>(), g->uy<double>(), (double*)g->aux, g->stream))) return rc;
         if ((rc = download_field<double>(*g, omega, (double*)g->aux))) return rc;
@@ -597,6 +657,7 @@ int plbm_l2_sums(plbm_handle g, const void* uxa, const void* uya, double out[2])
         set_error("l2_sums: null pointer");
         return PLBM_ERR_ARG;
     }
+    if ((rc = need_aux(*g, 2))) return rc;
     if (g->prec == PLBM_F64) {
         if ((rc = upload_field<double>(*g, (double*)g->aux, uxa))) return rc;
         if ((rc = upload_field<double>(*g, (double*)g->aux2, uya))) return rc;

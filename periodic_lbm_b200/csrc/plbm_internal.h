@@ -77,6 +77,7 @@ template <typename T> struct LbmArgs {
     const T* halo_lo;
     const T* halo_hi;
     CollideParams<T> cp;
+    T* pre = nullptr;      // optional: also store the streamed, pre-collision PDFs (perform_triple_step)
 };
 
 // ---- launchers (all asynchronous on `s`) -------------------------------------------------

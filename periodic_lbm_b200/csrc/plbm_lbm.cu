@@ -114,6 +114,16 @@ __global__ void __launch_bounds__(256) k_lbm(const LbmArgs<T> a)
     }
     if (!active) return;
 
+    if (STREAM && a.pre != nullptr) {  // perform_triple_step keeps the pre-collision lattice
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            Pack<T, V> p;
+#pragma unroll
+            for (int v = 0; v < V; ++v) p.v[v] = f[v][q];
+            *reinterpret_cast<Pack<T, V>*>(a.pre + ((size_t)q * a.nx + x) * (size_t)a.ld + y0) = p;
+        }
+    }
+
     if (MODEL != M_NONE) {
 #pragma unroll
         for (int v = 0; v < V; ++v) collide<T, MODEL>(f[v], a.cp);

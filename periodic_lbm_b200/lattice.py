@@ -29,7 +29,7 @@ from .capi import check, lib
 
 __all__ = [
     "LatticeGrid", "alloc_grid", "dealloc_grid", "set_properties", "set_pdf_to_equilibrium",
-    "perform_step", "perform_lbm_step", "perform_dugks_step", "update_macros",
+    "perform_step", "perform_lbm_step", "perform_triple_step", "perform_dugks_step", "update_macros",
     "lbm_stream", "stream_fvm_bardow", "collide_bgk", "collide_trt", "collide_rr", "collide_bgk_split",
     "dugks_collide", "dugks_stream", "vorticity_2nd", "vorticity_4th", "lambda_d", "magic_number",
     "cx", "cy", "csqr",
@@ -231,6 +231,16 @@ def perform_lbm_step(grid, nsteps=1) -> None:
 def perform_step(grid, nsteps=1) -> None:
     """perform_step (src/fvm_bardow.F90:307-320): identical sequence to perform_lbm_step."""
     perform_lbm_step(grid, nsteps)
+
+
+def perform_triple_step(grid, nsteps=1) -> None:
+    """perform_triple_step (src/fvm_bardow.F90:322-340) on a grid allocated with nf=3: the streamed,
+    pre-collision PDFs stay available in lattice `imid` after the index rotation."""
+    cid = _COLLISION_ID.get(grid.collision)
+    sid = {lbm_stream: capi.STREAM_LBM, stream_fvm_bardow: capi.STREAM_FVM_BARDOW}.get(grid.streaming)
+    if cid is None or sid is None:
+        raise capi.PlbmError("perform_triple_step: needs lbm_stream|stream_fvm_bardow and collide_bgk|trt|rr")
+    check(lib.plbm_perform_triple_step(grid._h, sid, cid, int(nsteps)), "perform_triple_step")
 
 
 def perform_dugks_step(grid, nsteps=1) -> None:

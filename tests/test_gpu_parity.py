@@ -128,8 +128,39 @@ def test_fvm_bardow_steps(plbm, nx, ny, prec):
     plbm.dealloc_grid(g)
 
 
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("scheme", ["lbm", "fvm"])
+def test_perform_triple_step(plbm, prec, scheme):
+    """perform_triple_step (src/fvm_bardow.F90:322-340): post-collision in iold, pre-collision in imid."""
+    nx, ny, steps = 40, 48, 4
+    o = Oracle(prec)
+    f = [random_state(o, nx, ny), o.alloc_f(nx, ny, fill=0.0), o.alloc_f(nx, ny, fill=0.0)]
+    props = o.set_properties(0.02, 0.3 if scheme == "fvm" else 1.0, 0.25)
+    g = plbm.alloc_grid(nx, ny, nf=3, precision=prec)
+    plbm.set_properties(g, 0.02, 0.3 if scheme == "fvm" else 1.0, 0.25)
+    iold, inew, imid = g.iold, g.inew, g.imid
+    assert (iold, inew, imid) == (2, 1, 3)
+    g.upload_f(iold, np.nan_to_num(f[0], nan=0.0))
+    lat = {iold: f[0], inew: f[1], imid: f[2]}
+    g.collision = plbm.collide_rr
+    g.streaming = plbm.lbm_stream if scheme == "lbm" else plbm.stream_fvm_bardow
+    plbm.perform_triple_step(g, steps)
+    for _ in range(steps):
+        if scheme == "lbm":
+            o.lbm_stream(lat[iold], lat[inew], ny)
+        else:
+            o.stream_fvm_bardow(lat[iold], lat[inew], ny, props["dt"])
+        lat[iold][...] = lat[inew]
+        o.collide_rr(lat[inew], ny, props["omega"])
+        iold, inew, imid = inew, imid, iold
+    assert (g.iold, g.inew, g.imid) == (iold, inew, imid)
+    assert np.array_equal(g.download_f(g.iold)[:, :, :ny], lat[iold][:, :, :ny])
+    assert np.array_equal(g.download_f(g.imid)[:, :, :ny], lat[imid][:, :, :ny])
+    plbm.dealloc_grid(g)
+
+
 @pytest.mark.parametrize("dugks", [True, False])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("nx,ny", [(64, 64), (67, 53), (5, 3), (34, 130)])
 def test_dugks_steps(plbm, nx, ny, prec, variant, dugks):
