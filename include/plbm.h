@@ -42,7 +42,12 @@ enum plbm_precision { PLBM_F64 = 0, PLBM_F32 = 1 };
 /* collision operators: collide_bgk (src/collision_bgk.F90:17), collide_trt
  * (src/collision_trt.F90:41), collide_rr (src/collision_regularized.F90:21), and the
  * -DSPLIT re-associated BGK (src/collision_bgk.F90:84-176). */
-enum plbm_collision { PLBM_BGK = 0, PLBM_TRT = 1, PLBM_RR = 2, PLBM_BGK_SPLIT = 3 };
+enum plbm_collision {
+    PLBM_BGK = 0, PLBM_TRT = 1, PLBM_RR = 2,
+    PLBM_BGK_SPLIT = 3,    /* collide_bgk built with -DSPLIT (bgk_kernel_cache)              */
+    PLBM_TRT_SPLIT = 4,    /* collide_trt built with -DSPLIT (src/collision_trt.F90:162-290) */
+    PLBM_BGK_IMPROVED = 5  /* collide_bgk_improved (src/collision_bgk_improved.f90:16-107)   */
+};
 
 /* streaming schemes: lbm_stream (src/periodic_lbm.f90:32), stream_fvm_bardow
  * (src/fvm_bardow.F90:393). */

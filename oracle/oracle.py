@@ -39,7 +39,7 @@ def padded_ld(ny: int) -> int:
 
 class Oracle:
     SCHEME_LBM, SCHEME_FVM_BARDOW, SCHEME_DUGKS, SCHEME_DUGKS_OFF = 0, 1, 2, 3
-    BGK, TRT, RR, BGK_SPLIT = 0, 1, 2, 3
+    BGK, TRT, RR, BGK_SPLIT, TRT_SPLIT, BGK_IMPROVED = 0, 1, 2, 3, 4, 5
 
     def __init__(self, precision: str = "f64", omp: bool = False):
         build()
@@ -68,6 +68,8 @@ class Oracle:
         self._kbgk = self._fn("orc_kernel_bgk", None, [I, I, I, P, R])
         self._trt = self._fn("orc_collide_trt", None, [I, I, I, P, R, R])
         self._rr = self._fn("orc_collide_rr", None, [I, I, I, P, R])
+        self._trt_split = self._fn("orc_collide_trt_split", None, [I, I, I, P, R, R])
+        self._bgk_improved = self._fn("orc_collide_bgk_improved", None, [I, I, I, P, R])
         self._lambda_d = self._fn("orc_lambda_d", R, [R, R])
         self._magic = self._fn("orc_magic_number", R, [R, R])
         self._fvm = self._fn("orc_stream_fvm_bardow", None, [I, I, I, P, P, R])
@@ -151,6 +153,12 @@ class Oracle:
 
     def collide_trt(self, f, ny, omega, magic):
         self._trt(f.shape[1], ny, f.shape[2], self._p(self._chk(f)), omega, self._lambda_d(omega, magic))
+
+    def collide_trt_split(self, f, ny, omega, magic):
+        self._trt_split(f.shape[1], ny, f.shape[2], self._p(self._chk(f)), omega, self._lambda_d(omega, magic))
+
+    def collide_bgk_improved(self, f, ny, omega):
+        self._bgk_improved(f.shape[1], ny, f.shape[2], self._p(self._chk(f)), omega)
 
     def collide_rr(self, f, ny, omega):
         self._rr(f.shape[1], ny, f.shape[2], self._p(self._chk(f)), omega)

@@ -304,6 +304,103 @@ void SFX(orc_collide_trt)(int nx, int ny, int ld, REAL *f1, REAL lambda_e, REAL 
         }
 }
 
+/* src/collision_trt.F90:162-290 trt_split (-DSPLIT).  Per node: trt_naive except that the axis
+ * pairs evaluate `fac1 * vel * vel` left to right instead of fac1 * (vel*vel). */
+void SFX(orc_collide_trt_split)(int nx, int ny, int ld, REAL *f1, REAL lambda_e, REAL lambda_d)
+{
+    const REAL t0 = R(4.0) / R(9.0);
+    const REAL t1x2 = (R(1.0) / R(9.0)) * R(2.0);
+    const REAL t2x2 = (R(1.0) / R(36.0)) * R(2.0);
+    const REAL inv2csq2 = R(1.0) / (R(2.0) * (R(1.0) / R(3.0)) * (R(1.0) / R(3.0)));
+    const REAL fac1 = t1x2 * inv2csq2;
+    const REAL fac2 = t2x2 * inv2csq2;
+    REAL lambda_e_scaled = R(0.5) * lambda_e;
+    REAL lambda_d_scaled = R(0.5) * lambda_d;
+#pragma omp parallel for schedule(static)
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) {
+            REAL vC = f1[FIDX(y, x, 0)], vE = f1[FIDX(y, x, 1)], vN = f1[FIDX(y, x, 2)];
+            REAL vW = f1[FIDX(y, x, 3)], vS = f1[FIDX(y, x, 4)], vNE = f1[FIDX(y, x, 5)];
+            REAL vNW = f1[FIDX(y, x, 6)], vSW = f1[FIDX(y, x, 7)], vSE = f1[FIDX(y, x, 8)];
+            REAL rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
+            REAL velX = (((vNE - vSW) + (vSE - vNW)) + (vE - vW));
+            REAL velY = (((vNE - vSW) + (vNW - vSE)) + (vN - vS));
+            REAL feq_common = rho - R(1.5) * (velX * velX + velY * velY);
+            f1[FIDX(y, x, 0)] = vC * (R(1.0) - lambda_e) + lambda_e * t0 * feq_common;
+
+            REAL velXPY = velX + velY;
+            REAL sym_NE_SW = lambda_e_scaled * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common);
+            REAL asym_NE_SW = lambda_d_scaled * (vNE - vSW - R(3.0) * t2x2 * velXPY);
+            f1[FIDX(y, x, 5)] = vNE - sym_NE_SW - asym_NE_SW;
+            f1[FIDX(y, x, 7)] = vSW - sym_NE_SW + asym_NE_SW;
+
+            REAL velXMY = velX - velY;
+            REAL sym_SE_NW = lambda_e_scaled * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common);
+            REAL asym_SE_NW = lambda_d_scaled * (vSE - vNW - R(3.0) * t2x2 * velXMY);
+            f1[FIDX(y, x, 8)] = vSE - sym_SE_NW - asym_SE_NW;
+            f1[FIDX(y, x, 6)] = vNW - sym_SE_NW + asym_SE_NW;
+
+            REAL sym_N_S = lambda_e_scaled * (vN + vS - fac1 * velY * velY - t1x2 * feq_common);
+            REAL asym_N_S = lambda_d_scaled * (vN - vS - R(3.0) * t1x2 * velY);
+            f1[FIDX(y, x, 2)] = vN - sym_N_S - asym_N_S;
+            f1[FIDX(y, x, 4)] = vS - sym_N_S + asym_N_S;
+
+            REAL sym_E_W = lambda_e_scaled * (vE + vW - fac1 * velX * velX - t1x2 * feq_common);
+            REAL asym_E_W = lambda_d_scaled * (vE - vW - R(3.0) * t1x2 * velX);
+            f1[FIDX(y, x, 1)] = vE - sym_E_W - asym_E_W;
+            f1[FIDX(y, x, 3)] = vW - sym_E_W + asym_E_W;
+        }
+}
+
+/* src/collision_bgk_improved.f90:24-107 bgk_improved_kernel.  The reference declares f1(ny,nx,0:8)
+ * (it ignores the padded leading dimension, SURVEY F9: only correct when ny % 16 == 0); the
+ * restatement indexes with ld, identical in that case. */
+void SFX(orc_collide_bgk_improved)(int nx, int ny, int ld, REAL *f1, REAL omega)
+{
+    const REAL one_third = R(1.0) / R(3.0), two_thirds = R(2.0) / R(3.0);
+    REAL fac = R(4.5) - R(2.25) * omega;
+    REAL omegabar = R(1.0) - omega;
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) {
+            REAL vC = f1[FIDX(y, x, 0)], vE = f1[FIDX(y, x, 1)], vN = f1[FIDX(y, x, 2)];
+            REAL vW = f1[FIDX(y, x, 3)], vS = f1[FIDX(y, x, 4)], vNE = f1[FIDX(y, x, 5)];
+            REAL vNW = f1[FIDX(y, x, 6)], vSW = f1[FIDX(y, x, 7)], vSE = f1[FIDX(y, x, 8)];
+            REAL rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
+            REAL invrho = R(1.0) / rho;
+            REAL sumX1 = vE + vNE + vSE;
+            REAL sumXN = vW + vNW + vSW;
+            REAL sumY1 = vN + vNE + vNW;
+            REAL sumYN = vS + vSE + vSW;
+            REAL m10 = invrho * (sumX1 - sumXN);
+            REAL m01 = invrho * (sumY1 - sumYN);
+            REAL u2 = m10 * m10;
+            REAL v2 = m01 * m01;
+            REAL m20 = invrho * (sumX1 + sumXN);
+            REAL m02 = invrho * (sumY1 + sumYN);
+            REAL Gx = fac * u2 * (m20 - one_third - u2);
+            REAL Gy = fac * v2 * (m02 - one_third - v2);
+            REAL X0 = -two_thirds + u2 + Gx;
+            REAL X1 = -(X0 + R(1.0) + m10) * R(0.5);
+            REAL XN = X1 + m10;
+            REAL Y0 = -two_thirds + v2 + Gy;
+            REAL Y1 = -(Y0 + R(1.0) + m01) * R(0.5);
+            REAL YN = Y1 + m01;
+            REAL rho_omega = rho * omega;
+            X0 = X0 * rho_omega;
+            X1 = X1 * rho_omega;
+            XN = XN * rho_omega;
+            f1[FIDX(y, x, 0)] = omegabar * vC + X0 * Y0;
+            f1[FIDX(y, x, 1)] = omegabar * vE + X1 * Y0;
+            f1[FIDX(y, x, 2)] = omegabar * vN + X0 * Y1;
+            f1[FIDX(y, x, 3)] = omegabar * vW + XN * Y0;
+            f1[FIDX(y, x, 4)] = omegabar * vS + X0 * YN;
+            f1[FIDX(y, x, 5)] = omegabar * vNE + X1 * Y1;
+            f1[FIDX(y, x, 6)] = omegabar * vNW + XN * Y1;
+            f1[FIDX(y, x, 7)] = omegabar * vSW + XN * YN;
+            f1[FIDX(y, x, 8)] = omegabar * vSE + X1 * YN;
+        }
+}
+
 /* ------------------------------------------------------------------ */
 /* src/collision_regularized.F90:40-202 rr_kernel_naive */
 void SFX(orc_collide_rr)(int nx, int ny, int ld, REAL *f1, REAL omega)
@@ -714,6 +811,8 @@ void SFX(orc_run)(int nx, int ny, int ld, REAL *f1, REAL *f2, int *idx, int sche
             case 0: SFX(orc_collide_bgk)(nx, ny, ld, fn, omega); break;
             case 1: SFX(orc_collide_trt)(nx, ny, ld, fn, omega, SFX(orc_lambda_d)(omega, trt_magic)); break;
             case 2: SFX(orc_collide_rr)(nx, ny, ld, fn, omega); break;
+            case 4: SFX(orc_collide_trt_split)(nx, ny, ld, fn, omega, SFX(orc_lambda_d)(omega, trt_magic)); break;
+            case 5: SFX(orc_collide_bgk_improved)(nx, ny, ld, fn, omega); break;
             default: SFX(orc_kernel_bgk)(nx, ny, ld, fn, omega); break;
             }
         } else {

@@ -6,7 +6,7 @@ the host-side mirror of the reference's Fortran module interfaces used by tests 
 Importing it requires the built library; there is no CPU fallback.
 """
 from . import capi  # noqa: F401  (raises ImportError when libplbm_b200.so is missing)
-from .capi import BGK, BGK_SPLIT, F32, F64, RR, TRT, PlbmError  # noqa: F401
+from .capi import BGK, BGK_IMPROVED, BGK_SPLIT, F32, F64, RR, TRT, TRT_SPLIT, PlbmError  # noqa: F401
 from .cases import TaylorGreen, VortexCase, steps_until, taylor_green_params, vortex_params  # noqa: F401
 from .lattice import *  # noqa: F401,F403
 from .plugin import SimPlugin  # noqa: F401

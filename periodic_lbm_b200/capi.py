@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplbm_b200.so")
 
 F64, F32 = 0, 1
-BGK, TRT, RR, BGK_SPLIT = 0, 1, 2, 3
+BGK, TRT, RR, BGK_SPLIT, TRT_SPLIT, BGK_IMPROVED = 0, 1, 2, 3, 4, 5
 STREAM_LBM, STREAM_FVM_BARDOW = 0, 1
 DIAG_MAX_SPEED, DIAG_MIN_SPEED, DIAG_SUM_RHO, DIAG_KINETIC, DIAG_COUNT = 0, 1, 2, 3, 4
 

@@ -42,7 +42,7 @@ int need_props(plbm_handle g)
     return PLBM_OK;
 }
 
-bool valid_model(int m) { return m == PLBM_BGK || m == PLBM_TRT || m == PLBM_RR || m == PLBM_BGK_SPLIT; }
+bool valid_model(int m) { return m >= PLBM_BGK && m <= PLBM_BGK_IMPROVED; }
 
 void swap_lattices(Grid& g)
 {
@@ -58,7 +58,7 @@ template <typename T> CollideParams<T> collide_params(const Grid& g, int model)
 {
     CollideParams<T> cp;
     cp.omega = (T)g.omega;
-    cp.lambda_d = model == PLBM_TRT ? lambda_d<T>((T)g.omega, (T)g.trt_magic) : T(0);
+    cp.lambda_d = (model == PLBM_TRT || model == PLBM_TRT_SPLIT) ? lambda_d<T>((T)g.omega, (T)g.trt_magic) : T(0);
     return cp;
 }
 
@@ -149,7 +149,8 @@ template <typename T> int step_fvm_t(Grid& g, int model, int nsteps)
     g.dugks_pending = false;  // lattice inew is overwritten below
     for (int s = 0; s < nsteps; ++s) {
         int rc;
-        if (g.variant == 0 && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
+        if (g.comm && (rc = comm_fv_exchange<T>(g, g.lat<T>(g.iold)))) return rc;  // slab: neighbours' boundary lines
+        if ((g.variant == 0 || g.comm) && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
             rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), 2, model, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
         else
             rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, model, cp, g.stream);
@@ -166,11 +167,12 @@ template <typename T> int step_dugks_t(Grid& g, bool dugks, int nsteps)
     for (int s = 0; s < nsteps; ++s) {
         int rc;
         g.dugks_pending = false;  // lattice inew is overwritten below
-        if (g.variant == 1) {  // reference structure: collide pass + stream pass
+        if (g.comm && (rc = comm_fv_exchange<T>(g, g.lat<T>(g.iold)))) return rc;  // slab: neighbours' boundary lines
+        if (g.variant == 1 && !g.comm) {  // reference structure: collide pass + stream pass
             rc = launch_dugks_collide<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), of, oh, g.stream);
             if (rc) return rc;
             rc = launch_dugks_stream<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, oc, dugks, g.stream);
-        } else if (g.variant == 0 && g.tmap_ok) {
+        } else if ((g.variant == 0 || g.comm) && g.tmap_ok) {
             // fused, TMA-pipelined: lattice iold (ftilde^n) is left untouched, inew receives ftilde^{n+1}.
             rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), dugks ? 0 : 1, M_NONE, (T)g.dt, of, oh, oc,
                                   CollideParams<T>{T(0), T(0)}, g.stream);
@@ -180,7 +182,7 @@ template <typename T> int step_dugks_t(Grid& g, bool dugks, int nsteps)
         }
         if (rc) return rc;
         swap_lattices(g);
-        if (g.variant != 1) {
+        if (!(g.variant == 1 && !g.comm)) {
             g.dugks_pending = true;
             g.dugks_pending_omega = (double)oh;
         }
@@ -450,8 +452,8 @@ int plbm_perform_step(plbm_handle g, int streaming, int collision, int nsteps)
         set_error("perform_step: bad streaming/collision id or nsteps");
         return PLBM_ERR_ARG;
     }
-    if (g->comm) {
-        set_error("perform_step(fvm_bardow): slab decomposition not supported for this scheme");
+    if (g->comm && !g->tmap_ok) {
+        set_error("perform_step(fvm_bardow): the slab decomposition needs the TMA tile kernel (no tensor map on this device)");
         return PLBM_ERR_ARG;
     }
     return DISPATCH(g, step_fvm_t<double>(*g, collision, nsteps), step_fvm_t<float>(*g, collision, nsteps));
@@ -486,8 +488,8 @@ int plbm_perform_dugks_step(plbm_handle g, int dugks, int nsteps)
         set_error("perform_dugks_step: bad nsteps");
         return PLBM_ERR_ARG;
     }
-    if (g->comm) {
-        set_error("perform_dugks_step: slab decomposition not supported for this scheme");
+    if (g->comm && !g->tmap_ok) {
+        set_error("perform_dugks_step: the slab decomposition needs the TMA tile kernel (no tensor map on this device)");
         return PLBM_ERR_ARG;
     }
     return DISPATCH(g, step_dugks_t<double>(*g, dugks != 0, nsteps), step_dugks_t<float>(*g, dugks != 0, nsteps));

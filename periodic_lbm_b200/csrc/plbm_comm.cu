@@ -95,6 +95,13 @@ struct Comm {
     void* send_hi = nullptr;                // line nx-1 of q = 1,5,8 -> rank hi
     void* halo_lo[2] = {nullptr, nullptr};  // from lo: q = 1,5,8
     void* halo_hi[2] = {nullptr, nullptr};  // from hi: q = 3,6,7
+    // FVM / DUGKS: all nine populations of one line per direction (not overlapped: those kernels are
+    // ALU-bound and the 9*ld-real message is microseconds)
+    void* send9_lo = nullptr;
+    void* send9_hi = nullptr;
+    void* halo9_lo = nullptr;
+    void* halo9_hi = nullptr;
+    cudaEvent_t ev9_packed = nullptr, ev9_done = nullptr;
     size_t bytes = 0;
     int parity = 0;        // halo slot holding the neighbours' lines of lattice `iold`
     bool halo_valid = false;
@@ -154,6 +161,12 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
     }
     PLBM_CUDA(cudaMalloc(&c->send_lo, c->bytes));
     PLBM_CUDA(cudaMalloc(&c->send_hi, c->bytes));
+    PLBM_CUDA(cudaMalloc(&c->send9_lo, 3 * c->bytes));
+    PLBM_CUDA(cudaMalloc(&c->send9_hi, 3 * c->bytes));
+    PLBM_CUDA(cudaMalloc(&c->halo9_lo, 3 * c->bytes));
+    PLBM_CUDA(cudaMalloc(&c->halo9_hi, 3 * c->bytes));
+    PLBM_CUDA(cudaEventCreateWithFlags(&c->ev9_packed, cudaEventDisableTiming));
+    PLBM_CUDA(cudaEventCreateWithFlags(&c->ev9_done, cudaEventDisableTiming));
     g.comm = c;
     g.nx_global = nx_global;
     g.x_offset = x_offset;
@@ -175,6 +188,13 @@ int comm_finalize(Grid& g)
     }
     if (c->send_lo) cudaFree(c->send_lo);
     if (c->send_hi) cudaFree(c->send_hi);
+    if (c->send9_lo) cudaFree(c->send9_lo);
+    if (c->send9_hi) cudaFree(c->send9_hi);
+    if (c->halo9_lo) cudaFree(c->halo9_lo);
+    if (c->halo9_hi) cudaFree(c->halo9_hi);
+    if (c->ev9_packed) cudaEventDestroy(c->ev9_packed);
+    if (c->ev9_done) cudaEventDestroy(c->ev9_done);
+    g.fv_halo_lo = g.fv_halo_hi = nullptr;
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -256,6 +276,33 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
     }
     return PLBM_OK;
 }
+
+// Exchange the boundary lines of all nine populations of lattice `f` with the ring neighbours and
+// publish them as g.fv_halo_lo / g.fv_halo_hi (stream-ordered: the caller's next kernel on g.stream
+// sees them).  rank r's line 0 goes to r-1's halo_hi, its line nx-1 to r+1's halo_lo.
+template <typename T> int comm_fv_exchange(Grid& g, const T* f)
+{
+    Comm* c = g.comm;
+    int rc;
+    const size_t bytes9 = 3 * c->bytes;
+    if ((rc = launch_halo_pack9<T>(g, f, (T*)c->send9_lo, (T*)c->send9_hi, g.stream))) return rc;
+    PLBM_CUDA(cudaEventRecord(c->ev9_packed, g.stream));
+    PLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev9_packed, 0));
+    PLBM_NCCL(g_nccl.GroupStart());
+    PLBM_NCCL(g_nccl.Send(c->send9_lo, bytes9, kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Send(c->send9_hi, bytes9, kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv(c->halo9_hi, bytes9, kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv(c->halo9_lo, bytes9, kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.GroupEnd());
+    PLBM_CUDA(cudaEventRecord(c->ev9_done, c->stream));
+    PLBM_CUDA(cudaStreamWaitEvent(g.stream, c->ev9_done, 0));
+    g.fv_halo_lo = c->halo9_lo;
+    g.fv_halo_hi = c->halo9_hi;
+    c->halo_valid = false;  // the LBM halo slots are stale after an FVM/DUGKS step
+    return PLBM_OK;
+}
+template int comm_fv_exchange<double>(Grid&, const double*);
+template int comm_fv_exchange<float>(Grid&, const float*);
 
 template int comm_lbm_steps<double>(Grid&, int, const CollideParams<double>&, int);
 template int comm_lbm_steps<float>(Grid&, int, const CollideParams<float>&, int);

@@ -124,6 +124,8 @@ int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, co
     case M_TRT: return launch_fv<T, MODE_BARDOW, M_TRT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
     case M_RR: return launch_fv<T, MODE_BARDOW, M_RR>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
     case M_BGK_SPLIT: return launch_fv<T, MODE_BARDOW, M_BGK_SPLIT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    case M_TRT_SPLIT: return launch_fv<T, MODE_BARDOW, M_TRT_SPLIT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+    case M_BGK_IMPROVED: return launch_fv<T, MODE_BARDOW, M_BGK_IMPROVED>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
     }
     set_error("fvm_bardow: unknown collision model");
     return PLBM_ERR_ARG;

@@ -78,6 +78,21 @@ __device__ __forceinline__ int pmod(int i, int n)
     return i < 0 ? i + n : i;
 }
 
+// Line (row 0) of population q at slow index gx, which may lie outside the slab: periodic wrap on a
+// single GPU, the ring neighbours' halo lines ([9][ld]) under a slab decomposition.
+template <typename T>
+__device__ __forceinline__ const T* wrapped_line(const T* fin, const T* hlo, const T* hhi, int q, int gx, int nx, int ld)
+{
+    if (gx < 0) {
+        if (hlo) return hlo + (size_t)q * ld;
+        gx = pmod(gx, nx);
+    } else if (gx >= nx) {
+        if (hhi) return hhi + (size_t)q * ld;
+        gx = pmod(gx, nx);
+    }
+    return fin + ((size_t)q * nx + gx) * (size_t)ld;
+}
+
 enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2 };
 
 // DUGKS keeps ONE raw stage (+ the fbar tile): the raw tile is dead after stage 1, so the next tile's
@@ -86,7 +101,8 @@ enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2 };
 template <typename T, int MODE, int MODEL, int MINB>
 __global__ void __launch_bounds__(FY* FX, MINB)
     k_fv_tma(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ fin, T* __restrict__ fout, int nx, int ny, int ld,
-             int nty, int ntiles, T dt, T omega_full, T omega_half, T omega_face, CollideParams<T> cp)
+             int nty, int ntiles, T dt, T omega_full, T omega_half, T omega_face, CollideParams<T> cp, const T* __restrict__ hlo,
+             const T* __restrict__ hhi)
 {
     using B = Box<T>;
     constexpr bool IS_DUGKS = MODE != MODE_BARDOW;
@@ -156,9 +172,9 @@ __global__ void __launch_bounds__(FY* FX, MINB)
 #pragma unroll
                 for (int q = 0; q < 9; ++q) b[q] = c[q * B::PLANE];
             } else {  // tile overhangs the grid: TMA zero-filled this cell, fetch the wrapped node
-                const int xs = pmod(x, nx), ys = pmod(y, ny);
+                const int ys = pmod(y, ny);
 #pragma unroll
-                for (int q = 0; q < 9; ++q) b[q] = fin[((size_t)q * nx + xs) * (size_t)ld + ys];
+                for (int q = 0; q < 9; ++q) b[q] = wrapped_line(fin, hlo, hhi, q, x, nx, ld)[ys];
             }
 #pragma unroll
             for (int q = 0; q < 9; ++q) fp[q] = b[q];
@@ -185,9 +201,9 @@ __global__ void __launch_bounds__(FY* FX, MINB)
                     for (int q = 0; q < 9; ++q) b[q] = c[q * B::PLANE];
                 }
             } else {
-                const int xs = pmod(gx, nx), ys = pmod(gy, ny);
+                const int ys = pmod(gy, ny);
 #pragma unroll
-                for (int q = 0; q < 9; ++q) b[q] = fin[((size_t)q * nx + xs) * (size_t)ld + ys];
+                for (int q = 0; q < 9; ++q) b[q] = wrapped_line(fin, hlo, hhi, q, gx, nx, ld)[ys];
             }
             if (IS_DUGKS) {
                 collide_bgk_split(b, omega_half);
@@ -260,7 +276,8 @@ int launch_one(const Grid& g, int which_src, const T* fin, T* fout, T dt, T of, 
     CUtensorMap map;
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
     memcpy(&map, g.tmap[which_src - 1], sizeof(map));
-    k_fv_tma<T, MODE, MODEL, MINB><<<nblocks, dim3(FY, FX), smem, s>>>(map, fin, fout, g.nx, g.ny, g.ld, nty, ntiles, dt, of, oh, oc, cp);
+    k_fv_tma<T, MODE, MODEL, MINB><<<nblocks, dim3(FY, FX), smem, s>>>(map, fin, fout, g.nx, g.ny, g.ld, nty, ntiles, dt, of, oh, oc, cp,
+                                                                       static_cast<const T*>(g.fv_halo_lo), static_cast<const T*>(g.fv_halo_hi));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
@@ -311,6 +328,8 @@ int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode,
     case M_TRT: return launch_one<T, MODE_BARDOW, M_TRT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
     case M_RR: return launch_one<T, MODE_BARDOW, M_RR, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
     case M_BGK_SPLIT: return launch_one<T, MODE_BARDOW, M_BGK_SPLIT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+    case M_TRT_SPLIT: return launch_one<T, MODE_BARDOW, M_TRT_SPLIT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+    case M_BGK_IMPROVED: return launch_one<T, MODE_BARDOW, M_BGK_IMPROVED, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
     }
     set_error("fv_tma: unknown collision model");
     return PLBM_ERR_ARG;

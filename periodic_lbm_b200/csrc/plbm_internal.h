@@ -55,6 +55,10 @@ struct Grid {
     // a (FY+2, FX+2, 9) box: used by the pipelined FVM/DUGKS tile kernel (plbm_fvm_tma.cu)
     alignas(64) unsigned char tmap[3][128];
     bool tmap_ok = false;
+    // neighbours' boundary lines of all nine populations ([9][ld]) for the FVM/DUGKS tile kernel under a
+    // slab decomposition; nullptr = periodic self-wrap
+    const void* fv_halo_lo = nullptr;
+    const void* fv_halo_hi = nullptr;
     // slab decomposition (single GPU: nx_global == nx, x_offset == 0)
     int nx_global = 0, x_offset = 0;
 
@@ -107,6 +111,9 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
 int comm_finalize(Grid& g);
 void comm_invalidate_halo(Grid& g);  // the lattices were modified behind the ring's back
 template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps);
+// one FVM/DUGKS halo exchange: all nine populations of lines 0 and nx-1 of `f` -> g.fv_halo_lo/hi
+template <typename T> int comm_fv_exchange(Grid& g, const T* f);
+template <typename T> int launch_halo_pack9(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s);
 
 }  // namespace plbm
 

@@ -171,6 +171,8 @@ template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream
         case M_TRT: return launch_v<T, M_TRT, true>(a, variant, s);
         case M_RR: return launch_v<T, M_RR, true>(a, variant, s);
         case M_BGK_SPLIT: return launch_v<T, M_BGK_SPLIT, true>(a, variant, s);
+        case M_TRT_SPLIT: return launch_v<T, M_TRT_SPLIT, true>(a, variant, s);
+        case M_BGK_IMPROVED: return launch_v<T, M_BGK_IMPROVED, true>(a, variant, s);
         }
     } else {
         switch (model) {
@@ -178,6 +180,8 @@ template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream
         case M_TRT: return launch_v<T, M_TRT, false>(a, variant, s);
         case M_RR: return launch_v<T, M_RR, false>(a, variant, s);
         case M_BGK_SPLIT: return launch_v<T, M_BGK_SPLIT, false>(a, variant, s);
+        case M_TRT_SPLIT: return launch_v<T, M_TRT_SPLIT, false>(a, variant, s);
+        case M_BGK_IMPROVED: return launch_v<T, M_BGK_IMPROVED, false>(a, variant, s);
         }
     }
     set_error("launch_lbm: unknown collision model");
@@ -208,6 +212,25 @@ template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
 }
+// all nine populations of line 0 (-> send_lo) and line nx-1 (-> send_hi): FVM / DUGKS halo
+template <typename T> __global__ void k_halo_pack9(const T* f, T* send_lo, T* send_hi, int nx, int ld)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * ld) return;
+    const int q = i / ld, y = i - q * ld;
+    send_lo[i] = f[((size_t)q * nx + 0) * (size_t)ld + y];
+    send_hi[i] = f[((size_t)q * nx + (nx - 1)) * (size_t)ld + y];
+}
+template <typename T> int launch_halo_pack9(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s)
+{
+    const int n = 9 * g.ld;
+    k_halo_pack9<T><<<(n + 255) / 256, 256, 0, s>>>(f, send_lo, send_hi, g.nx, g.ld);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    return PLBM_OK;
+}
+template int launch_halo_pack9<double>(const Grid&, const double*, double*, double*, cudaStream_t);
+template int launch_halo_pack9<float>(const Grid&, const float*, float*, float*, cudaStream_t);
 template int launch_halo_pack<double>(const Grid&, const double*, double*, double*, cudaStream_t);
 template int launch_halo_pack<float>(const Grid&, const float*, float*, float*, cudaStream_t);
 

@@ -23,7 +23,7 @@ namespace plbm {
 __host__ __device__ constexpr int cxi(int q) { return q == 1 || q == 5 || q == 8 ? 1 : (q == 3 || q == 6 || q == 7 ? -1 : 0); }
 __host__ __device__ constexpr int cyi(int q) { return q == 2 || q == 5 || q == 6 ? 1 : (q == 4 || q == 7 || q == 8 ? -1 : 0); }
 
-enum Model : int { M_NONE = -1, M_BGK = 0, M_TRT = 1, M_RR = 2, M_BGK_SPLIT = 3 };
+enum Model : int { M_NONE = -1, M_BGK = 0, M_TRT = 1, M_RR = 2, M_BGK_SPLIT = 3, M_TRT_SPLIT = 4, M_BGK_IMPROVED = 5 };
 
 template <typename T> struct K {
     // evaluated in working precision, like the Fortran `parameter`s with _wp literals
@@ -289,12 +289,105 @@ template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T om
     f[8] = feq[8] + omega_wd * vSE;
 }
 
+// trt_split (-DSPLIT, src/collision_trt.F90:162-290): the column-blocked variant.  Per node it differs
+// from trt_naive only in the axis pairs, where `fac1 * vel * vel` is (fac1*vel)*vel instead of
+// fac1*(vel*vel) -- a last-bit difference, reproduced.
+template <typename T> __device__ __forceinline__ void collide_trt_split(T (&f)[9], T lambda_e, T lambda_d)
+{
+    const T t0 = T(4) / T(9);
+    const T t1x2 = (T(1) / T(9)) * T(2);
+    const T t2x2 = (T(1) / T(36)) * T(2);
+    const T inv2csq2 = T(1) / (T(2) * (T(1) / T(3)) * (T(1) / T(3)));
+    const T fac1 = t1x2 * inv2csq2;
+    const T fac2 = t2x2 * inv2csq2;
+    T lambda_e_scaled = T(0.5) * lambda_e;
+    T lambda_d_scaled = T(0.5) * lambda_d;
+
+    T vC = f[0], vE = f[1], vN = f[2], vW = f[3], vS = f[4];
+    T vNE = f[5], vNW = f[6], vSW = f[7], vSE = f[8];
+    T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
+    T velX = (((vNE - vSW) + (vSE - vNW)) + (vE - vW));
+    T velY = (((vNE - vSW) + (vNW - vSE)) + (vN - vS));
+    T feq_common = rho - T(1.5) * (velX * velX + velY * velY);
+    f[0] = vC * (T(1) - lambda_e) + lambda_e * t0 * feq_common;
+
+    T velXPY = velX + velY;
+    T sym_NE_SW = lambda_e_scaled * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common);
+    T asym_NE_SW = lambda_d_scaled * (vNE - vSW - T(3) * t2x2 * velXPY);
+    f[5] = vNE - sym_NE_SW - asym_NE_SW;
+    f[7] = vSW - sym_NE_SW + asym_NE_SW;
+
+    T velXMY = velX - velY;
+    T sym_SE_NW = lambda_e_scaled * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common);
+    T asym_SE_NW = lambda_d_scaled * (vSE - vNW - T(3) * t2x2 * velXMY);
+    f[8] = vSE - sym_SE_NW - asym_SE_NW;
+    f[6] = vNW - sym_SE_NW + asym_SE_NW;
+
+    T sym_N_S = lambda_e_scaled * (vN + vS - fac1 * velY * velY - t1x2 * feq_common);
+    T asym_N_S = lambda_d_scaled * (vN - vS - T(3) * t1x2 * velY);
+    f[2] = vN - sym_N_S - asym_N_S;
+    f[4] = vS - sym_N_S + asym_N_S;
+
+    T sym_E_W = lambda_e_scaled * (vE + vW - fac1 * velX * velX - t1x2 * feq_common);
+    T asym_E_W = lambda_d_scaled * (vE - vW - T(3) * t1x2 * velX);
+    f[1] = vE - sym_E_W - asym_E_W;
+    f[3] = vW - sym_E_W + asym_E_W;
+}
+
+// collide_bgk_improved (src/collision_bgk_improved.f90:24-107): product-form BGK with a cubic
+// Galilean-invariance correction.  The reference kernel ignores the padded leading dimension
+// (identical when ny is a multiple of 16); the intended per-node arithmetic is kept.
+template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f)[9], T omega)
+{
+    const T one_third = T(1) / T(3), two_thirds = T(2) / T(3);
+    T fac = T(4.5) - T(2.25) * omega;
+    T omegabar = T(1) - omega;
+    T vC = f[0], vE = f[1], vN = f[2], vW = f[3], vS = f[4];
+    T vNE = f[5], vNW = f[6], vSW = f[7], vSE = f[8];
+
+    T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
+    T invrho = T(1) / rho;
+    T sumX1 = vE + vNE + vSE;
+    T sumXN = vW + vNW + vSW;
+    T sumY1 = vN + vNE + vNW;
+    T sumYN = vS + vSE + vSW;
+    T m10 = invrho * (sumX1 - sumXN);
+    T m01 = invrho * (sumY1 - sumYN);
+    T u2 = m10 * m10;
+    T v2 = m01 * m01;
+    T m20 = invrho * (sumX1 + sumXN);
+    T m02 = invrho * (sumY1 + sumYN);
+    T Gx = fac * u2 * (m20 - one_third - u2);
+    T Gy = fac * v2 * (m02 - one_third - v2);
+    T X0 = -two_thirds + u2 + Gx;
+    T X1 = -(X0 + T(1) + m10) * T(0.5);
+    T XN = X1 + m10;
+    T Y0 = -two_thirds + v2 + Gy;
+    T Y1 = -(Y0 + T(1) + m01) * T(0.5);
+    T YN = Y1 + m01;
+    T rho_omega = rho * omega;
+    X0 = X0 * rho_omega;
+    X1 = X1 * rho_omega;
+    XN = XN * rho_omega;
+    f[0] = omegabar * vC + X0 * Y0;
+    f[1] = omegabar * vE + X1 * Y0;
+    f[2] = omegabar * vN + X0 * Y1;
+    f[3] = omegabar * vW + XN * Y0;
+    f[4] = omegabar * vS + X0 * YN;
+    f[5] = omegabar * vNE + X1 * Y1;
+    f[6] = omegabar * vNW + XN * Y1;
+    f[7] = omegabar * vSW + XN * YN;
+    f[8] = omegabar * vSE + X1 * YN;
+}
+
 template <typename T, int MODEL> __device__ __forceinline__ void collide(T (&f)[9], const CollideParams<T>& p)
 {
     if (MODEL == M_BGK) collide_bgk(f, p.omega);
     else if (MODEL == M_TRT) collide_trt(f, p.omega, p.lambda_d);
     else if (MODEL == M_RR) collide_rr(f, p.omega);
     else if (MODEL == M_BGK_SPLIT) collide_bgk_split(f, p.omega);
+    else if (MODEL == M_TRT_SPLIT) collide_trt_split(f, p.omega, p.lambda_d);
+    else if (MODEL == M_BGK_IMPROVED) collide_bgk_improved(f, p.omega);
 }
 
 // 2nd-order, half-step back-traced face reconstruction of one population from its 3x3

@@ -41,7 +41,11 @@ contains
    subroutine collide_trt(grid)
       class(lattice_grid), intent(inout) :: grid
       call plbm_check(plbm_set_omega(grid%dev, real(grid%omega,c_double)), "set_omega")
+#if SPLIT
+      call plbm_check(plbm_collide(grid%dev, 4_c_int), "collide_trt")   ! PLBM_TRT_SPLIT
+#else
       call plbm_check(plbm_collide(grid%dev, PLBM_TRT), "collide_trt")
+#endif
    end subroutine
 end module collision_trt
 
@@ -59,3 +63,18 @@ contains
       call plbm_check(plbm_collide(grid%dev, PLBM_RR), "collide_rr")
    end subroutine
 end module collision_regularized
+
+module collision_bgk_improved
+   use, intrinsic :: iso_c_binding
+   use fvm_bardow, only: lattice_grid
+   use plbm_c
+   implicit none
+   private
+   public :: collide_bgk_improved
+contains
+   subroutine collide_bgk_improved(grid)
+      class(lattice_grid), intent(inout) :: grid
+      call plbm_check(plbm_set_omega(grid%dev, real(grid%omega,c_double)), "set_omega")
+      call plbm_check(plbm_collide(grid%dev, 5_c_int), "collide_bgk_improved")   ! PLBM_BGK_IMPROVED
+   end subroutine
+end module collision_bgk_improved

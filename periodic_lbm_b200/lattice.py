@@ -31,6 +31,7 @@ __all__ = [
     "LatticeGrid", "alloc_grid", "dealloc_grid", "set_properties", "set_pdf_to_equilibrium",
     "perform_step", "perform_lbm_step", "perform_triple_step", "perform_dugks_step", "update_macros",
     "lbm_stream", "stream_fvm_bardow", "collide_bgk", "collide_trt", "collide_rr", "collide_bgk_split",
+    "collide_trt_split", "collide_bgk_improved",
     "dugks_collide", "dugks_stream", "vorticity_2nd", "vorticity_4th", "lambda_d", "magic_number",
     "cx", "cy", "csqr",
 ]
@@ -191,6 +192,16 @@ def collide_rr(grid):
     check(lib.plbm_collide(grid._h, capi.RR), "collide_rr")
 
 
+def collide_trt_split(grid):
+    """collide_trt as built with -DSPLIT (trt_split, src/collision_trt.F90:162-290)."""
+    check(lib.plbm_collide(grid._h, capi.TRT_SPLIT), "collide_trt_split")
+
+
+def collide_bgk_improved(grid):
+    """collide_bgk_improved (src/collision_bgk_improved.f90:16-107)."""
+    check(lib.plbm_collide(grid._h, capi.BGK_IMPROVED), "collide_bgk_improved")
+
+
 def collide_bgk_split(grid):
     """collide_bgk as built with -DSPLIT (bgk_kernel_cache, src/collision_bgk.F90:84-176)."""
     check(lib.plbm_collide(grid._h, capi.BGK_SPLIT), "collide_bgk_split")
@@ -204,7 +215,8 @@ def dugks_stream(grid):
     check(lib.plbm_dugks_stream(grid._h, int(grid.dugks)), "dugks_stream")
 
 
-_COLLISION_ID = {collide_bgk: capi.BGK, collide_trt: capi.TRT, collide_rr: capi.RR, collide_bgk_split: capi.BGK_SPLIT}
+_COLLISION_ID = {collide_bgk: capi.BGK, collide_trt: capi.TRT, collide_rr: capi.RR, collide_bgk_split: capi.BGK_SPLIT,
+                 collide_trt_split: capi.TRT_SPLIT, collide_bgk_improved: capi.BGK_IMPROVED}
 
 
 def _swap(grid):

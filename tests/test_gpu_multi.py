@@ -31,11 +31,21 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed):
         idb = idq.get(timeout=120)
     check(lib.plbm_comm_init(g._h, C.create_string_buffer(idb, 128), rank, world, nxg, sl.x_offset), "comm_init")
     g.upload_f(g.iold, np.ascontiguousarray(f0[:, sl.x_offset:sl.x_end]))
-    g.collision = {0: p.collide_bgk, 1: p.collide_trt, 2: p.collide_rr}[coll_id]
-    g.streaming = p.lbm_stream
-    # two calls: exercises the "halo already in flight" path between calls
-    p.perform_lbm_step(g, steps // 2)
-    p.perform_lbm_step(g, steps - steps // 2)
+    g.collision = {0: p.collide_bgk, 1: p.collide_trt, 2: p.collide_rr}[coll_id % 10]
+    if coll_id >= 20:      # DUGKS (9-population halo, TMA tile kernel)
+        p.set_properties(g, 0.02, 0.3, 0.25)
+        g.collision = g.streaming = None
+        p.perform_dugks_step(g, steps // 2)
+        p.perform_dugks_step(g, steps - steps // 2)
+    elif coll_id >= 10:    # Bardow FVM + collision
+        p.set_properties(g, 0.02, 0.3, 0.25)
+        g.streaming = p.stream_fvm_bardow
+        p.perform_step(g, steps)
+    else:
+        g.streaming = p.lbm_stream
+        # two calls: exercises the "halo already in flight" path between calls
+        p.perform_lbm_step(g, steps // 2)
+        p.perform_lbm_step(g, steps - steps // 2)
     got = g.download_f(g.iold)
     p.update_macros(g, lagged=False)
     outq.put((rank, sl.x_offset, got, g.rho.copy()))
@@ -44,7 +54,8 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed):
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-@pytest.mark.parametrize("nxg,ny,steps,coll_id", [(64, 64, 9, 0), (37, 53, 8, 2), (130, 128, 11, 1), (4, 32, 5, 0)])
+@pytest.mark.parametrize("nxg,ny,steps,coll_id", [(64, 64, 9, 0), (37, 53, 8, 2), (130, 128, 11, 1), (4, 32, 5, 0),
+                                                  (64, 64, 6, 20), (37, 53, 5, 20), (70, 96, 5, 12)])
 def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec):
     world = min(plbm.device_count(), 4 if nxg >= 8 else 2)
     if world < 2:
@@ -71,9 +82,18 @@ def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec):
     g = plbm.alloc_grid(nxg, ny, precision=prec)
     plbm.set_properties(g, 0.02, 1.0, 0.25)
     g.upload_f(g.iold, f0)
-    g.collision = {0: plbm.collide_bgk, 1: plbm.collide_trt, 2: plbm.collide_rr}[coll_id]
-    g.streaming = plbm.lbm_stream
-    plbm.perform_lbm_step(g, steps)
+    g.collision = {0: plbm.collide_bgk, 1: plbm.collide_trt, 2: plbm.collide_rr}[coll_id % 10]
+    if coll_id >= 20:
+        plbm.set_properties(g, 0.02, 0.3, 0.25)
+        g.collision = g.streaming = None
+        plbm.perform_dugks_step(g, steps)
+    elif coll_id >= 10:
+        plbm.set_properties(g, 0.02, 0.3, 0.25)
+        g.streaming = plbm.stream_fvm_bardow
+        plbm.perform_step(g, steps)
+    else:
+        g.streaming = plbm.lbm_stream
+        plbm.perform_lbm_step(g, steps)
     single = g.download_f(g.iold)
     plbm.dealloc_grid(g)
     assert np.array_equal(multi[:, :, :ny], single[:, :, :ny])

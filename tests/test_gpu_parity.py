@@ -30,6 +30,28 @@ def make_pair(plbm, nx, ny, prec, nu=0.02, dt=1.0, magic=0.25, seed=None):
     return og, g
 
 
+def collisions(plbm):
+    """(device procedure, oracle collision id) for every collision operator of the reference."""
+    return ((plbm.collide_bgk, Oracle.BGK), (plbm.collide_trt, Oracle.TRT), (plbm.collide_rr, Oracle.RR),
+            (plbm.collide_bgk_split, Oracle.BGK_SPLIT), (plbm.collide_trt_split, Oracle.TRT_SPLIT),
+            (plbm.collide_bgk_improved, Oracle.BGK_IMPROVED))
+
+
+def oracle_collide(o, f, ny, p, ocoll):
+    if ocoll == Oracle.BGK:
+        o.collide_bgk(f, ny, p["omega"])
+    elif ocoll == Oracle.TRT:
+        o.collide_trt(f, ny, p["omega"], p["trt_magic"])
+    elif ocoll == Oracle.RR:
+        o.collide_rr(f, ny, p["omega"])
+    elif ocoll == Oracle.BGK_SPLIT:
+        o.kernel_bgk(f, ny, p["omega"])
+    elif ocoll == Oracle.TRT_SPLIT:
+        o.collide_trt_split(f, ny, p["omega"], p["trt_magic"])
+    else:
+        o.collide_bgk_improved(f, ny, p["omega"])
+
+
 def assert_same_lattice(g, og, which_g, which_o, ny):
     got = g.download_f(which_g)[:, :, :ny]
     want = og.lattice(which_o)[:, :, :ny]
@@ -71,22 +93,13 @@ def test_set_pdf_to_equilibrium_and_macros(plbm, nx, ny, prec):
 @pytest.mark.parametrize("nx,ny", SIZES)
 def test_unfused_stream_then_collide_entries(plbm, nx, ny, prec):
     """lbm_stream, collide_bgk/trt/rr as separate calls + swap == oracle, bitwise."""
-    for coll, ocoll in ((plbm.collide_bgk, Oracle.BGK), (plbm.collide_trt, Oracle.TRT), (plbm.collide_rr, Oracle.RR),
-                        (plbm.collide_bgk_split, Oracle.BGK_SPLIT)):
+    for coll, ocoll in collisions(plbm):
         og, g = make_pair(plbm, nx, ny, prec)
         plbm.lbm_stream(g)
         og.o.lbm_stream(og.lattice(og.iold), og.lattice(og.inew), ny)
         assert_same_lattice(g, og, g.inew, og.inew, ny)
         coll(g)
-        p = og.props
-        if ocoll == Oracle.BGK:
-            og.o.collide_bgk(og.lattice(og.inew), ny, p["omega"])
-        elif ocoll == Oracle.TRT:
-            og.o.collide_trt(og.lattice(og.inew), ny, p["omega"], p["trt_magic"])
-        elif ocoll == Oracle.RR:
-            og.o.collide_rr(og.lattice(og.inew), ny, p["omega"])
-        else:
-            og.o.kernel_bgk(og.lattice(og.inew), ny, p["omega"])
+        oracle_collide(og.o, og.lattice(og.inew), ny, og.props, ocoll)
         assert_same_lattice(g, og, g.inew, og.inew, ny)
         plbm.dealloc_grid(g)
 
@@ -96,8 +109,7 @@ def test_unfused_stream_then_collide_entries(plbm, nx, ny, prec):
 @pytest.mark.parametrize("nx,ny", SIZES)
 def test_fused_lbm_steps(plbm, nx, ny, prec, variant):
     """perform_lbm_step (fused kernel), 7 steps, every collision model, every load variant."""
-    for coll, ocoll in ((plbm.collide_bgk, Oracle.BGK), (plbm.collide_trt, Oracle.TRT), (plbm.collide_rr, Oracle.RR),
-                        (plbm.collide_bgk_split, Oracle.BGK_SPLIT)):
+    for coll, ocoll in collisions(plbm):
         og, g = make_pair(plbm, nx, ny, prec)
         g.set_variant(variant)
         g.collision, g.streaming = coll, plbm.lbm_stream
@@ -115,12 +127,24 @@ def test_fused_lbm_steps(plbm, nx, ny, prec, variant):
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("nx,ny", [(64, 64), (67, 67), (5, 5), (130, 130)])
 def test_fvm_bardow_steps(plbm, nx, ny, prec):
-    """perform_step with stream_fvm_bardow + collide_bgk (what app/main_vortex.f90 runs)."""
+    """perform_step with stream_fvm_bardow + collide_bgk (what app/main_vortex.f90 runs), TMA-pipelined
+    (variant 0) and plain-load (variant 2) tile kernels, then every other collision operator."""
+    for variant in (0, 2):
+        og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+        g.set_variant(variant)
+        g.collision, g.streaming = plbm.collide_bgk, plbm.stream_fvm_bardow
+        plbm.perform_step(g, 5)
+        og.run(Oracle.SCHEME_FVM_BARDOW, Oracle.BGK, 5)
+        assert_same_lattice(g, og, g.iold, og.iold, ny)
+        plbm.dealloc_grid(g)
+    for coll, ocoll in collisions(plbm)[1:]:
+        og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+        g.collision, g.streaming = coll, plbm.stream_fvm_bardow
+        plbm.perform_step(g, 3)
+        og.run(Oracle.SCHEME_FVM_BARDOW, ocoll, 3)
+        assert_same_lattice(g, og, g.iold, og.iold, ny)
+        plbm.dealloc_grid(g)
     og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
-    g.collision, g.streaming = plbm.collide_bgk, plbm.stream_fvm_bardow
-    plbm.perform_step(g, 5)
-    og.run(Oracle.SCHEME_FVM_BARDOW, Oracle.BGK, 5)
-    assert_same_lattice(g, og, g.iold, og.iold, ny)
     # unfused entry point
     plbm.stream_fvm_bardow(g)
     og.o.stream_fvm_bardow(og.lattice(og.iold), og.lattice(og.inew), ny, og.props["dt"])
