@@ -134,6 +134,16 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
 {
     g.dugks_pending = false;  // lattice inew is overwritten below
     if (g.comm) return comm_lbm_steps<T>(g, model, collide_params<T>(g, model), nsteps);
+    if (g.variant == 0 && nsteps >= 4) {
+        // small grids: all the steps in ONE launch, lattices resident in the shared memory of a cluster
+        bool done = false;
+        int rc = try_lbm_cluster_steps<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), model, collide_params<T>(g, model), nsteps, &done, g.stream);
+        if (rc) return rc;
+        if (done) {
+            if (nsteps & 1) swap_lattices(g);
+            return PLBM_OK;
+        }
+    }
     for (int s = 0; s < nsteps; ++s) {
         LbmArgs<T> a = lbm_args<T>(g, g.iold, g.inew, model);
         int rc = launch_lbm<T>(a, model, true, g.variant, g.stream);

@@ -98,6 +98,10 @@ template <typename T> int launch_dugks_stream(const Grid& g, const T* ft, T* fp,
 template <typename T>
 int launch_dugks_fused(const Grid& g, const T* fin, T* fout, T dt, T omega_full, T omega_half, T omega_face, bool dugks,
                        cudaStream_t s);
+// cluster-resident multi-step kernel for grids that fit in the shared memory of one cluster (plbm_small.cu)
+template <typename T>
+int try_lbm_cluster_steps(const Grid& g, T* f_iold, T* f_inew, int model, const CollideParams<T>& cp, int nsteps, bool* done,
+                          cudaStream_t s);
 // TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice
 int make_tensor_maps(Grid& g);
 template <typename T>
