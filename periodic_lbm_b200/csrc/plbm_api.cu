@@ -145,6 +145,13 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         }
     }
     for (int s = 0; s < nsteps; ++s) {
+        if (g.variant == 3 && g.tmap_ok && model <= PLBM_RR) {  // measurement variant: TMA-staged halo tile
+            int rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), 3, model, T(0), T(0), T(0), T(0),
+                                      collide_params<T>(g, model), g.stream);
+            if (rc) return rc;
+            swap_lattices(g);
+            continue;
+        }
         LbmArgs<T> a = lbm_args<T>(g, g.iold, g.inew, model);
         int rc = launch_lbm<T>(a, model, true, g.variant, g.stream);
         if (rc) return rc;

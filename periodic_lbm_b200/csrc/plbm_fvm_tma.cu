@@ -19,7 +19,10 @@ namespace plbm {
 
 namespace {
 
-constexpr int FY = 32, FX = 8;
+#ifndef PLBM_TMA_FX
+#define PLBM_TMA_FX 8
+#endif
+constexpr int FY = 32, FX = PLBM_TMA_FX;
 constexpr int GY = FY + 2, GX = FX + 2;
 constexpr int NHALO = GX * GY - FX * FY;
 constexpr int FPITCH = GY + 1;  // fbar tile pitch (DUGKS)
@@ -93,7 +96,10 @@ __device__ __forceinline__ const T* wrapped_line(const T* fin, const T* hlo, con
     return fin + ((size_t)q * nx + gx) * (size_t)ld;
 }
 
-enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2 };
+// MODE_LBM: the standard pull stream + collide with the halo tile staged by TMA (variant 3 of
+// perform_lbm_step).  It exists to MEASURE the north-star's "TMA staging of the row halo" against the
+// direct-load kernel k_lbm: staging cannot reduce the 144 B/node and over-fetches the halo ring.
+enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2, MODE_LBM = 3 };
 
 // DUGKS keeps ONE raw stage (+ the fbar tile): the raw tile is dead after stage 1, so the next tile's
 // TMA is issued right after the stage-1 barrier and lands during stage 2 (the long phase).  Bardow
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(FY* FX, MINB)
              const T* __restrict__ hhi)
 {
     using B = Box<T>;
-    constexpr bool IS_DUGKS = MODE != MODE_BARDOW;
+    constexpr bool IS_DUGKS = MODE == MODE_DUGKS || MODE == MODE_DUGKS_OFF;
     extern __shared__ __align__(128) unsigned char smem[];
     T* const raw0 = reinterpret_cast<T*>(smem);
     T* const raw1 = reinterpret_cast<T*>(smem + B::STAGE_BYTES);  // Bardow only
@@ -224,9 +230,14 @@ __global__ void __launch_bounds__(FY* FX, MINB)
             if (IS_DUGKS) {
                 const T* c0 = fbar + (tx + 1) * FPITCH + (ty + 1);
                 flux_update<T, MODE == MODE_DUGKS, FPITCH, GX * FPITCH>(c0, dt, omega_face, fp);
-            } else {
+            } else if (MODE == MODE_BARDOW) {
                 const T* c0 = rw + (tx + 1) * B::BY + (ty + 1) + B::COL0;
                 flux_update<T, false, B::BY, B::PLANE>(c0, dt, omega_face, fp);
+                if (MODEL != M_NONE) collide<T, MODEL>(fp, cp);
+            } else {  // MODE_LBM: fdst(y,x,q) = fsrc(y-cy, x-cx, q) from the staged tile, then collide
+                const T* c0 = rw + (tx + 1) * B::BY + (ty + 1) + B::COL0;
+#pragma unroll
+                for (int q = 1; q < 9; ++q) fp[q] = c0[q * B::PLANE - cxi(q) * B::BY - cyi(q)];
                 if (MODEL != M_NONE) collide<T, MODEL>(fp, cp);
             }
 #pragma unroll
@@ -262,7 +273,7 @@ template <typename T, int MODE, int MODEL, int MINB>
 int launch_one(const Grid& g, int which_src, const T* fin, T* fout, T dt, T of, T oh, T oc, const CollideParams<T>& cp, cudaStream_t s)
 {
     using B = Box<T>;
-    constexpr bool IS_DUGKS = MODE != MODE_BARDOW;
+    constexpr bool IS_DUGKS = MODE == MODE_DUGKS || MODE == MODE_DUGKS_OFF;
     const int nty = (g.ny + FY - 1) / FY, ntx = (g.nx + FX - 1) / FX;
     const int ntiles = nty * ntx;
     const size_t smem = (IS_DUGKS ? (size_t)B::STAGE_BYTES + B::FBAR_BYTES : 2 * (size_t)B::STAGE_BYTES) + 16;
@@ -319,9 +330,19 @@ int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode,
     const int minb = minb_env ? minb_env : (sizeof(T) == 8 ? 1 : 2);
     if (mode == MODE_DUGKS) {
         if (minb == 1) return launch_one<T, MODE_DUGKS, M_NONE, 1>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        if (minb == 3) return launch_one<T, MODE_DUGKS, M_NONE, 3>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        if (minb == 4) return launch_one<T, MODE_DUGKS, M_NONE, 4>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
         return launch_one<T, MODE_DUGKS, M_NONE, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
     }
     if (mode == MODE_DUGKS_OFF) return launch_one<T, MODE_DUGKS_OFF, M_NONE, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+    if (mode == MODE_LBM) {
+        switch (model) {
+        case M_BGK: return launch_one<T, MODE_LBM, M_BGK, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        case M_TRT: return launch_one<T, MODE_LBM, M_TRT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        case M_RR: return launch_one<T, MODE_LBM, M_RR, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        default: set_error("fv_tma: the TMA-staged LBM variant supports bgk, trt, rr"); return PLBM_ERR_ARG;
+        }
+    }
     switch (model) {
     case M_NONE: return launch_one<T, MODE_BARDOW, M_NONE, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
     case M_BGK: return launch_one<T, MODE_BARDOW, M_BGK, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);

@@ -104,11 +104,12 @@ def test_unfused_stream_then_collide_entries(plbm, nx, ny, prec):
         plbm.dealloc_grid(g)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("nx,ny", SIZES)
 def test_fused_lbm_steps(plbm, nx, ny, prec, variant):
-    """perform_lbm_step (fused kernel), 7 steps, every collision model, every load variant."""
+    """perform_lbm_step (fused kernel), 7 steps, every collision model, every load variant
+    (0 direct loads [+ cluster-resident kernel on small grids], 1 shuffle, 2 scalar, 3 TMA-staged tile)."""
     for coll, ocoll in collisions(plbm):
         og, g = make_pair(plbm, nx, ny, prec)
         g.set_variant(variant)

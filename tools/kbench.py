@@ -76,7 +76,7 @@ if __name__ == "__main__":
     if "lbm" in a.what:
         for prec in ("f64", "f32"):
             for coll in ("bgk", "trt", "rr"):
-                for variant in (0, 1, 2):
+                for variant in (0, 1, 2, 3):
                     rows.append(run(n, n, prec, "lbm", coll, variant, a.steps))
                     print(json.dumps(rows[-1]), flush=True)
     if "fvm" in a.what:
