@@ -19,6 +19,36 @@ template <typename T, int V> struct alignas(sizeof(T) * V) Pack {
     T v[V];
 };
 
+// 128-bit accesses with a streaming (evict-first) hint: LM = 2 measurement variant
+template <typename T, int V> __device__ __forceinline__ Pack<T, V> ld_stream(const T* p)
+{
+    Pack<T, V> r;
+    if constexpr (V == 2 && sizeof(T) == 8) {
+        double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+        r.v[0] = v.x;
+        r.v[1] = v.y;
+    } else if constexpr (V == 4 && sizeof(T) == 4) {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        r.v[0] = v.x;
+        r.v[1] = v.y;
+        r.v[2] = v.z;
+        r.v[3] = v.w;
+    } else {
+        r = *reinterpret_cast<const Pack<T, V>*>(p);
+    }
+    return r;
+}
+template <typename T, int V> __device__ __forceinline__ void st_stream(T* p, const Pack<T, V>& r)
+{
+    if constexpr (V == 2 && sizeof(T) == 8) {
+        __stcs(reinterpret_cast<double2*>(p), make_double2(r.v[0], r.v[1]));
+    } else if constexpr (V == 4 && sizeof(T) == 4) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+    } else {
+        *reinterpret_cast<Pack<T, V>*>(p) = r;
+    }
+}
+
 // halo slot of a population inside halo_lo (cx=+1: q=1,5,8) / halo_hi (cx=-1: q=3,6,7)
 __host__ __device__ constexpr int halo_slot(int q) { return (q == 1 || q == 3) ? 0 : ((q == 5 || q == 6) ? 1 : 2); }
 
@@ -45,10 +75,10 @@ __device__ __forceinline__ void load_pop(const LbmArgs<T>& a, int x, int y0, boo
     constexpr int cy = cyi(Q);
     const T* line = src_line<T, Q>(a, x);
     if (cy == 0) {
-        Pack<T, V> p = *reinterpret_cast<const Pack<T, V>*>(line + y0);
+        Pack<T, V> p = LM == 2 ? ld_stream<T, V>(line + y0) : *reinterpret_cast<const Pack<T, V>*>(line + y0);
 #pragma unroll
         for (int v = 0; v < V; ++v) f[v][Q] = p.v[v];
-    } else if (LM == 0 || V == 1) {
+    } else if (LM == 0 || LM == 2 || V == 1) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             int ys = y0 + v - cy;
@@ -78,8 +108,11 @@ __device__ __forceinline__ void load_pop(const LbmArgs<T>& a, int x, int y0, boo
 
 // STREAM = true : pull from src neighbours (fused stream+collide, or stream only if MODEL = M_NONE)
 // STREAM = false: in-place collision on dst (the reference's separate collide_* entry points)
-template <typename T, int MODEL, bool STREAM, int V, int LM>
-__global__ void __launch_bounds__(256) k_lbm(const LbmArgs<T> a)
+// PRE = true additionally stores the streamed, pre-collision PDFs to a.pre (perform_triple_step); it is a
+// separate instantiation because the extra store block costs the hot kernels registers (RR fp64: 84 vs 80
+// registers = 2 instead of 3 resident blocks per SM, measured -24 %).
+template <typename T, int MODEL, bool STREAM, int V, int LM, bool PRE>
+__global__ void __launch_bounds__(256, 3) k_lbm(const LbmArgs<T> a)
 {
     const int ldv = a.ld / V;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,7 +121,7 @@ __global__ void __launch_bounds__(256) k_lbm(const LbmArgs<T> a)
     int y0 = ((int)(g - (size_t)xrel * ldv)) * V;
     const bool active = (x < a.x_end) && (y0 < a.ny);
     if (!active) {  // keep the lane alive for the shuffles, on a harmless address
-        if (LM == 0 || V == 1) return;
+        if (LM == 0 || LM == 2 || V == 1) return;
         x = a.x_begin;
         y0 = 0;
     }
@@ -114,7 +147,7 @@ __global__ void __launch_bounds__(256) k_lbm(const LbmArgs<T> a)
     }
     if (!active) return;
 
-    if (STREAM && a.pre != nullptr) {  // perform_triple_step keeps the pre-collision lattice
+    if (STREAM && PRE) {  // perform_triple_step keeps the pre-collision lattice
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
             Pack<T, V> p;
@@ -134,17 +167,23 @@ __global__ void __launch_bounds__(256) k_lbm(const LbmArgs<T> a)
         Pack<T, V> p;
 #pragma unroll
         for (int v = 0; v < V; ++v) p.v[v] = f[v][q];
-        *reinterpret_cast<Pack<T, V>*>(a.dst + ((size_t)q * a.nx + x) * (size_t)a.ld + y0) = p;
+        if (LM == 2)
+            st_stream<T, V>(a.dst + ((size_t)q * a.nx + x) * (size_t)a.ld + y0, p);
+        else
+            *reinterpret_cast<Pack<T, V>*>(a.dst + ((size_t)q * a.nx + x) * (size_t)a.ld + y0) = p;
     }
 }
 
-template <typename T, int MODEL, bool STREAM, int V, int LM> static int launch_one(const LbmArgs<T>& a, cudaStream_t s)
+template <typename T, int MODEL, bool STREAM, int V, int LM> static int launch_one(const LbmArgs<T>& a, cudaStream_t s, bool pre = false)
 {
     const size_t nthreads = (size_t)(a.x_end - a.x_begin) * (size_t)(a.ld / V);
     if (nthreads == 0) return PLBM_OK;
     const int block = 256;
     const size_t nblocks = (nthreads + block - 1) / block;
-    k_lbm<T, MODEL, STREAM, V, LM><<<(unsigned)nblocks, block, 0, s>>>(a);
+    if (pre)
+        k_lbm<T, MODEL, STREAM, V, 0, STREAM><<<(unsigned)nblocks, block, 0, s>>>(a);  // element-load variant only
+    else
+        k_lbm<T, MODEL, STREAM, V, LM, false><<<(unsigned)nblocks, block, 0, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
@@ -157,8 +196,10 @@ template <typename T, int MODEL, bool STREAM> static int launch_v(const LbmArgs<
     // variant 0 (default) = 128-bit vectors, element loads for the six y-shifted populations
     // (measured fastest on B200: ~1.05x the measured copy bandwidth, profiles/);
     // variant 1 = 128-bit vectors + warp shuffle of the aligned vector; 2 = scalar (1 node/thread)
+    if (a.pre != nullptr) return vec_ok ? launch_one<T, MODEL, STREAM, VMAX, 0>(a, s, true) : launch_one<T, MODEL, STREAM, 1, 0>(a, s, true);
     if (!vec_ok || variant == 2) return launch_one<T, MODEL, STREAM, 1, 0>(a, s);
     if (variant == 1) return launch_one<T, MODEL, STREAM, VMAX, 1>(a, s);
+    if (variant == 4) return launch_one<T, MODEL, STREAM, VMAX, 2>(a, s);  // streaming cache hints (measurement)
     return launch_one<T, MODEL, STREAM, VMAX, 0>(a, s);
 }
 
