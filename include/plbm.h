@@ -50,8 +50,11 @@ enum plbm_collision {
 };
 
 /* streaming schemes: lbm_stream (src/periodic_lbm.f90:32), stream_fvm_bardow
- * (src/fvm_bardow.F90:393). */
-enum plbm_streaming { PLBM_STREAM_LBM = 0, PLBM_STREAM_FVM_BARDOW = 1 };
+ * (src/fvm_bardow.F90:393), stream_fdm_bardow (:511, default build: Lax-Wendroff with plain central
+ * differences; the FDM_WLS / FDM_ISO cpp variants are not built), stream_fdm_sofonea (:688). */
+enum plbm_streaming {
+    PLBM_STREAM_LBM = 0, PLBM_STREAM_FVM_BARDOW = 1, PLBM_STREAM_FDM_BARDOW = 2, PLBM_STREAM_FDM_SOFONEA = 3
+};
 
 enum plbm_status {
     PLBM_OK = 0,
@@ -102,7 +105,8 @@ int plbm_set_pdf_to_equilibrium(plbm_handle grid, const void* rho, const void* u
 /* perform_lbm_step (src/periodic_lbm.f90:15-29): lbm_stream + collision + swap, fused
  * into one pull-scheme kernel; nsteps >= 1 steps per call. */
 int plbm_perform_lbm_step(plbm_handle grid, int collision, int nsteps);
-/* perform_step (src/fvm_bardow.F90:307-320) with streaming = stream_fvm_bardow. */
+/* perform_step (src/fvm_bardow.F90:307-320) with streaming = stream_fvm_bardow, stream_fdm_bardow
+ * or stream_fdm_sofonea (PLBM_STREAM_LBM forwards to plbm_perform_lbm_step). */
 int plbm_perform_step(plbm_handle grid, int streaming, int collision, int nsteps);
 /* perform_triple_step (src/fvm_bardow.F90:322-340), needs nf = 3: like perform_step but the
  * streamed, pre-collision PDFs are kept in lattice `iold` before the indices rotate
@@ -118,6 +122,8 @@ int plbm_perform_dugks_step(plbm_handle grid, int dugks, int nsteps);
  * like the Fortran procedures and do NOT swap. */
 int plbm_lbm_stream(plbm_handle grid);                       /* src/periodic_lbm.f90:32  */
 int plbm_stream_fvm_bardow(plbm_handle grid);                /* src/fvm_bardow.F90:393   */
+int plbm_stream_fdm_bardow(plbm_handle grid);                /* src/fvm_bardow.F90:511   */
+int plbm_stream_fdm_sofonea(plbm_handle grid);               /* src/fvm_bardow.F90:688   */
 int plbm_collide(plbm_handle grid, int collision);           /* collide_bgk/trt/rr       */
 int plbm_dugks_collide(plbm_handle grid, int dugks);         /* src/periodic_dugks.F90:46  */
 int plbm_dugks_stream(plbm_handle grid, int dugks);          /* src/periodic_dugks.F90:172 */

@@ -38,7 +38,7 @@ def padded_ld(ny: int) -> int:
 
 
 class Oracle:
-    SCHEME_LBM, SCHEME_FVM_BARDOW, SCHEME_DUGKS, SCHEME_DUGKS_OFF = 0, 1, 2, 3
+    SCHEME_LBM, SCHEME_FVM_BARDOW, SCHEME_DUGKS, SCHEME_DUGKS_OFF, SCHEME_FDM_BARDOW, SCHEME_FDM_SOFONEA = 0, 1, 2, 3, 4, 5
     BGK, TRT, RR, BGK_SPLIT, TRT_SPLIT, BGK_IMPROVED = 0, 1, 2, 3, 4, 5
 
     def __init__(self, precision: str = "f64", omp: bool = False):
@@ -73,6 +73,8 @@ class Oracle:
         self._lambda_d = self._fn("orc_lambda_d", R, [R, R])
         self._magic = self._fn("orc_magic_number", R, [R, R])
         self._fvm = self._fn("orc_stream_fvm_bardow", None, [I, I, I, P, P, R])
+        self._fdm_bardow = self._fn("orc_stream_fdm_bardow", None, [I, I, I, P, P, R])
+        self._fdm_sofonea = self._fn("orc_stream_fdm_sofonea", None, [I, I, I, P, P, R])
         self._dcollide = self._fn("orc_dugks_collide", None, [I, I, I, P, P, R, R, R, I])
         self._dstream = self._fn("orc_dugks_stream", None, [I, I, I, P, P, R, R, I])
         self._v2 = self._fn("orc_vorticity_2nd", None, [I, I, P, P, P])
@@ -165,6 +167,12 @@ class Oracle:
 
     def stream_fvm_bardow(self, fold, fnew, ny, dt):
         self._fvm(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)
+
+    def stream_fdm_bardow(self, fold, fnew, ny, dt):
+        self._fdm_bardow(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)
+
+    def stream_fdm_sofonea(self, fold, fnew, ny, dt):
+        self._fdm_sofonea(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)
 
     def dugks_collide(self, fold, fnew, ny, omega, tau, dt, dugks=True):
         self._dcollide(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), omega, tau, dt, int(dugks))

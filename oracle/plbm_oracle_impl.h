@@ -567,6 +567,76 @@ void SFX(orc_stream_fvm_bardow)(int nx, int ny, int ld, const REAL *fold, REAL *
     }
 }
 
+/* src/fvm_bardow.F90:525-683 fdm_bardow_kernel, default build (none of FDM_WLS, FDM_WLS_GAUSS_V1/V2,
+ * FDM_ISO defined): second-order Lax-Wendroff with plain central differences. */
+void SFX(orc_stream_fdm_bardow)(int nx, int ny, int ld, const REAL *fold, REAL *fnew, REAL dt)
+{
+    const REAL p2 = R(0.5);
+#pragma omp parallel
+    {
+#pragma omp for schedule(static)
+        for (int x = 0; x < nx; ++x)
+            for (int y = 0; y < ny; ++y) fnew[FIDX(y, x, 0)] = fold[FIDX(y, x, 0)];
+        for (int q = 1; q < 9; ++q) {
+            REAL cxq = dt * R(SFX(ocx)[q]);
+            REAL cyq = dt * R(SFX(ocy)[q]);
+            REAL cxxq = R(0.5) * cxq * cxq;
+            REAL cyyq = R(0.5) * cyq * cyq;
+            REAL cxyq = cxq * cyq;
+            const REAL *fq = fold + FIDX(0, 0, q);
+#define FQ(yy, xx) fq[(size_t)(yy) + (size_t)ld * (size_t)(xx)]
+#pragma omp for schedule(static)
+            for (int x = 0; x < nx; ++x) {
+                int xp1 = WRAP_P1(x, nx);
+                int xm1 = WRAP_M1(x, nx);
+                for (int y = 0; y < ny; ++y) {
+                    int yp1 = WRAP_P1(y, ny);
+                    int ym1 = WRAP_M1(y, ny);
+                    REAL fc = FQ(y, x), fe = FQ(y, xp1), fn = FQ(yp1, x), fw = FQ(y, xm1), fs = FQ(ym1, x);
+                    REAL fne = FQ(yp1, xp1), fnw = FQ(yp1, xm1), fsw = FQ(ym1, xm1), fse = FQ(ym1, xp1);
+                    REAL dfx = p2 * (fe - fw);
+                    REAL dfy = p2 * (fn - fs);
+                    REAL dfxx = fe - R(2.0) * fc + fw;
+                    REAL dfyy = fn - R(2.0) * fc + fs;
+                    REAL dfxy = R(0.25) * (fne - fse - fnw + fsw);
+                    fnew[FIDX(y, x, q)] = fc - cxq * dfx - cyq * dfy + (cxxq * dfxx + cxyq * dfxy + cyyq * dfyy);
+                }
+            }
+#undef FQ
+        }
+    }
+}
+
+/* src/fvm_bardow.F90:702-891 fdm_sofonea_kernel: per population, 1-D Lax-Wendroff along its own
+ * characteristic; fu = f(x + c_q), fd = f(x - c_q).  (Loop bounds swapped in the reference, F9.) */
+void SFX(orc_stream_fdm_sofonea)(int nx, int ny, int ld, const REAL *fold, REAL *fnew, REAL dt)
+{
+    const REAL p2 = R(0.5) / MSQRT(R(2.0));
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) fnew[FIDX(y, x, 0)] = fold[FIDX(y, x, 0)];
+    for (int q = 1; q < 9; ++q) {
+        const int cx = SFX(ocx)[q], cy = SFX(ocy)[q];
+        for (int x = 0; x < nx; ++x) {
+            int xu = cx == 1 ? WRAP_P1(x, nx) : (cx == -1 ? WRAP_M1(x, nx) : x);
+            int xd = cx == 1 ? WRAP_M1(x, nx) : (cx == -1 ? WRAP_P1(x, nx) : x);
+            for (int y = 0; y < ny; ++y) {
+                int yu = cy == 1 ? WRAP_P1(y, ny) : (cy == -1 ? WRAP_M1(y, ny) : y);
+                int yd = cy == 1 ? WRAP_M1(y, ny) : (cy == -1 ? WRAP_P1(y, ny) : y);
+                REAL fc = fold[FIDX(y, x, q)], fu = fold[FIDX(yu, xu, q)], fd = fold[FIDX(yd, xd, q)];
+                REAL du1, du2;
+                if (q <= 4) {
+                    du1 = R(0.5) * (fu - fd);
+                    du2 = fu - R(2.0) * fc + fd;
+                } else {
+                    du1 = p2 * (fu - fd);
+                    du2 = R(0.5) * (fu - R(2.0) * fc + fd);
+                }
+                fnew[FIDX(y, x, q)] = fc + dt * (R(0.5) * dt * du2 - du1);
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* src/periodic_dugks.F90:310-434 update_ew / update_ns (-DDUGKS):
  * face moments from all nine face values, relaxation of the flux-carrying
@@ -794,6 +864,7 @@ REAL SFX(orc_l2_norm)(int nx, int ny, const REAL *ux, const REAL *uy, const REAL
  *   scheme 1: perform_step       src/fvm_bardow.F90:307-320  (stream_fvm_bardow)
  *   scheme 2: perform_dugks_step src/periodic_dugks.F90:25-38 (-DDUGKS)
  *   scheme 3: perform_dugks_step without -DDUGKS
+ *   scheme 4 / 5: perform_step with stream_fdm_bardow / stream_fdm_sofonea (src/fvm_bardow.F90:511, 688)
  * collision: 0 bgk, 1 trt, 2 rr, 3 bgk -DSPLIT (schemes 0/1 only).
  * idx[0]=iold, idx[1]=inew (1-based), updated in place. */
 void SFX(orc_run)(int nx, int ny, int ld, REAL *f1, REAL *f2, int *idx, int scheme, int collision,
@@ -802,11 +873,15 @@ void SFX(orc_run)(int nx, int ny, int ld, REAL *f1, REAL *f2, int *idx, int sche
     REAL *f[3] = {0, f1, f2};
     for (long s = 0; s < nsteps; ++s) {
         REAL *fo = f[idx[0]], *fn = f[idx[1]];
-        if (scheme == 0 || scheme == 1) {
+        if (scheme == 0 || scheme == 1 || scheme == 4 || scheme == 5) {
             if (scheme == 0)
                 SFX(orc_lbm_stream)(nx, ny, ld, fo, fn);
-            else
+            else if (scheme == 1)
                 SFX(orc_stream_fvm_bardow)(nx, ny, ld, fo, fn, dt);
+            else if (scheme == 4)
+                SFX(orc_stream_fdm_bardow)(nx, ny, ld, fo, fn, dt);
+            else
+                SFX(orc_stream_fdm_sofonea)(nx, ny, ld, fo, fn, dt);
             switch (collision) {
             case 0: SFX(orc_collide_bgk)(nx, ny, ld, fn, omega); break;
             case 1: SFX(orc_collide_trt)(nx, ny, ld, fn, omega, SFX(orc_lambda_d)(omega, trt_magic)); break;

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libplbm_b200.so")
 
 F64, F32 = 0, 1
 BGK, TRT, RR, BGK_SPLIT, TRT_SPLIT, BGK_IMPROVED = 0, 1, 2, 3, 4, 5
-STREAM_LBM, STREAM_FVM_BARDOW = 0, 1
+STREAM_LBM, STREAM_FVM_BARDOW, STREAM_FDM_BARDOW, STREAM_FDM_SOFONEA = 0, 1, 2, 3
 DIAG_MAX_SPEED, DIAG_MIN_SPEED, DIAG_SUM_RHO, DIAG_KINETIC, DIAG_COUNT = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); must list every symbol include/plbm.h declares
@@ -39,6 +39,8 @@ SIGNATURES = {
     "plbm_perform_dugks_step": (_I, [_H, _I, _I]),
     "plbm_lbm_stream": (_I, [_H]),
     "plbm_stream_fvm_bardow": (_I, [_H]),
+    "plbm_stream_fdm_bardow": (_I, [_H]),
+    "plbm_stream_fdm_sofonea": (_I, [_H]),
     "plbm_collide": (_I, [_H, _I]),
     "plbm_dugks_collide": (_I, [_H, _I]),
     "plbm_dugks_stream": (_I, [_H, _I]),

@@ -160,17 +160,37 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
     return PLBM_OK;
 }
 
-template <typename T> int step_fvm_t(Grid& g, int model, int nsteps)
+// kernel mode of a finite-volume / finite-difference streaming scheme (plbm_fvm*.cu)
+int fv_mode(int streaming) { return streaming == PLBM_STREAM_FVM_BARDOW ? 2 : (streaming == PLBM_STREAM_FDM_BARDOW ? 4 : 5); }
+
+// One sweep iold -> inew of stream_fvm_bardow / stream_fdm_bardow / stream_fdm_sofonea, fused with
+// the collision `model` (M_NONE = streaming only).  Collisions the tile kernels do not instantiate for
+// a scheme are applied by a second, in-place launch.
+template <typename T> int fv_sweep(Grid& g, int streaming, int model, const CollideParams<T>& cp)
+{
+    int rc;
+    const int mode = fv_mode(streaming);
+    const bool fusable = model == M_NONE || mode == 2 || model <= PLBM_RR;
+    const int kmodel = fusable ? model : (int)M_NONE;
+    if (g.comm && (rc = comm_fv_exchange<T>(g, g.lat<T>(g.iold)))) return rc;  // slab: neighbours' boundary lines
+    if ((g.variant == 0 || g.comm) && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
+        rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), mode, kmodel, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
+    else
+        rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, kmodel, cp, g.stream, mode);
+    if (rc) return rc;
+    if (!fusable) {
+        LbmArgs<T> c = lbm_args<T>(g, g.inew, g.inew, model);
+        rc = launch_lbm<T>(c, model, false, g.variant, g.stream);
+    }
+    return rc;
+}
+
+template <typename T> int step_fvm_t(Grid& g, int streaming, int model, int nsteps)
 {
     const CollideParams<T> cp = collide_params<T>(g, model);
     g.dugks_pending = false;  // lattice inew is overwritten below
     for (int s = 0; s < nsteps; ++s) {
-        int rc;
-        if (g.comm && (rc = comm_fv_exchange<T>(g, g.lat<T>(g.iold)))) return rc;  // slab: neighbours' boundary lines
-        if ((g.variant == 0 || g.comm) && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
-            rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), 2, model, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
-        else
-            rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, model, cp, g.stream);
+        int rc = fv_sweep<T>(g, streaming, model, cp);
         if (rc) return rc;
         swap_lattices(g);
     }
@@ -224,7 +244,7 @@ template <typename T> int step_triple_t(Grid& g, int streaming, int model, int n
             std::swap(g.f[g.iold - 1], g.f[g.imid - 1]);
             for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.imid - 1][b]);
         } else {
-            if ((rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, M_NONE, cp, g.stream))) return rc;
+            if ((rc = fv_sweep<T>(g, streaming, M_NONE, cp))) return rc;
             PLBM_CUDA(cudaMemcpyAsync(g.f[g.iold - 1], g.f[g.inew - 1], g.lattice_elems() * g.esize(), cudaMemcpyDeviceToDevice, g.stream));
             if ((rc = launch_lbm<T>(lbm_args<T>(g, g.inew, g.inew, model), model, false, g.variant, g.stream))) return rc;
         }
@@ -465,7 +485,7 @@ int plbm_perform_step(plbm_handle g, int streaming, int collision, int nsteps)
     int rc = check(g);
     if (rc) return rc;
     if ((rc = need_props(g))) return rc;
-    if (streaming != PLBM_STREAM_FVM_BARDOW || !valid_model(collision) || nsteps < 0) {
+    if (streaming < PLBM_STREAM_FVM_BARDOW || streaming > PLBM_STREAM_FDM_SOFONEA || !valid_model(collision) || nsteps < 0) {
         set_error("perform_step: bad streaming/collision id or nsteps");
         return PLBM_ERR_ARG;
     }
@@ -473,7 +493,7 @@ int plbm_perform_step(plbm_handle g, int streaming, int collision, int nsteps)
         set_error("perform_step(fvm_bardow): the slab decomposition needs the TMA tile kernel (no tensor map on this device)");
         return PLBM_ERR_ARG;
     }
-    return DISPATCH(g, step_fvm_t<double>(*g, collision, nsteps), step_fvm_t<float>(*g, collision, nsteps));
+    return DISPATCH(g, step_fvm_t<double>(*g, streaming, collision, nsteps), step_fvm_t<float>(*g, streaming, collision, nsteps));
 }
 
 int plbm_perform_triple_step(plbm_handle g, int streaming, int collision, int nsteps)
@@ -485,7 +505,7 @@ int plbm_perform_triple_step(plbm_handle g, int streaming, int collision, int ns
         set_error("perform_triple_step: the grid was allocated with nf = 2");
         return PLBM_ERR_STATE;
     }
-    if ((streaming != PLBM_STREAM_LBM && streaming != PLBM_STREAM_FVM_BARDOW) || !valid_model(collision) || nsteps < 0) {
+    if (streaming < PLBM_STREAM_LBM || streaming > PLBM_STREAM_FDM_SOFONEA || !valid_model(collision) || nsteps < 0) {
         set_error("perform_triple_step: bad streaming/collision id or nsteps");
         return PLBM_ERR_ARG;
     }
@@ -525,18 +545,23 @@ int plbm_lbm_stream(plbm_handle g)
     return launch_lbm<float>(lbm_args<float>(*g, g->iold, g->inew, PLBM_BGK), M_NONE, true, g->variant, g->stream);
 }
 
-int plbm_stream_fvm_bardow(plbm_handle g)
+static int stream_only(plbm_handle g, int streaming)
 {
     int rc = check(g);
     if (rc) return rc;
     if ((rc = need_props(g))) return rc;
+    if (g->comm && !g->tmap_ok) {
+        set_error("streaming: the slab decomposition needs the TMA tile kernel");
+        return PLBM_ERR_ARG;
+    }
     g->dugks_pending = false;  // lattice inew is overwritten
-    if (g->prec == PLBM_F64)
-        return launch_fvm_bardow<double>(*g, g->lat<double>(g->iold), g->lat<double>(g->inew), (double)g->dt, M_NONE,
-                                         CollideParams<double>{0, 0}, g->stream);
-    return launch_fvm_bardow<float>(*g, g->lat<float>(g->iold), g->lat<float>(g->inew), (float)g->dt, M_NONE,
-                                    CollideParams<float>{0, 0}, g->stream);
+    if (g->prec == PLBM_F64) return fv_sweep<double>(*g, streaming, M_NONE, CollideParams<double>{0, 0});
+    return fv_sweep<float>(*g, streaming, M_NONE, CollideParams<float>{0, 0});
 }
+
+int plbm_stream_fvm_bardow(plbm_handle g) { return stream_only(g, PLBM_STREAM_FVM_BARDOW); }
+int plbm_stream_fdm_bardow(plbm_handle g) { return stream_only(g, PLBM_STREAM_FDM_BARDOW); }
+int plbm_stream_fdm_sofonea(plbm_handle g) { return stream_only(g, PLBM_STREAM_FDM_SOFONEA); }
 
 int plbm_collide(plbm_handle g, int collision)
 {

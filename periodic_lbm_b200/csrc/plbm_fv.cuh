@@ -109,4 +109,62 @@ template <typename T, bool DUGKS, int PITCH, int PLANE> __device__ __forceinline
     }
 }
 
+// stream_fdm_bardow, default build (src/fvm_bardow.F90:511-685): second-order Lax-Wendroff update with
+// plain central differences,  fnew = fc - cxq*dfx - cyq*dfy + (cxxq*dfxx + cxyq*dfxy + cyyq*dfyy).
+// Terms that carry an exact-zero factor (cx = 0 or cy = 0) are skipped.
+template <typename T, int Q, int PITCH> __device__ __forceinline__ T fdm_bardow_pop(const T* c, T dt)
+{
+    constexpr int CX = cxi(Q), CY = cyi(Q);
+    const T cxq = dt * T(CX), cyq = dt * T(CY);
+    const T fc = c[0];
+    T r = fc;
+    if (CX != 0) r = r - cxq * (T(0.5) * (c[PITCH] - c[-PITCH]));
+    if (CY != 0) r = r - cyq * (T(0.5) * (c[1] - c[-1]));
+    T paren;
+    if (CX != 0 && CY != 0) {
+        const T cxxq = T(0.5) * cxq * cxq, cyyq = T(0.5) * cyq * cyq, cxyq = cxq * cyq;
+        const T dfxx = c[PITCH] - T(2) * fc + c[-PITCH];
+        const T dfyy = c[1] - T(2) * fc + c[-1];
+        const T dfxy = T(0.25) * (c[PITCH + 1] - c[PITCH - 1] - c[-PITCH + 1] + c[-PITCH - 1]);
+        paren = cxxq * dfxx + cxyq * dfxy + cyyq * dfyy;
+    } else if (CX != 0) {
+        paren = (T(0.5) * cxq * cxq) * (c[PITCH] - T(2) * fc + c[-PITCH]);
+    } else {
+        paren = (T(0.5) * cyq * cyq) * (c[1] - T(2) * fc + c[-1]);
+    }
+    return r + paren;
+}
+
+// stream_fdm_sofonea (src/fvm_bardow.F90:688-893): one-dimensional Lax-Wendroff along each
+// characteristic, fu = f(x + c), fd = f(x - c); the diagonals carry the 1/sqrt(2) grid spacing.
+template <typename T, int Q, int PITCH> __device__ __forceinline__ T fdm_sofonea_pop(const T* c, T dt)
+{
+    constexpr int CX = cxi(Q), CY = cyi(Q);
+    const T fc = c[0], fu = c[CX * PITCH + CY], fd = c[-CX * PITCH - CY];
+    T du1, du2;
+    if (CX == 0 || CY == 0) {
+        du1 = T(0.5) * (fu - fd);
+        du2 = fu - T(2) * fc + fd;
+    } else {
+        const T p2 = T(0.5) / sqrt(T(2));
+        du1 = p2 * (fu - fd);
+        du2 = T(0.5) * (fu - T(2) * fc + fd);
+    }
+    return fc + dt * (T(0.5) * dt * du2 - du1);
+}
+
+template <typename T, bool SOFONEA, int PITCH, int PLANE> __device__ __forceinline__ void fdm_update(const T* c0, T dt, T (&fp)[9])
+{
+#define PLBM_FDM_Q(Q) fp[Q] = SOFONEA ? fdm_sofonea_pop<T, Q, PITCH>(c0 + Q * PLANE, dt) : fdm_bardow_pop<T, Q, PITCH>(c0 + Q * PLANE, dt)
+    PLBM_FDM_Q(1);
+    PLBM_FDM_Q(2);
+    PLBM_FDM_Q(3);
+    PLBM_FDM_Q(4);
+    PLBM_FDM_Q(5);
+    PLBM_FDM_Q(6);
+    PLBM_FDM_Q(7);
+    PLBM_FDM_Q(8);
+#undef PLBM_FDM_Q
+}
+
 }  // namespace plbm

@@ -43,7 +43,7 @@ constexpr int NHALO = GX * GY - FX * FY; // 84 ring nodes
 //   stage 2: faces from the tile, face relaxation (DUGKS), flux update, collision (Bardow), store.
 // fbar^+ of the previous step (what the reference leaves in lattice `inew`, read by the lagged
 // update_macros) is not stored: it is recomputed on demand from fin, bit-identically.
-enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2 };
+enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2, MODE_FDM_BARDOW = 4, MODE_FDM_SOFONEA = 5 };
 
 template <typename T, int MODE, int MODEL>
 __global__ void __launch_bounds__(FY* FX, 2)
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(FY* FX, 2)
     const int x0 = blockIdx.y * FX, y0 = blockIdx.x * FY;
     const int tx = threadIdx.y, ty = threadIdx.x;
     const int tid = tx * FY + ty;
-    constexpr bool IS_DUGKS = MODE != MODE_BARDOW;
+    constexpr bool IS_DUGKS = MODE == MODE_DUGKS || MODE == MODE_DUGKS_OFF;
 
     // own node (tiles may overhang the grid: wrap, the result is discarded)
     const int x = x0 + tx, y = y0 + ty;
@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(FY* FX, 2)
     if (!active) return;
 
     const T* c0 = sm + (tx + 1) * PITCH + (ty + 1);
-    flux_update<T, MODE == MODE_DUGKS, PITCH, GX * PITCH>(c0, dt, omega_face, fp);
-    if (MODE == MODE_BARDOW && MODEL != M_NONE) collide<T, MODEL>(fp, cp);
+    if (MODE == MODE_FDM_BARDOW || MODE == MODE_FDM_SOFONEA)
+        fdm_update<T, MODE == MODE_FDM_SOFONEA, PITCH, GX * PITCH>(c0, dt, fp);
+    else
+        flux_update<T, MODE == MODE_DUGKS, PITCH, GX * PITCH>(c0, dt, omega_face, fp);
+    if (!IS_DUGKS && MODEL != M_NONE) collide<T, MODEL>(fp, cp);
 #pragma unroll
     for (int q = 0; q < 9; ++q) fout[((size_t)q * nx + x) * (size_t)ld + y] = fp[q];
 }
@@ -116,8 +119,22 @@ static int launch_fv(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T o
 }
 
 template <typename T>
-int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s)
+int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s, int mode)
 {
+    if (mode == MODE_FDM_BARDOW || mode == MODE_FDM_SOFONEA) {  // plain-load fallback of the FDM schemes
+        const bool sof = mode == MODE_FDM_SOFONEA;
+        switch (model) {
+        case M_NONE: return sof ? launch_fv<T, MODE_FDM_SOFONEA, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s)
+                                : launch_fv<T, MODE_FDM_BARDOW, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        case M_BGK: return sof ? launch_fv<T, MODE_FDM_SOFONEA, M_BGK>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s)
+                               : launch_fv<T, MODE_FDM_BARDOW, M_BGK>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        case M_TRT: return sof ? launch_fv<T, MODE_FDM_SOFONEA, M_TRT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s)
+                               : launch_fv<T, MODE_FDM_BARDOW, M_TRT>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        case M_RR: return sof ? launch_fv<T, MODE_FDM_SOFONEA, M_RR>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s)
+                              : launch_fv<T, MODE_FDM_BARDOW, M_RR>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        default: set_error("fdm streaming: only none/bgk/trt/rr are fused"); return PLBM_ERR_ARG;
+        }
+    }
     switch (model) {
     case M_NONE: return launch_fv<T, MODE_BARDOW, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
     case M_BGK: return launch_fv<T, MODE_BARDOW, M_BGK>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
@@ -220,7 +237,7 @@ int launch_dugks_stream(const Grid& g, const T* ft, T* fp, T dt, T omega_face, b
 }
 
 #define INST(T)                                                                                                    \
-    template int launch_fvm_bardow<T>(const Grid&, const T*, T*, T, int, const CollideParams<T>&, cudaStream_t);    \
+    template int launch_fvm_bardow<T>(const Grid&, const T*, T*, T, int, const CollideParams<T>&, cudaStream_t, int); \
     template int launch_dugks_collide<T>(const Grid&, T*, T*, T, T, cudaStream_t);                                 \
     template int launch_dugks_stream<T>(const Grid&, const T*, T*, T, T, bool, cudaStream_t);                      \
     template int launch_dugks_fused<T>(const Grid&, const T*, T*, T, T, T, T, bool, cudaStream_t);

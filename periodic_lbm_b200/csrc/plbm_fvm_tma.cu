@@ -99,7 +99,8 @@ __device__ __forceinline__ const T* wrapped_line(const T* fin, const T* hlo, con
 // MODE_LBM: the standard pull stream + collide with the halo tile staged by TMA (variant 3 of
 // perform_lbm_step).  It exists to MEASURE the north-star's "TMA staging of the row halo" against the
 // direct-load kernel k_lbm: staging cannot reduce the 144 B/node and over-fetches the halo ring.
-enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2, MODE_LBM = 3 };
+// MODE_FDM_BARDOW / MODE_FDM_SOFONEA: the reference's finite-difference streaming schemes.
+enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2, MODE_LBM = 3, MODE_FDM_BARDOW = 4, MODE_FDM_SOFONEA = 5 };
 
 // DUGKS keeps ONE raw stage (+ the fbar tile): the raw tile is dead after stage 1, so the next tile's
 // TMA is issued right after the stage-1 barrier and lands during stage 2 (the long phase).  Bardow
@@ -234,6 +235,10 @@ __global__ void __launch_bounds__(FY* FX, MINB)
                 const T* c0 = rw + (tx + 1) * B::BY + (ty + 1) + B::COL0;
                 flux_update<T, false, B::BY, B::PLANE>(c0, dt, omega_face, fp);
                 if (MODEL != M_NONE) collide<T, MODEL>(fp, cp);
+            } else if (MODE == MODE_FDM_BARDOW || MODE == MODE_FDM_SOFONEA) {
+                const T* c0 = rw + (tx + 1) * B::BY + (ty + 1) + B::COL0;
+                fdm_update<T, MODE == MODE_FDM_SOFONEA, B::BY, B::PLANE>(c0, dt, fp);
+                if (MODEL != M_NONE) collide<T, MODEL>(fp, cp);
             } else {  // MODE_LBM: fdst(y,x,q) = fsrc(y-cy, x-cx, q) from the staged tile, then collide
                 const T* c0 = rw + (tx + 1) * B::BY + (ty + 1) + B::COL0;
 #pragma unroll
@@ -341,6 +346,20 @@ int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode,
         case M_TRT: return launch_one<T, MODE_LBM, M_TRT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
         case M_RR: return launch_one<T, MODE_LBM, M_RR, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
         default: set_error("fv_tma: the TMA-staged LBM variant supports bgk, trt, rr"); return PLBM_ERR_ARG;
+        }
+    }
+    if (mode == MODE_FDM_BARDOW || mode == MODE_FDM_SOFONEA) {
+        const bool sof = mode == MODE_FDM_SOFONEA;
+        switch (model) {
+        case M_NONE: return sof ? launch_one<T, MODE_FDM_SOFONEA, M_NONE, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s)
+                                : launch_one<T, MODE_FDM_BARDOW, M_NONE, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        case M_BGK: return sof ? launch_one<T, MODE_FDM_SOFONEA, M_BGK, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s)
+                               : launch_one<T, MODE_FDM_BARDOW, M_BGK, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        case M_TRT: return sof ? launch_one<T, MODE_FDM_SOFONEA, M_TRT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s)
+                               : launch_one<T, MODE_FDM_BARDOW, M_TRT, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        case M_RR: return sof ? launch_one<T, MODE_FDM_SOFONEA, M_RR, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s)
+                              : launch_one<T, MODE_FDM_BARDOW, M_RR, 2>(g, which_src, fin, fout, dt, of, oh, oc, cp, s);
+        default: set_error("fv_tma: the FDM streaming kernels fuse bgk, trt, rr (others: stream, then collide)"); return PLBM_ERR_ARG;
         }
     }
     switch (model) {

@@ -92,7 +92,8 @@ template <typename T> int launch_vorticity(const Grid& g, int order, const T* ux
 template <typename T> int launch_diagnostics(Grid& g, double out[PLBM_DIAG_COUNT], cudaStream_t s);
 template <typename T> int launch_l2_sums(Grid& g, const T* uxa, const T* uya, double out[2], cudaStream_t s);
 template <typename T>
-int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s);
+int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s,
+                      int mode = 2 /* 2 Bardow FVM, 4 Bardow FDM (Lax-Wendroff), 5 Sofonea FDM */);
 template <typename T> int launch_dugks_collide(const Grid& g, T* fold, T* fnew, T omega_full, T omega_half, cudaStream_t s);
 template <typename T> int launch_dugks_stream(const Grid& g, const T* ft, T* fp, T dt, T omega_face, bool dugks, cudaStream_t s);
 template <typename T>

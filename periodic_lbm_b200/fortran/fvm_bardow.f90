@@ -19,7 +19,9 @@ module fvm_bardow
    public :: update_macros
    public :: set_pdf_to_equilibrium
    public :: equilibrium
+   public :: stream_fdm_bardow
    public :: stream_fvm_bardow
+   public :: stream_fdm_sofonea
    public :: cx, cy, csqr
    public :: sync_indices
 
@@ -180,6 +182,16 @@ contains
    subroutine stream_fvm_bardow(grid)
       class(lattice_grid), intent(inout) :: grid
       call plbm_check(plbm_stream_fvm_bardow(grid%dev), "stream_fvm_bardow")
+   end subroutine
+
+   subroutine stream_fdm_bardow(grid)
+      class(lattice_grid), intent(inout) :: grid
+      call plbm_check(plbm_stream_fdm_bardow(grid%dev), "stream_fdm_bardow")
+   end subroutine
+
+   subroutine stream_fdm_sofonea(grid)
+      class(lattice_grid), intent(inout) :: grid
+      call plbm_check(plbm_stream_fdm_sofonea(grid%dev), "stream_fdm_sofonea")
    end subroutine
 
 end module fvm_bardow

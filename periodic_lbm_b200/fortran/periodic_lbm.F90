@@ -4,7 +4,7 @@
 !! whole step; any other (user-supplied) pair is called one after the other like the reference does.
 module periodic_lbm
    use, intrinsic :: iso_c_binding
-   use fvm_bardow, only: lattice_grid, stream_fvm_bardow, sync_indices
+   use fvm_bardow, only: lattice_grid, stream_fvm_bardow, stream_fdm_bardow, stream_fdm_sofonea, sync_indices
    use collision_bgk, only: collide_bgk
    use collision_trt, only: collide_trt
    use collision_regularized, only: collide_rr
@@ -43,6 +43,8 @@ contains
       sid = -1
       if (associated(grid%streaming, lbm_stream)) sid = PLBM_STREAM_LBM
       if (associated(grid%streaming, stream_fvm_bardow)) sid = PLBM_STREAM_FVM_BARDOW
+      if (associated(grid%streaming, stream_fdm_bardow)) sid = PLBM_STREAM_FDM_BARDOW
+      if (associated(grid%streaming, stream_fdm_sofonea)) sid = PLBM_STREAM_FDM_SOFONEA
 
       call plbm_check(plbm_set_omega(grid%dev, real(grid%omega,c_double)), "set_omega")
       if (cid >= 0 .and. sid >= 0) then

@@ -11,7 +11,8 @@ module plbm_c
 
    integer(c_int), parameter :: PLBM_F64 = 0, PLBM_F32 = 1
    integer(c_int), parameter :: PLBM_BGK = 0, PLBM_TRT = 1, PLBM_RR = 2, PLBM_BGK_SPLIT = 3
-   integer(c_int), parameter :: PLBM_STREAM_LBM = 0, PLBM_STREAM_FVM_BARDOW = 1
+   integer(c_int), parameter :: PLBM_STREAM_LBM = 0, PLBM_STREAM_FVM_BARDOW = 1, &
+                                PLBM_STREAM_FDM_BARDOW = 2, PLBM_STREAM_FDM_SOFONEA = 3
 
    interface
       function plbm_last_error() bind(c, name="plbm_last_error") result(msg)
@@ -84,6 +85,16 @@ module plbm_c
          integer(c_int) :: stat
       end function
       function plbm_stream_fvm_bardow(grid) bind(c, name="plbm_stream_fvm_bardow") result(stat)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: grid
+         integer(c_int) :: stat
+      end function
+      function plbm_stream_fdm_bardow(grid) bind(c, name="plbm_stream_fdm_bardow") result(stat)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: grid
+         integer(c_int) :: stat
+      end function
+      function plbm_stream_fdm_sofonea(grid) bind(c, name="plbm_stream_fdm_sofonea") result(stat)
          import :: c_ptr, c_int
          type(c_ptr), value :: grid
          integer(c_int) :: stat

@@ -30,7 +30,7 @@ from .capi import check, lib
 __all__ = [
     "LatticeGrid", "alloc_grid", "dealloc_grid", "set_properties", "set_pdf_to_equilibrium",
     "perform_step", "perform_lbm_step", "perform_triple_step", "perform_dugks_step", "update_macros",
-    "lbm_stream", "stream_fvm_bardow", "collide_bgk", "collide_trt", "collide_rr", "collide_bgk_split",
+    "lbm_stream", "stream_fvm_bardow", "stream_fdm_bardow", "stream_fdm_sofonea", "collide_bgk", "collide_trt", "collide_rr", "collide_bgk_split",
     "collide_trt_split", "collide_bgk_improved",
     "dugks_collide", "dugks_stream", "vorticity_2nd", "vorticity_4th", "lambda_d", "magic_number",
     "cx", "cy", "csqr",
@@ -180,6 +180,16 @@ def stream_fvm_bardow(grid):
     check(lib.plbm_stream_fvm_bardow(grid._h), "stream_fvm_bardow")
 
 
+def stream_fdm_bardow(grid):
+    """stream_fdm_bardow (src/fvm_bardow.F90:511-685, default build: Lax-Wendroff finite differences)."""
+    check(lib.plbm_stream_fdm_bardow(grid._h), "stream_fdm_bardow")
+
+
+def stream_fdm_sofonea(grid):
+    """stream_fdm_sofonea (src/fvm_bardow.F90:688-893): characteristic-wise Lax-Wendroff."""
+    check(lib.plbm_stream_fdm_sofonea(grid._h), "stream_fdm_sofonea")
+
+
 def collide_bgk(grid):
     check(lib.plbm_collide(grid._h, capi.BGK), "collide_bgk")
 
@@ -219,6 +229,10 @@ _COLLISION_ID = {collide_bgk: capi.BGK, collide_trt: capi.TRT, collide_rr: capi.
                  collide_trt_split: capi.TRT_SPLIT, collide_bgk_improved: capi.BGK_IMPROVED}
 
 
+_STREAMING_ID = {stream_fvm_bardow: capi.STREAM_FVM_BARDOW, stream_fdm_bardow: capi.STREAM_FDM_BARDOW,
+                 stream_fdm_sofonea: capi.STREAM_FDM_SOFONEA}
+
+
 def _swap(grid):
     check(lib.plbm_swap(grid._h), "swap")
 
@@ -231,8 +245,8 @@ def perform_lbm_step(grid, nsteps=1) -> None:
     cid = _COLLISION_ID.get(grid.collision)
     if grid.streaming is lbm_stream and cid is not None:
         check(lib.plbm_perform_lbm_step(grid._h, cid, int(nsteps)), "perform_lbm_step")
-    elif grid.streaming is stream_fvm_bardow and cid is not None:
-        check(lib.plbm_perform_step(grid._h, capi.STREAM_FVM_BARDOW, cid, int(nsteps)), "perform_step")
+    elif grid.streaming in _STREAMING_ID and cid is not None:
+        check(lib.plbm_perform_step(grid._h, _STREAMING_ID[grid.streaming], cid, int(nsteps)), "perform_step")
     else:
         for _ in range(int(nsteps)):
             grid.streaming(grid)
@@ -249,7 +263,7 @@ def perform_triple_step(grid, nsteps=1) -> None:
     """perform_triple_step (src/fvm_bardow.F90:322-340) on a grid allocated with nf=3: the streamed,
     pre-collision PDFs stay available in lattice `imid` after the index rotation."""
     cid = _COLLISION_ID.get(grid.collision)
-    sid = {lbm_stream: capi.STREAM_LBM, stream_fvm_bardow: capi.STREAM_FVM_BARDOW}.get(grid.streaming)
+    sid = {lbm_stream: capi.STREAM_LBM, **_STREAMING_ID}.get(grid.streaming)
     if cid is None or sid is None:
         raise capi.PlbmError("perform_triple_step: needs lbm_stream|stream_fvm_bardow and collide_bgk|trt|rr")
     check(lib.plbm_perform_triple_step(grid._h, sid, cid, int(nsteps)), "perform_triple_step")

@@ -154,6 +154,31 @@ def test_fvm_bardow_steps(plbm, nx, ny, prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("scheme", ["fdm_bardow", "fdm_sofonea"])
+@pytest.mark.parametrize("nx,ny", [(64, 64), (67, 53), (5, 3), (40, 130)])
+def test_fdm_streaming_schemes(plbm, nx, ny, prec, scheme):
+    """stream_fdm_bardow / stream_fdm_sofonea (src/fvm_bardow.F90:511-893): unfused entry, fused with
+    every collision (bgk/trt/rr in-kernel, the others as a second launch), TMA and plain-load kernels."""
+    stream = getattr(plbm, "stream_" + scheme)
+    osch = Oracle.SCHEME_FDM_BARDOW if scheme == "fdm_bardow" else Oracle.SCHEME_FDM_SOFONEA
+    og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+    stream(g)
+    getattr(og.o, "stream_" + scheme)(og.lattice(og.iold), og.lattice(og.inew), ny, og.props["dt"])
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    plbm.dealloc_grid(g)
+    for variant in (0, 2):
+        for coll, ocoll in collisions(plbm):
+            og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.3)
+            g.set_variant(variant)
+            g.collision, g.streaming = coll, stream
+            plbm.perform_step(g, 3)
+            og.run(osch, ocoll, 3)
+            assert (g.iold, g.inew) == (og.iold, og.inew)
+            assert_same_lattice(g, og, g.iold, og.iold, ny)
+            plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("scheme", ["lbm", "fvm"])
 def test_perform_triple_step(plbm, prec, scheme):
     """perform_triple_step (src/fvm_bardow.F90:322-340): post-collision in iold, pre-collision in imid."""

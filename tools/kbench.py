@@ -38,8 +38,8 @@ def run(nx, ny, prec, scheme, coll, variant, steps, warmup=3, dugks=True):
     if scheme == "lbm":
         g.streaming = p.lbm_stream
         step = lambda n: p.perform_lbm_step(g, n)  # noqa: E731
-    elif scheme == "fvm":
-        g.streaming = p.stream_fvm_bardow
+    elif scheme in ("fvm", "fdmb", "fdms"):
+        g.streaming = {"fvm": p.stream_fvm_bardow, "fdmb": p.stream_fdm_bardow, "fdms": p.stream_fdm_sofonea}[scheme]
         step = lambda n: p.perform_step(g, n)  # noqa: E731
     else:
         g.collision = g.streaming = None
