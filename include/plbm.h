@@ -181,6 +181,9 @@ int plbm_case_vortex(int precision, int nx, int ny, double U0, double xc, double
  * (torch.distributed / MPI_Bcast) and every rank calls plbm_comm_init. */
 int plbm_comm_unique_id(void* id128);
 int plbm_comm_init(plbm_handle grid, const void* id128, int rank, int nranks, int nx_global, int x_offset);
+/* halo transport in use: 1 = p2p (CUDA IPC stores over NVLink + stream wait-value flags, default),
+ * 0 = nccl (grouped ncclSend/ncclRecv; PLBM_HALO=nccl or no IPC), -1 = no ring */
+int plbm_comm_transport(plbm_handle grid);
 int plbm_comm_finalize(plbm_handle grid);
 
 #ifdef __cplusplus

@@ -58,6 +58,7 @@ SIGNATURES = {
     "plbm_set_variant": (_I, [_H, _I]),
     "plbm_comm_unique_id": (_I, [_P]),
     "plbm_comm_init": (_I, [_H, _P, _I, _I, _I, _I]),
+    "plbm_comm_transport": (_I, [_H]),
     "plbm_comm_finalize": (_I, [_H]),
     "plbm_case_tg_decay_time": (_D, [_I, _D, _D, _D]),
     "plbm_case_taylor_green": (_I, [_I, _I, _I, _D, _D, _D, _D, _D, _P, _P, _P]),

@@ -787,6 +787,12 @@ int plbm_comm_init(plbm_handle g, const void* id128, int rank, int nranks, int n
     return comm_init(*g, id128, rank, nranks, nx_global, x_offset);
 }
 
+int plbm_comm_transport(plbm_handle g)
+{
+    if (!g) return -1;
+    return g->comm ? (comm_transport_is_p2p(*g) ? 1 : 0) : -1;
+}
+
 int plbm_comm_finalize(plbm_handle g)
 {
     int rc = check(g);

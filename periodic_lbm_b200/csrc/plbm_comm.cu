@@ -12,7 +12,18 @@
 //   comm : wait(packed) -> grouped ncclSend x2 / ncclRecv x2 into halo[dst] -> record(halo[dst])
 // Halo buffers are double-buffered by step parity.  NCCL is resolved with dlopen at
 // comm_init time so the single-GPU library has no link-time dependency on it.
+//
+// Two transports for the LBM halo (same schedule, same result):
+//   p2p  (default): the neighbours' halo buffers are mapped into this process with CUDA IPC and a small
+//         push kernel stores the three outgoing populations of each boundary line STRAIGHT into the
+//         neighbour's halo slot over NVLink, then raises an epoch flag there; the consumer's stream
+//         blocks on that flag with cuStreamWaitValue32 (no spinning kernel, no send/recv kernels, no
+//         staging copies).  NCCL is only used to bootstrap (IPC handles, agreement, quiesce barrier).
+//   nccl (PLBM_HALO=nccl, or when IPC is unavailable): pack kernel + grouped ncclSend/ncclRecv.
+#include <cuda.h>
 #include <dlfcn.h>
+
+#include <cstdlib>
 
 #include <cstring>
 
@@ -26,7 +37,7 @@ struct NcclUniqueId {
 };
 typedef void* ncclComm_t;
 typedef int ncclResult_t;
-constexpr int kNcclInt8 = 0;
+constexpr int kNcclInt8 = 0, kNcclInt32 = 2, kNcclMin = 3;
 
 struct NcclApi {
     void* lib = nullptr;
@@ -35,6 +46,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -64,6 +76,7 @@ int load_nccl()
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -102,11 +115,158 @@ struct Comm {
     void* halo9_lo = nullptr;
     void* halo9_hi = nullptr;
     cudaEvent_t ev9_packed = nullptr, ev9_done = nullptr;
+    // p2p transport: one IPC-exported block [halo_lo0 | halo_lo1 | halo_hi0 | halo_hi1 | flags]
+    bool p2p = false;
+    unsigned char* ipc_block = nullptr;
+    unsigned char* peer_lo = nullptr;   // rank lo's block, mapped here (== ipc_block when nranks == 1)
+    unsigned char* peer_hi = nullptr;
+    bool opened_lo = false, opened_hi = false;
+    size_t slot_bytes = 0;              // halo slot stride inside the block (256-B multiple)
+    unsigned* ticket = nullptr;         // completion counter of the push kernel (local)
+    unsigned epoch = 0;                 // number of exchanges issued; exchange e uses slot e & 1, flag value e
+    cudaEvent_t ev_boundary = nullptr;  // boundary lines of dst written (main -> comm)
     size_t bytes = 0;
     int parity = 0;        // halo slot holding the neighbours' lines of lattice `iold`
     bool halo_valid = false;
     int halo_of_lattice = 0;
 };
+
+
+namespace {
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+WaitValue32Fn wait_value32()
+{
+    static WaitValue32Fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<WaitValue32Fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// flags live behind the four halo slots: u32 flag_lo[2], flag_hi[2]
+__host__ __device__ inline size_t off_lo(size_t slot_bytes, int p) { return (size_t)p * slot_bytes; }
+__host__ __device__ inline size_t off_hi(size_t slot_bytes, int p) { return (size_t)(2 + p) * slot_bytes; }
+__host__ __device__ inline size_t off_flag_lo(size_t slot_bytes, int p) { return 4 * slot_bytes + 4 * (size_t)p; }
+__host__ __device__ inline size_t off_flag_hi(size_t slot_bytes, int p) { return 4 * slot_bytes + 8 + 4 * (size_t)p; }
+
+// Store the outgoing populations of the two boundary lines of `f` into the neighbours' halo slots over
+// NVLink (peer pointers), then -- last block to finish -- publish the epoch in their flag words.
+//   line 0    of q = 3,6,7 -> rank lo's halo_hi[slot]      line nx-1 of q = 1,5,8 -> rank hi's halo_lo[slot]
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_halo_push(const T* __restrict__ f, T* __restrict__ peer_lo_halo_hi, T* __restrict__ peer_hi_halo_lo, int nx, int ld,
+                unsigned* peer_lo_flag_hi, unsigned* peer_hi_flag_lo, unsigned epoch, unsigned* ticket)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * ld) {
+        const int slot = i / ld, y = i - slot * ld;
+        const int qlo[3] = {3, 6, 7}, qhi[3] = {1, 5, 8};
+        peer_lo_halo_hi[i] = f[((size_t)qlo[slot] * nx + 0) * (size_t)ld + y];
+        peer_hi_halo_lo[i] = f[((size_t)qhi[slot] * nx + (nx - 1)) * (size_t)ld + y];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {  // every block's stores are fenced before its ticket
+            *ticket = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(peer_lo_flag_hi) = epoch;
+            *reinterpret_cast<volatile unsigned*>(peer_hi_flag_lo) = epoch;
+            __threadfence_system();
+        }
+    }
+}
+}  // namespace
+
+// Neighbour barrier: both streams drained, then a 4-byte ring handshake.  Needed before an exchange that
+// is not preceded by a consuming step (initial condition / upload), see comm_lbm_steps.
+static int quiesce(Grid& g)
+{
+    Comm* c = g.comm;
+    PLBM_CUDA(cudaStreamSynchronize(g.stream));
+    PLBM_CUDA(cudaStreamSynchronize(c->stream));
+    PLBM_NCCL(g_nccl.GroupStart());
+    PLBM_NCCL(g_nccl.Send(c->send_lo, 4, kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Send(c->send_hi, 4, kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv((char*)c->send9_lo, 4, kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv((char*)c->send9_hi, 4, kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.GroupEnd());
+    PLBM_CUDA(cudaStreamSynchronize(c->stream));
+    return PLBM_OK;
+}
+
+// Try to set up the p2p transport; on any failure (on ANY rank: agreed by an all-reduce) stay on NCCL.
+static int p2p_setup(Grid& g)
+{
+    Comm* c = g.comm;
+    const char* env = getenv("PLBM_HALO");
+    int ok = !(env && env[0] == 'n') && wait_value32() != nullptr;
+    c->slot_bytes = (c->bytes + 255) / 256 * 256;
+    const size_t block_bytes = 4 * c->slot_bytes + 256;
+    cudaIpcMemHandle_t mine, from_lo, from_hi;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaMalloc(&c->ipc_block, block_bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(c->ipc_block, 0, block_bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMalloc(&c->ticket, 256) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(c->ticket, 0, 256) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, c->ipc_block) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    // every rank takes part in the handle exchange, whatever its own state (keeps NCCL calls matched)
+    char* stage = (char*)c->send9_lo;  // scratch device memory: [mine | from_lo | from_hi]
+    PLBM_CUDA(cudaMemcpy(stage, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    PLBM_NCCL(g_nccl.GroupStart());
+    PLBM_NCCL(g_nccl.Send(stage, sizeof(mine), kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Send(stage, sizeof(mine), kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv(stage + 128, sizeof(mine), kNcclInt8, c->hi, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.Recv(stage + 256, sizeof(mine), kNcclInt8, c->lo, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.GroupEnd());
+    PLBM_CUDA(cudaStreamSynchronize(c->stream));
+    PLBM_CUDA(cudaMemcpy(&from_hi, stage + 128, sizeof(mine), cudaMemcpyDeviceToHost));
+    PLBM_CUDA(cudaMemcpy(&from_lo, stage + 256, sizeof(mine), cudaMemcpyDeviceToHost));
+    if (ok) {
+        if (c->nranks == 1) {
+            c->peer_lo = c->peer_hi = c->ipc_block;
+        } else {
+            if (cudaIpcOpenMemHandle((void**)&c->peer_lo, from_lo, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
+                c->opened_lo = true;
+            else
+                ok = 0;
+            if (ok && c->lo == c->hi) {
+                c->peer_hi = c->peer_lo;  // two ranks: the same neighbour on both sides
+            } else if (ok) {
+                if (cudaIpcOpenMemHandle((void**)&c->peer_hi, from_hi, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
+                    c->opened_hi = true;
+                else
+                    ok = 0;
+            }
+            cudaGetLastError();
+        }
+    }
+    // agreement: p2p only if it works everywhere
+    int* flag = (int*)c->send9_hi;
+    PLBM_CUDA(cudaMemcpy(flag, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    PLBM_NCCL(g_nccl.AllReduce(flag, flag, 1, kNcclInt32, kNcclMin, c->comm, c->stream));
+    PLBM_CUDA(cudaStreamSynchronize(c->stream));
+    PLBM_CUDA(cudaMemcpy(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    c->p2p = ok != 0;
+    if (c->p2p) {
+        for (int p = 0; p < 2; ++p) {  // the halo slots now live inside the exported block
+            cudaFree(c->halo_lo[p]);
+            cudaFree(c->halo_hi[p]);
+            c->halo_lo[p] = c->ipc_block + off_lo(c->slot_bytes, p);
+            c->halo_hi[p] = c->ipc_block + off_hi(c->slot_bytes, p);
+        }
+    }
+    return PLBM_OK;
+}
+
+int comm_transport_is_p2p(const Grid& g) { return g.comm && g.comm->p2p ? 1 : 0; }
 
 int comm_unique_id(void* id128)
 {
@@ -167,10 +327,11 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
     PLBM_CUDA(cudaMalloc(&c->halo9_hi, 3 * c->bytes));
     PLBM_CUDA(cudaEventCreateWithFlags(&c->ev9_packed, cudaEventDisableTiming));
     PLBM_CUDA(cudaEventCreateWithFlags(&c->ev9_done, cudaEventDisableTiming));
+    PLBM_CUDA(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
     g.comm = c;
     g.nx_global = nx_global;
     g.x_offset = x_offset;
-    return PLBM_OK;
+    return p2p_setup(g);
 }
 
 int comm_finalize(Grid& g)
@@ -179,7 +340,17 @@ int comm_finalize(Grid& g)
     if (!c) return PLBM_OK;
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (g.stream) cudaStreamSynchronize(g.stream);
+    if (c->p2p && c->comm) {  // every rank leaves the ring together: nobody unmaps while a neighbour may still push
+        quiesce(g);
+        if (c->opened_lo) cudaIpcCloseMemHandle(c->peer_lo);
+        if (c->opened_hi) cudaIpcCloseMemHandle(c->peer_hi);
+        quiesce(g);
+        c->halo_lo[0] = c->halo_lo[1] = c->halo_hi[0] = c->halo_hi[1] = nullptr;  // inside ipc_block
+    }
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->ipc_block) cudaFree(c->ipc_block);
+    if (c->ticket) cudaFree(c->ticket);
+    if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
     for (int p = 0; p < 2; ++p) {
         if (c->halo_lo[p]) cudaFree(c->halo_lo[p]);
         if (c->halo_hi[p]) cudaFree(c->halo_hi[p]);
@@ -227,10 +398,87 @@ static int exchange(Grid& g, int p)
     return PLBM_OK;
 }
 
+
+// p2p transport of the step loop.  Exchange number e (1, 2, ...) targets slot e & 1 and flag value e.
+template <typename T> static int p2p_push(Grid& g, const T* f, cudaStream_t s)
+{
+    Comm* c = g.comm;
+    const unsigned e = ++c->epoch;
+    const int slot = (int)(e & 1u);
+    const size_t sb = c->slot_bytes;
+    const int n = 3 * g.ld;
+    k_halo_push<T><<<(n + 255) / 256, 256, 0, s>>>(f, (T*)(c->peer_lo + off_hi(sb, slot)), (T*)(c->peer_hi + off_lo(sb, slot)), g.nx, g.ld,
+                                                  (unsigned*)(c->peer_lo + off_flag_hi(sb, slot)),
+                                                  (unsigned*)(c->peer_hi + off_flag_lo(sb, slot)), e, c->ticket);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    return PLBM_OK;
+}
+
+static int p2p_wait(Grid& g, unsigned e)
+{
+    Comm* c = g.comm;
+    const int slot = (int)(e & 1u);
+    WaitValue32Fn wv = wait_value32();
+    CUresult r1 = wv((CUstream)g.stream, (CUdeviceptr)(c->ipc_block + off_flag_lo(c->slot_bytes, slot)), e, CU_STREAM_WAIT_VALUE_GEQ);
+    CUresult r2 = wv((CUstream)g.stream, (CUdeviceptr)(c->ipc_block + off_flag_hi(c->slot_bytes, slot)), e, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+        set_error("cuStreamWaitValue32 failed");
+        return PLBM_ERR_COMM;
+    }
+    return PLBM_OK;
+}
+
+template <typename T> static int p2p_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps)
+{
+    Comm* c = g.comm;
+    int rc;
+    if (nsteps > 0 && (!c->halo_valid || c->halo_of_lattice != g.iold)) {
+        // not preceded by a consuming step: make sure no neighbour still reads the slot we are about to fill
+        if ((rc = quiesce(g))) return rc;
+        if ((rc = p2p_push<T>(g, g.lat<T>(g.iold), g.stream))) return rc;
+        c->halo_valid = true;
+        c->halo_of_lattice = g.iold;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        const unsigned e = c->epoch;
+        const int slot = (int)(e & 1u);
+        LbmArgs<T> a;
+        a.src = g.lat<T>(g.iold);
+        a.dst = g.lat<T>(g.inew);
+        a.nx = g.nx;
+        a.ny = g.ny;
+        a.ld = g.ld;
+        a.halo_lo = (const T*)c->halo_lo[slot];
+        a.halo_hi = (const T*)c->halo_hi[slot];
+        a.cp = cp;
+        if ((rc = p2p_wait(g, e))) return rc;  // the neighbours' lines of lattice `iold` have landed
+        a.x_begin = 0;
+        a.x_end = 1;
+        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        a.x_begin = g.nx - 1;
+        a.x_end = g.nx;
+        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        // push the fresh boundary lines on the second stream, overlapped with the interior update
+        PLBM_CUDA(cudaEventRecord(c->ev_boundary, g.stream));
+        PLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_boundary, 0));
+        if ((rc = p2p_push<T>(g, a.dst, c->stream))) return rc;
+        a.x_begin = 1;
+        a.x_end = g.nx - 1;
+        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        int t = g.iold;
+        g.iold = g.inew;
+        g.inew = t;
+        c->halo_of_lattice = g.iold;
+    }
+    return PLBM_OK;
+}
+
 template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps)
 {
     Comm* c = g.comm;
     int rc;
+    if (c->p2p) return p2p_lbm_steps<T>(g, model, cp, nsteps);
     if (nsteps > 0 && (!c->halo_valid || c->halo_of_lattice != g.iold)) {
         // first step after an initial condition / upload: exchange the boundary lines of `iold`
         if ((rc = launch_halo_pack<T>(g, g.lat<T>(g.iold), (T*)c->send_lo, (T*)c->send_hi, g.stream))) return rc;

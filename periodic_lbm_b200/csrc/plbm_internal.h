@@ -114,6 +114,7 @@ template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo
 int comm_unique_id(void* id128);
 int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, int x_offset);
 int comm_finalize(Grid& g);
+int comm_transport_is_p2p(const Grid& g);
 void comm_invalidate_halo(Grid& g);  // the lattices were modified behind the ring's back
 template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps);
 // one FVM/DUGKS halo exchange: all nine populations of lines 0 and nx-1 of `f` -> g.fv_halo_lo/hi

@@ -10,7 +10,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed):
+def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p2p"):
+    os.environ["PLBM_HALO"] = halo
     import periodic_lbm_b200 as p
     from periodic_lbm_b200.capi import check, lib
     from conftest import random_state
@@ -30,6 +31,7 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed):
     else:
         idb = idq.get(timeout=120)
     check(lib.plbm_comm_init(g._h, C.create_string_buffer(idb, 128), rank, world, nxg, sl.x_offset), "comm_init")
+    transport = lib.plbm_comm_transport(g._h)
     g.upload_f(g.iold, np.ascontiguousarray(f0[:, sl.x_offset:sl.x_end]))
     g.collision = {0: p.collide_bgk, 1: p.collide_trt, 2: p.collide_rr}[coll_id % 10]
     if coll_id >= 20:      # DUGKS (9-population halo, TMA tile kernel)
@@ -48,15 +50,18 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed):
         p.perform_lbm_step(g, steps - steps // 2)
     got = g.download_f(g.iold)
     p.update_macros(g, lagged=False)
-    outq.put((rank, sl.x_offset, got, g.rho.copy()))
+    outq.put((rank, sl.x_offset, got, transport))
     check(lib.plbm_comm_finalize(g._h), "comm_finalize")
     p.dealloc_grid(g)
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("nxg,ny,steps,coll_id", [(64, 64, 9, 0), (37, 53, 8, 2), (130, 128, 11, 1), (4, 32, 5, 0),
                                                   (64, 64, 6, 20), (37, 53, 5, 20), (70, 96, 5, 12)])
-def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec):
+def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec, halo):
+    if halo == "nccl" and (coll_id >= 10 or prec == "f32"):
+        pytest.skip("the NCCL fallback transport is covered by the fp64 LBM cases")
     world = min(plbm.device_count(), 4 if nxg >= 8 else 2)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -67,7 +72,7 @@ def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec):
     seed = 99
     ctx = mp.get_context("spawn")
     idq, outq = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, idq, outq, nxg, ny, steps, coll_id, prec, seed)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo)) for r in range(world)]
     for pr in procs:
         pr.start()
     parts = [outq.get(timeout=300) for _ in range(world)]
@@ -75,6 +80,7 @@ def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec):
         pr.join(timeout=120)
         assert pr.exitcode == 0
     parts.sort(key=lambda t: t[1])
+    assert all(t[3] == (1 if halo == "p2p" else 0) for t in parts), [t[3] for t in parts]  # transport actually used
     multi = np.concatenate([t[2] for t in parts], axis=1)
 
     o = Oracle(prec)
