@@ -13,8 +13,9 @@ Default workload = BASELINE.json configs[4], the configuration the metric is quo
 One "step" = one fused stream+collide pass over the whole grid.
 
 For N > 1 the driver launches this file with torch.distributed.run, one rank per GPU; ranks
-exchange one halo line of three populations per direction per step over NCCL (inside
-libplbm_b200.so), overlapped with the interior update.
+exchange one halo line of three populations per direction per step (inside libplbm_b200.so: peer
+stores over NVLink through CUDA IPC mappings, or NCCL send/recv as fallback), overlapped with the
+interior update.
 
 `--impl reference` times the reference's own CPU algorithm (the line-faithful C/OpenMP restatement
 in oracle/, because the Fortran reference cannot be compiled in this image -- no gfortran) with all
@@ -238,6 +239,8 @@ def run_ours(args):
         dist.broadcast(idbuf, 0)
         idraw = C.create_string_buffer(idbuf.cpu().numpy().tobytes(), 128)
         check(lib.plbm_comm_init(g._h, idraw, rank, world, nx_global, rank * nxl), "comm_init")
+        transport = {1: "CUDA-IPC peer stores over NVLink from a push kernel + cuStreamWaitValue32 epoch flags (NCCL only bootstraps)",
+                     0: "grouped ncclSend/ncclRecv"}.get(lib.plbm_comm_transport(g._h), "?")
 
     def barrier():
         torch.cuda.synchronize()
@@ -316,7 +319,7 @@ def run_ours(args):
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": precision,
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "ny_fast": ny, "nx_slow_per_gpu": nxl, "nx_slow_global": nx_global,
-                       "collision": collision, "lattice": "D2Q9, two lattices, SoA f(ld,nx,0:8)", "halo": "1 line x 3 populations per direction per step (NCCL send/recv)" if world > 1 else "none (periodic index wrap)",
+                       "collision": collision, "lattice": "D2Q9, two lattices, SoA f(ld,nx,0:8)", "halo": f"1 line x 3 populations per direction per step, overlapped with the interior update; transport: {transport}" if world > 1 else "none (periodic index wrap)",
                        "l2": f"inputs larger than L2: {2 * 9 * nxl * ny * np.dtype(dtype).itemsize / 1e9:.1f} GB of PDFs per GPU vs 126 MB L2 (no flush needed)",
                        "mass_sum_rho": mass},
             "clocks": clocks,
