@@ -1,8 +1,8 @@
-"""Print our GPU value next to every row of the reference's golden files (development tool)."""
+"""Print our GPU value next to every row of the reference golden files (helper script, lives under tests/ because it uses the oracle-backed test helpers)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import periodic_lbm_b200 as p
 from test_gpu_golden import gpu_tg_run, load_rows
 for name, scheme in (("ref_fvm_bardow_64.txt", "fvm"), ("ref_fvm_dugks_64.txt", "dugks")):
