@@ -158,7 +158,11 @@ int plbm_set_stream(plbm_handle grid, void* cuda_stream);
 int plbm_synchronize(plbm_handle grid);
 /* kernels launched by this process through the library since load (for bench accounting) */
 long long plbm_launch_count(void);
-/* select a kernel variant for the fused LBM step (tuning / A-B measurements); 0 = default */
+/* select a kernel variant (tuning / A-B measurements); 0 = default everywhere.
+ *   perform_lbm_step : 0 direct 128-bit loads (+ the cluster-resident multi-step kernel when the grid fits
+ *                      in shared memory), 1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints
+ *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
+ *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused */
 int plbm_set_variant(plbm_handle grid, int variant);
 
 /* ---- flow cases (host side, O(N) input generators) ------------------------------------- */

@@ -106,7 +106,6 @@ template <typename T> int set_properties_t(Grid& g, double nu_, double dt_, doub
     return PLBM_OK;
 }
 
-// Apply the deferred half-step collision of the last fused DUGKS step to lattice `inew`.
 // scratch fields, allocated on first use
 int need_aux(Grid& g, int count)
 {
@@ -116,6 +115,7 @@ int need_aux(Grid& g, int count)
     return PLBM_OK;
 }
 
+// Apply the deferred half-step collision of the last fused DUGKS step to lattice `inew`.
 int materialize_inew(Grid& g)
 {
     if (!g.dugks_pending) return PLBM_OK;
