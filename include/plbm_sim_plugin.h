@@ -28,6 +28,14 @@ void c_plbm_free(void* sim);
 /* c_slbm_norm (sim/sim_slbm.F90:198-205): norm2(u - ua) / norm2(ua) over nx*ny host values */
 double c_plbm_norm(int nx, int ny, const double* u, const double* ua);
 
+/* The same entry points under the reference plugin's own name (sim/sim_slbm.F90:135-205), so that a
+ * symlink libslbm.so -> libplbm_b200.so is a drop-in for the reference's libslbm.so. */
+void* c_slbm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params);
+void c_slbm_step(void* sim, double omega);
+void c_slbm_vars(void* sim, double* rho, double* u);
+void c_slbm_free(void* sim);
+double c_slbm_norm(int nx, int ny, const double* u, const double* ua);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,11 @@ SIGNATURES = {
     "c_plbm_vars": (None, [_P, _P, _P]),
     "c_plbm_free": (None, [_P]),
     "c_plbm_norm": (_D, [_I, _I, _P, _P]),
+    "c_slbm_init": (_P, [_I, _I, _D, _P, _P, _P, _P]),
+    "c_slbm_step": (None, [_P, _D]),
+    "c_slbm_vars": (None, [_P, _P, _P]),
+    "c_slbm_free": (None, [_P]),
+    "c_slbm_norm": (_D, [_I, _I, _P, _P]),
 }
 
 

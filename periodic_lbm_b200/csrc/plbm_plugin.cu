@@ -208,4 +208,17 @@ double c_plbm_norm(int nx, int ny, const double* u, const double* ua)
     return std::sqrt(a) / std::sqrt(b);
 }
 
+
+// The same plugin under the reference's own name: the loader derives the symbol prefix from the file
+// name (sim/cases.py:27-39, lib<name>.so -> c_<name>_*), so `ln -s libplbm_b200.so libslbm.so` makes this
+// library a drop-in for the reference's libslbm.so in sim/cases.py and sim/standard_lbm.F90.
+void* c_slbm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    return c_plbm_init(nx, ny, dt, rho, u, sigma, params);
+}
+void c_slbm_step(void* sim, double omega) { c_plbm_step_n(sim, omega, 1); }
+void c_slbm_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
+void c_slbm_free(void* sim) { c_plbm_free(sim); }
+double c_slbm_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
+
 }  // extern "C"

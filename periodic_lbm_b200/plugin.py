@@ -22,7 +22,7 @@ class SimPlugin:
         self.name = name
         self._init = getattr(lib, f"c_{name}_init")
         self._step = getattr(lib, f"c_{name}_step")
-        self._step_n = getattr(lib, f"c_{name}_step_n")
+        self._step_n = getattr(lib, f"c_{name}_step_n", None)
         self._vars = getattr(lib, f"c_{name}_vars")
         self._free = getattr(lib, f"c_{name}_free")
         self._norm = getattr(lib, f"c_{name}_norm")
@@ -42,8 +42,9 @@ class SimPlugin:
         self.shape = (nx, ny)
 
     def step(self, omega, n=1):
-        if n == 1:
-            self._step(self.ptr, float(omega))
+        if n == 1 or self._step_n is None:
+            for _ in range(int(n)):
+                self._step(self.ptr, float(omega))
         else:
             self._step_n(self.ptr, float(omega), int(n))
 

@@ -330,6 +330,13 @@ def test_sim_plugin_seam(plbm):
     assert np.array_equal(rho, rho_w) and np.array_equal(uu[0], u_w) and np.array_equal(uu[1], v_w)
     assert abs(sim.norm(uu[0], u_w + 1e-3) - np.sqrt(((uu[0] - u_w - 1e-3) ** 2).sum() / ((u_w + 1e-3) ** 2).sum())) < 1e-12
     sim.free()
+    # the same plugin under the reference's own symbol names (libslbm.so drop-in)
+    ref_named = plbm.SimPlugin(name="slbm")
+    ref_named.init((nx, ny), 1.0, p, u)
+    ref_named.step(omega, n=steps)
+    rho2, uu2 = ref_named.vars()
+    assert np.array_equal(rho2, rho_w) and np.array_equal(uu2[0], u_w)
+    ref_named.free()
     with pytest.raises(plbm.PlbmError):
         plbm.SimPlugin().init((nx, ny), 0.5, p, u)  # "Standard LBM only supports dt = 1.0!"
 
