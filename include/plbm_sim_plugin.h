@@ -36,6 +36,15 @@ void c_slbm_vars(void* sim, double* rho, double* u);
 void c_slbm_free(void* sim);
 double c_slbm_norm(int nx, int ny, const double* u, const double* ua);
 
+/* The reference's second-order Lax-Wendroff plugin `lw` (sim/sim_lw.F90: lw_stream :24-85, lw_collision
+ * :87-166, lw_bc :169-197, exports :333-425), one fused kernel per step; any dt.  liblw.so drop-in. */
+void* c_lw_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params);
+void c_lw_step(void* sim, double omega);
+void c_lw_step_n(void* sim, double omega, int n);
+void c_lw_vars(void* sim, double* rho, double* u);
+void c_lw_free(void* sim);
+double c_lw_norm(int nx, int ny, const double* u, const double* ua);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,9 @@ class Oracle:
         self._sim_step = self._fn("orc_sim_collide_and_stream", None, [I, I, P, P, R])
         self._sim_bc = self._fn("orc_sim_periodic_bc_push", None, [I, I, P])
         self._sim_macros = self._fn("orc_sim_macros", None, [I, I, P, P, P, P])
+        self._lw_stream = self._fn("orc_lw_stream", None, [I, I, P, P, R])
+        self._lw_collision = self._fn("orc_lw_collision", None, [I, I, P, R])
+        self._lw_bc = self._fn("orc_lw_bc", None, [I, I, P])
         self.lib.orc_num_threads.restype = C.c_int
         self.lib.orc_set_num_threads.argtypes = [C.c_int]
 

@@ -1015,6 +1015,80 @@ void SFX(orc_sim_macros)(int nx, int ny, const REAL *fsrc, REAL *rho, REAL *u, R
         }
 }
 
+/* sim/sim_lw.F90:24-85 lw_stream: second-order Lax-Wendroff streaming on the haloed (0:nx+1,0:ny+1,0:8)
+ * arrays (interior only; the halo must have been filled by lw_bc). */
+void SFX(orc_lw_stream)(int nx, int ny, const REAL *fsrc, REAL *fdst, REAL dt)
+{
+    static const int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    static const int cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    for (int j = 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) fdst[SIDX(i, j, 0)] = fsrc[SIDX(i, j, 0)];
+    for (int k = 1; k < 9; ++k) {
+        REAL vx = dt * R(cx[k]), vy = dt * R(cy[k]);
+        REAL vxx = R(0.5) * vx * vx, vyy = R(0.5) * vy * vy, vxy = vx * vy;
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                REAL dfx = R(0.5) * (fsrc[SIDX(i + 1, j, k)] - fsrc[SIDX(i - 1, j, k)]);
+                REAL dfy = R(0.5) * (fsrc[SIDX(i, j + 1, k)] - fsrc[SIDX(i, j - 1, k)]);
+                REAL dfxx = fsrc[SIDX(i + 1, j, k)] - R(2.0) * fsrc[SIDX(i, j, k)] + fsrc[SIDX(i - 1, j, k)];
+                REAL dfyy = fsrc[SIDX(i, j + 1, k)] - R(2.0) * fsrc[SIDX(i, j, k)] + fsrc[SIDX(i, j - 1, k)];
+                REAL dfxy = R(0.25) * (fsrc[SIDX(i + 1, j + 1, k)] - fsrc[SIDX(i - 1, j + 1, k)] + fsrc[SIDX(i - 1, j - 1, k)] -
+                                       fsrc[SIDX(i + 1, j - 1, k)]);
+                fdst[SIDX(i, j, k)] = fsrc[SIDX(i, j, k)] - vx * dfx - vy * dfy + (vxx * dfxx + vxy * dfxy + vyy * dfyy);
+            }
+    }
+}
+
+/* sim/sim_lw.F90:87-166 lw_collision: DDF-shifted BGK, velocity by reciprocal multiplication */
+void SFX(orc_lw_collision)(int nx, int ny, REAL *pdf, REAL omega)
+{
+    const REAL rho0 = R(1.0);
+    const REAL w[9] = {W0, WS, WS, WS, WS, WD, WD, WD, WD};
+    for (int j = 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) {
+            REAL f[9], feq[9];
+            for (int k = 0; k < 9; ++k) f[k] = pdf[SIDX(i, j, k)];
+            REAL rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + rho0;
+            REAL irho = R(1.0) / rho;
+            REAL ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) * irho;
+            REAL uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) * irho;
+            REAL uxx = ux * ux, uyy = uy * uy;
+            REAL indp = -R(1.5) * (uxx + uyy);
+            feq[0] = W0 * rho * (indp);
+            feq[1] = WS * rho * (indp + R(3.0) * ux + R(4.5) * uxx);
+            feq[2] = WS * rho * (indp + R(3.0) * uy + R(4.5) * uyy);
+            feq[3] = WS * rho * (indp - R(3.0) * ux + R(4.5) * uxx);
+            feq[4] = WS * rho * (indp - R(3.0) * uy + R(4.5) * uyy);
+            REAL uxpy = ux + uy;
+            feq[5] = WD * rho * (indp + R(3.0) * uxpy + R(4.5) * uxpy * uxpy);
+            feq[7] = WD * rho * (indp - R(3.0) * uxpy + R(4.5) * uxpy * uxpy);
+            REAL uxmy = ux - uy;
+            feq[6] = WD * rho * (indp - R(3.0) * uxmy + R(4.5) * uxmy * uxmy);
+            feq[8] = WD * rho * (indp + R(3.0) * uxmy + R(4.5) * uxmy * uxmy);
+            for (int k = 0; k < 9; ++k) feq[k] = feq[k] + w[k] * (rho - rho0);
+            for (int k = 0; k < 9; ++k) pdf[SIDX(i, j, k)] = f[k] + omega * (feq[k] - f[k]);
+        }
+}
+
+/* sim/sim_lw.F90:169-197 lw_bc: periodic halo of ALL populations, edges then corners */
+void SFX(orc_lw_bc)(int nx, int ny, REAL *f)
+{
+    for (int k = 0; k < 9; ++k) {
+        for (int i = 1; i <= nx; ++i) {
+            f[SIDX(i, 0, k)] = f[SIDX(i, ny, k)];
+            f[SIDX(i, ny + 1, k)] = f[SIDX(i, 1, k)];
+        }
+        for (int j = 1; j <= ny; ++j) {
+            f[SIDX(0, j, k)] = f[SIDX(nx, j, k)];
+            f[SIDX(nx + 1, j, k)] = f[SIDX(1, j, k)];
+        }
+        f[SIDX(0, 0, k)] = f[SIDX(nx, ny, k)];
+        f[SIDX(nx + 1, ny + 1, k)] = f[SIDX(1, 1, k)];
+        f[SIDX(0, ny + 1, k)] = f[SIDX(nx, 1, k)];
+        f[SIDX(nx + 1, 0, k)] = f[SIDX(1, ny, k)];
+    }
+}
+
 #undef SIDX
 #undef FIDX
 #undef MIDX

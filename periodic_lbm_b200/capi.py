@@ -71,6 +71,12 @@ SIGNATURES = {
     "c_plbm_vars": (None, [_P, _P, _P]),
     "c_plbm_free": (None, [_P]),
     "c_plbm_norm": (_D, [_I, _I, _P, _P]),
+    "c_lw_init": (_P, [_I, _I, _D, _P, _P, _P, _P]),
+    "c_lw_step": (None, [_P, _D]),
+    "c_lw_step_n": (None, [_P, _D, _I]),
+    "c_lw_vars": (None, [_P, _P, _P]),
+    "c_lw_free": (None, [_P]),
+    "c_lw_norm": (_D, [_I, _I, _P, _P]),
     "c_slbm_init": (_P, [_I, _I, _D, _P, _P, _P, _P]),
     "c_slbm_step": (None, [_P, _D]),
     "c_slbm_vars": (None, [_P, _P, _P]),

@@ -23,6 +23,7 @@ struct SimState {
     double *f1, *f2;   // [9][ny][nx], DDF-shifted
     double *rho, *u;   // device staging for vars(): rho[ny][nx], u[2][ny][nx]
     cudaStream_t stream;
+    double dt;         // time step (the Lax-Wendroff plugin accepts any dt, slbm requires 1)
 };
 
 __device__ __forceinline__ void sim_equilibrium(double rho, double ux, double uy, double (&feq)[9])
@@ -101,6 +102,59 @@ __global__ void k_sim_macros(const double* __restrict__ fsrc, double* __restrict
     u[n + m] = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / r;
 }
 
+// The reference's `lw` plugin (sim/sim_lw.F90): second-order Lax-Wendroff streaming of every population
+// (lw_stream :24-85) followed by the DDF-shifted BGK collision (lw_collision :87-166); the periodic halo
+// copy lw_bc (:169-197) is index arithmetic here.  One fused kernel per step.
+__global__ void __launch_bounds__(256) k_lw_step(const double* __restrict__ fsrc, double* __restrict__ fdst, int nx, int ny,
+                                                 double dt, double omega)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int j = (int)(m / nx), i = (int)(m - (size_t)j * nx);
+    const int ip = i + 1 == nx ? 0 : i + 1, im = i == 0 ? nx - 1 : i - 1;
+    const int jp = j + 1 == ny ? 0 : j + 1, jm = j == 0 ? ny - 1 : j - 1;
+    const double w0 = 4.0 / 9.0, ws = 1.0 / 9.0, wd = 1.0 / 36.0, rho0 = 1.0;
+    const double w[9] = {w0, ws, ws, ws, ws, wd, wd, wd, wd};
+    double f[9], feq[9];
+    f[0] = fsrc[m];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+        const double* fk = fsrc + k * n;
+        const double vx = dt * cxi(k), vy = dt * cyi(k);
+        const double vxx = 0.5 * vx * vx, vyy = 0.5 * vy * vy, vxy = vx * vy;
+#define F(ii, jj) fk[(size_t)(jj) * nx + (ii)]
+        const double dfx = 0.5 * (F(ip, j) - F(im, j));
+        const double dfy = 0.5 * (F(i, jp) - F(i, jm));
+        const double dfxx = F(ip, j) - 2.0 * F(i, j) + F(im, j);
+        const double dfyy = F(i, jp) - 2.0 * F(i, j) + F(i, jm);
+        const double dfxy = 0.25 * (F(ip, jp) - F(im, jp) + F(im, jm) - F(ip, jm));
+        f[k] = F(i, j) - vx * dfx - vy * dfy + (vxx * dfxx + vxy * dfxy + vyy * dfyy);
+#undef F
+    }
+    double rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + rho0;
+    double irho = 1.0 / rho;
+    double ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) * irho;
+    double uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) * irho;
+    double uxx = ux * ux, uyy = uy * uy;
+    double indp = -1.5 * (uxx + uyy);
+    feq[0] = w0 * rho * (indp);
+    feq[1] = ws * rho * (indp + 3.0 * ux + 4.5 * uxx);
+    feq[2] = ws * rho * (indp + 3.0 * uy + 4.5 * uyy);
+    feq[3] = ws * rho * (indp - 3.0 * ux + 4.5 * uxx);
+    feq[4] = ws * rho * (indp - 3.0 * uy + 4.5 * uyy);
+    double uxpy = ux + uy;
+    feq[5] = wd * rho * (indp + 3.0 * uxpy + 4.5 * uxpy * uxpy);
+    feq[7] = wd * rho * (indp - 3.0 * uxpy + 4.5 * uxpy * uxpy);
+    double uxmy = ux - uy;
+    feq[6] = wd * rho * (indp - 3.0 * uxmy + 4.5 * uxmy * uxmy);
+    feq[8] = wd * rho * (indp + 3.0 * uxmy + 4.5 * uxmy * uxmy);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) feq[k] = feq[k] + w[k] * (rho - rho0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fdst[k * n + m] = f[k] + omega * (feq[k] - f[k]);
+}
+
 void sim_destroy(SimState* s)
 {
     if (!s) return;
@@ -121,14 +175,13 @@ extern "C" {
 
 // void *siminit(int nx, int ny, double dt, double *rho, double *u, double *sigma, void *params)
 // Returns NULL on failure (the reference `error stop`s); see plbm_last_error().
-void* c_plbm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+static void* sim_init_common(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, bool need_unit_dt)
 {
-    (void)params;
     if (nx < 1 || ny < 1 || !rho || !u) {
         set_error("c_plbm_init: bad argument");
         return nullptr;
     }
-    if (dt != 1.0) {  // sim/sim_slbm.F90:48-51
+    if (need_unit_dt && dt != 1.0) {  // sim/sim_slbm.F90:48-51
         set_error("Standard LBM only supports dt = 1.0!");
         return nullptr;
     }
@@ -142,7 +195,7 @@ void* c_plbm_init(int nx, int ny, double dt, const double* rho, const double* u,
         set_error("no CUDA device available: libplbm_b200 has no CPU fallback");
         return nullptr;
     }
-    SimState* s = new SimState{nx, ny, nullptr, nullptr, nullptr, nullptr, nullptr};
+    SimState* s = new SimState{nx, ny, nullptr, nullptr, nullptr, nullptr, nullptr, dt};
     const size_t n = (size_t)nx * ny;
     bool ok = cudaMalloc(&s->f1, 9 * n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->f2, 9 * n * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&s->rho, n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->u, 2 * n * sizeof(double)) == cudaSuccess &&
@@ -160,6 +213,12 @@ void* c_plbm_init(int nx, int ny, double dt, const double* rho, const double* u,
         return nullptr;
     }
     return s;
+}
+
+void* c_plbm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    (void)params;
+    return sim_init_common(nx, ny, dt, rho, u, sigma, true);
 }
 
 void c_plbm_step_n(void* sim, double omega, int n)
@@ -220,5 +279,31 @@ void c_slbm_step(void* sim, double omega) { c_plbm_step_n(sim, omega, 1); }
 void c_slbm_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
 void c_slbm_free(void* sim) { c_plbm_free(sim); }
 double c_slbm_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
+
+
+// The reference's Lax-Wendroff plugin `lw` (sim/sim_lw.F90:295-425) under its own symbol names:
+// `ln -s libplbm_b200.so liblw.so` is a drop-in for the reference's liblw.so.  Any dt is accepted.
+void* c_lw_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    (void)params;
+    return sim_init_common(nx, ny, dt, rho, u, sigma, false);
+}
+void c_lw_step_n(void* sim, double omega, int n)
+{
+    SimState* s = static_cast<SimState*>(sim);
+    if (!s) return;
+    const size_t nn = (size_t)s->nx * s->ny;
+    for (int it = 0; it < n; ++it) {
+        k_lw_step<<<(unsigned)((nn + 255) / 256), 256, 0, s->stream>>>(s->f1, s->f2, s->nx, s->ny, s->dt, omega);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        double* t = s->f1;
+        s->f1 = s->f2;
+        s->f2 = t;
+    }
+}
+void c_lw_step(void* sim, double omega) { c_lw_step_n(sim, omega, 1); }
+void c_lw_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
+void c_lw_free(void* sim) { c_plbm_free(sim); }
+double c_lw_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
 
 }  // extern "C"

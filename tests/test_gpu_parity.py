@@ -341,6 +341,36 @@ def test_sim_plugin_seam(plbm):
         plbm.SimPlugin().init((nx, ny), 0.5, p, u)  # "Standard LBM only supports dt = 1.0!"
 
 
+@pytest.mark.parametrize("dt", [1.0, 0.4])
+def test_sim_lw_plugin_seam(plbm, dt):
+    """c_lw_{init,step,vars,free}: the reference's Lax-Wendroff plugin (sim/sim_lw.F90) vs its oracle."""
+    nx, ny, steps, omega = 40, 56, 12, 1.4
+    o = Oracle("f64")
+    rng = np.random.default_rng(12)
+    p = 1e-3 * rng.standard_normal((ny, nx))
+    u = 0.05 * rng.standard_normal((2, ny, nx))
+    f1 = np.zeros((9, ny + 2, nx + 2))
+    f2 = np.zeros_like(f1)
+    P = lambda a: a.ctypes.data  # noqa: E731
+    o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
+    o._lw_bc(nx, ny, P(f1))
+    for _ in range(steps):
+        o._lw_stream(nx, ny, P(f1), P(f2), dt)
+        o._lw_collision(nx, ny, P(f2), omega)
+        o._lw_bc(nx, ny, P(f2))
+        f1, f2 = f2, f1
+    rho_w, u_w, v_w = np.zeros((ny, nx)), np.zeros((ny, nx)), np.zeros((ny, nx))
+    o._sim_macros(nx, ny, P(f1), P(rho_w), P(u_w), P(v_w))
+
+    sim = plbm.SimPlugin(name="lw")
+    sim.init((nx, ny), dt, p, u)
+    sim.step(omega)
+    sim.step(omega, n=steps - 1)
+    rho, uu = sim.vars()
+    assert np.array_equal(rho, rho_w) and np.array_equal(uu[0], u_w) and np.array_equal(uu[1], v_w)
+    sim.free()
+
+
 def test_error_paths(plbm):
     with pytest.raises(plbm.PlbmError):
         plbm.alloc_grid(0, 8)
