@@ -164,10 +164,19 @@ def test_full_size_properties_8192(plbm):
         plbm.dealloc_grid(g)
 
 
-def test_cpp_driver_prints_golden_value():
-    """app/main_taylor_green.cpp (the C++ host mirror of app/main_taylor_green.f90) over the C ABI."""
+def test_cpp_drivers_over_the_cpp_module_mirror():
+    """app/main_taylor_green.cpp and app/main_vortex.cpp: the reference drivers written against
+    include/plbm_grid.hpp (the C++ host-side mirror of the Fortran modules) over the C ABI."""
     app = os.path.join(ROOT, "app")
     subprocess.run(["make", "-C", app], check=True, capture_output=True)
-    out = subprocess.run([os.path.join(app, "main_taylor_green"), "64", "dugks", "bgk", "r50"], check=True, capture_output=True, text=True).stdout
+    out = subprocess.run([os.path.join(app, "main_taylor_green"), "r50", "64", "dugks"], check=True, capture_output=True, text=True).stdout
     l2 = float(re.search(r"L2-norm =\s*([0-9.E+-]+)", out).group(1))
-    assert abs(l2 - 2.2824885e-02) < 1e-9, out
+    assert abs(l2 - 2.2824885e-02) < 1e-9, out          # graphs/fvm_dugks_64.txt, dt/tau = 50
+    out = subprocess.run([os.path.join(app, "main_taylor_green"), "r50", "64", "fvm", "bgk"], check=True, capture_output=True, text=True).stdout
+    l2 = float(re.search(r"L2-norm =\s*([0-9.E+-]+)", out).group(1))
+    assert abs(l2 - 6.7097665e-02) < 1e-9, out          # graphs/fvm_bardow_64.txt, dt/tau = 50
+    # reference defaults of main_vortex (128^2, collide_bgk + stream_fvm_bardow), first 2000 steps
+    out = subprocess.run([os.path.join(app, "main_vortex"), "0.05", "128", "fvm", "bgk", "2000"], check=True, capture_output=True, text=True).stdout
+    speed = float(re.search(r"max\|u\| =\s*([0-9.e+-]+)", out).group(1))
+    mass = float(re.search(r"sum\(rho\) =\s*([0-9.e+-]+)", out).group(1))
+    assert 0.05 < speed < 0.2 and abs(mass / 128**2 - 1.0) < 5e-3, out
