@@ -371,6 +371,33 @@ def test_sim_lw_plugin_seam(plbm, dt):
     sim.free()
 
 
+def test_output_npy_and_checkpoint_roundtrip(plbm, tmp_path):
+    """output_npy writes mf(ny,nx,3) in Fortran order like the reference; a PDF checkpoint restores a run
+    bit for bit (continuing from the checkpoint == never stopping)."""
+    nx, ny = 48, 40
+    og, g = make_pair(plbm, nx, ny, "f64")
+    g.collision, g.streaming = plbm.collide_trt, plbm.lbm_stream
+    plbm.perform_lbm_step(g, 5)
+    plbm.update_macros(g)
+    g.filename = "results"
+    plbm.set_output_folder(g, str(tmp_path / "out"))
+    name = plbm.output_npy(g, step=5)
+    assert name.endswith("out/results000000005.npy")
+    mf = np.load(name)
+    assert mf.shape == (ny, nx, 3) and np.isfortran(mf)
+    assert np.array_equal(mf[:, :, 0], g.rho.T) and np.array_equal(mf[:, :, 2], g.uy.T)
+    plbm.save_checkpoint(g, str(tmp_path / "ckpt"))
+    plbm.perform_lbm_step(g, 7)
+    want = g.download_f(g.iold)
+    h = plbm.load_checkpoint(str(tmp_path / "ckpt"))
+    h.collision, h.streaming = plbm.collide_trt, plbm.lbm_stream
+    plbm.perform_lbm_step(h, 7)
+    assert (h.iold, h.inew) == (g.iold, g.inew)
+    assert np.array_equal(h.download_f(h.iold)[:, :, :ny], want[:, :, :ny])
+    plbm.dealloc_grid(g)
+    plbm.dealloc_grid(h)
+
+
 def test_error_paths(plbm):
     with pytest.raises(plbm.PlbmError):
         plbm.alloc_grid(0, 8)
