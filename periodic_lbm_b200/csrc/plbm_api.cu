@@ -144,7 +144,20 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
             return PLBM_OK;
         }
     }
-    for (int s = 0; s < nsteps; ++s) {
+    int s = 0;
+    if ((g.variant == 0 || g.variant == 5) && lbm_pair_applicable(g)) {  // 5: also on grids the cluster kernel would take
+        // two steps per pass over HBM.  The last step stays single so that lattice `inew` ends up holding
+        // state n-1 exactly as in the reference (what the lagged update_macros reads).  A pair leaves its
+        // result in the buffer that was `inew`; two reference swaps leave the indices unchanged, so the
+        // buffers trade places instead.
+        for (; s + 2 < nsteps; s += 2) {
+            int rc = launch_lbm_pair<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), model, collide_params<T>(g, model), g.stream);
+            if (rc) return rc;
+            std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
+            for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
+        }
+    }
+    for (; s < nsteps; ++s) {
         if (g.variant == 3 && g.tmap_ok && model <= PLBM_RR) {  // measurement variant: TMA-staged halo tile
             int rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), 3, model, T(0), T(0), T(0), T(0),
                                       collide_params<T>(g, model), g.stream);

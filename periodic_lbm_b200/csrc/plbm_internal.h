@@ -103,6 +103,9 @@ int launch_dugks_fused(const Grid& g, const T* fin, T* fout, T dt, T omega_full,
 template <typename T>
 int try_lbm_cluster_steps(const Grid& g, T* f_iold, T* f_inew, int model, const CollideParams<T>& cp, int nsteps, bool* done,
                           cudaStream_t s);
+// two steps per pass over HBM through a shared-memory ring (plbm_lbm2.cu)
+bool lbm_pair_applicable(const Grid& g);
+template <typename T> int launch_lbm_pair(const Grid& g, const T* src, T* dst, int model, const CollideParams<T>& cp, cudaStream_t s);
 // TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice
 int make_tensor_maps(Grid& g);
 template <typename T>

@@ -126,6 +126,27 @@ def test_fused_lbm_steps(plbm, nx, ny, prec, variant):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", [(64, 64), (16, 132), (4, 8), (9, 4), (40, 516), (300, 260), (5, 1024), (37, 2048)])
+def test_two_step_kernel(plbm, nx, ny, prec):
+    """The temporal-blocking kernel (two steps per pass over HBM, plbm_lbm2.cu; variant 5 forces it on grids
+    the cluster kernel would take): several strips / x segments, ragged last strip, odd step counts, both
+    lattices and the lagged macros bit-identical to the oracle."""
+    for nsteps, (coll, ocoll) in zip((3, 4, 5, 8, 9, 6), collisions(plbm)):
+        og, g = make_pair(plbm, nx, ny, prec)
+        g.set_variant(5)
+        g.collision, g.streaming = coll, plbm.lbm_stream
+        plbm.perform_lbm_step(g, nsteps)
+        og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
+        assert (g.iold, g.inew) == (og.iold, og.inew)
+        assert_same_lattice(g, og, g.iold, og.iold, ny)
+        assert_same_lattice(g, og, g.inew, og.inew, ny)
+        plbm.update_macros(g)
+        r, u, v = og.update_macros(lagged=True)
+        assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v)
+        plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("nx,ny", [(64, 64), (67, 67), (5, 5), (130, 130)])
 def test_fvm_bardow_steps(plbm, nx, ny, prec):
     """perform_step with stream_fvm_bardow + collide_bgk (what app/main_vortex.f90 runs), TMA-pipelined
