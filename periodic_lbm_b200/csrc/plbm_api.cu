@@ -151,7 +151,7 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         // result in the buffer that was `inew`; two reference swaps leave the indices unchanged, so the
         // buffers trade places instead.
         for (; s + 2 < nsteps; s += 2) {
-            int rc = launch_lbm_pair<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), model, collide_params<T>(g, model), g.stream);
+            int rc = launch_lbm_pair<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, nullptr, nullptr, model, collide_params<T>(g, model), g.stream);
             if (rc) return rc;
             std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
             for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);

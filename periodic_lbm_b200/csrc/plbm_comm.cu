@@ -27,6 +27,8 @@
 
 #include <cstring>
 
+#include <utility>
+
 #include "plbm_internal.h"
 
 namespace plbm {
@@ -104,10 +106,10 @@ struct Comm {
     cudaEvent_t ev_packed = nullptr;        // send buffers ready (main -> comm)
     cudaEvent_t ev_halo[2] = {nullptr, nullptr};  // halo[p] received (comm -> main)
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // halo[p] read by the boundary kernels (main -> comm)
-    void* send_lo = nullptr;                // line 0 of q = 3,6,7   -> rank lo
-    void* send_hi = nullptr;                // line nx-1 of q = 1,5,8 -> rank hi
-    void* halo_lo[2] = {nullptr, nullptr};  // from lo: q = 1,5,8
-    void* halo_hi[2] = {nullptr, nullptr};  // from hi: q = 3,6,7
+    void* send_lo = nullptr;                // lines 0, 1       -> rank lo   ([2][9][ld], NCCL transport)
+    void* send_hi = nullptr;                // lines nx-2, nx-1 -> rank hi
+    void* halo_lo[2] = {nullptr, nullptr};  // from lo: its lines nx-2, nx-1 (our lines -2, -1)
+    void* halo_hi[2] = {nullptr, nullptr};  // from hi: its lines 0, 1      (our lines nx, nx+1)
     // FVM / DUGKS: all nine populations of one line per direction (not overlapped: those kernels are
     // ALU-bound and the 9*ld-real message is microseconds)
     void* send9_lo = nullptr;
@@ -125,7 +127,8 @@ struct Comm {
     unsigned* ticket = nullptr;         // completion counter of the push kernel (local)
     unsigned epoch = 0;                 // number of exchanges issued; exchange e uses slot e & 1, flag value e
     cudaEvent_t ev_boundary = nullptr;  // boundary lines of dst written (main -> comm)
-    size_t bytes = 0;
+    size_t bytes = 0;   // one LBM halo message
+    size_t bytes9 = 0;  // one FVM / DUGKS halo message
     int parity = 0;        // halo slot holding the neighbours' lines of lattice `iold`
     bool halo_valid = false;
     int halo_of_lattice = 0;
@@ -154,20 +157,21 @@ __host__ __device__ inline size_t off_hi(size_t slot_bytes, int p) { return (siz
 __host__ __device__ inline size_t off_flag_lo(size_t slot_bytes, int p) { return 4 * slot_bytes + 4 * (size_t)p; }
 __host__ __device__ inline size_t off_flag_hi(size_t slot_bytes, int p) { return 4 * slot_bytes + 8 + 4 * (size_t)p; }
 
-// Store the outgoing populations of the two boundary lines of `f` into the neighbours' halo slots over
-// NVLink (peer pointers), then -- last block to finish -- publish the epoch in their flag words.
-//   line 0    of q = 3,6,7 -> rank lo's halo_hi[slot]      line nx-1 of q = 1,5,8 -> rank hi's halo_lo[slot]
+// Store the two boundary lines of each side of `f` (all nine populations, [2][9][ld]) into the neighbours'
+// halo slots over NVLink (peer pointers), then -- last block to finish -- publish the epoch in their flags.
+//   lines 0, 1 -> rank lo's halo_hi[slot]      lines nx-2, nx-1 -> rank hi's halo_lo[slot]
+// One step consumes the nearest line only; a fused pair of steps (plbm_lbm2.cu) consumes both.
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_halo_push(const T* __restrict__ f, T* __restrict__ peer_lo_halo_hi, T* __restrict__ peer_hi_halo_lo, int nx, int ld,
                 unsigned* peer_lo_flag_hi, unsigned* peer_hi_flag_lo, unsigned epoch, unsigned* ticket)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 3 * ld) {
-        const int slot = i / ld, y = i - slot * ld;
-        const int qlo[3] = {3, 6, 7}, qhi[3] = {1, 5, 8};
-        peer_lo_halo_hi[i] = f[((size_t)qlo[slot] * nx + 0) * (size_t)ld + y];
-        peer_hi_halo_lo[i] = f[((size_t)qhi[slot] * nx + (nx - 1)) * (size_t)ld + y];
+    if (i < 18 * ld) {
+        const int lq = i / ld, y = i - lq * ld;
+        const int l = lq / 9, q = lq - 9 * l;
+        peer_lo_halo_hi[i] = f[((size_t)q * nx + l) * (size_t)ld + y];
+        peer_hi_halo_lo[i] = f[((size_t)q * nx + (nx - 2 + l)) * (size_t)ld + y];
     }
     __threadfence_system();
     __syncthreads();
@@ -303,7 +307,8 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
     c->nranks = nranks;
     c->lo = (rank + nranks - 1) % nranks;
     c->hi = (rank + 1) % nranks;
-    c->bytes = 3 * (size_t)g.ld * g.esize();
+    c->bytes = 18 * (size_t)g.ld * g.esize();   // [2 lines][9 populations][ld]
+    c->bytes9 = 9 * (size_t)g.ld * g.esize();
     NcclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
@@ -321,10 +326,10 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
     }
     PLBM_CUDA(cudaMalloc(&c->send_lo, c->bytes));
     PLBM_CUDA(cudaMalloc(&c->send_hi, c->bytes));
-    PLBM_CUDA(cudaMalloc(&c->send9_lo, 3 * c->bytes));
-    PLBM_CUDA(cudaMalloc(&c->send9_hi, 3 * c->bytes));
-    PLBM_CUDA(cudaMalloc(&c->halo9_lo, 3 * c->bytes));
-    PLBM_CUDA(cudaMalloc(&c->halo9_hi, 3 * c->bytes));
+    PLBM_CUDA(cudaMalloc(&c->send9_lo, c->bytes9));
+    PLBM_CUDA(cudaMalloc(&c->send9_hi, c->bytes9));
+    PLBM_CUDA(cudaMalloc(&c->halo9_lo, c->bytes9));
+    PLBM_CUDA(cudaMalloc(&c->halo9_hi, c->bytes9));
     PLBM_CUDA(cudaEventCreateWithFlags(&c->ev9_packed, cudaEventDisableTiming));
     PLBM_CUDA(cudaEventCreateWithFlags(&c->ev9_done, cudaEventDisableTiming));
     PLBM_CUDA(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
@@ -406,7 +411,7 @@ template <typename T> static int p2p_push(Grid& g, const T* f, cudaStream_t s)
     const unsigned e = ++c->epoch;
     const int slot = (int)(e & 1u);
     const size_t sb = c->slot_bytes;
-    const int n = 3 * g.ld;
+    const int n = 18 * g.ld;
     k_halo_push<T><<<(n + 255) / 256, 256, 0, s>>>(f, (T*)(c->peer_lo + off_hi(sb, slot)), (T*)(c->peer_hi + off_lo(sb, slot)), g.nx, g.ld,
                                                   (unsigned*)(c->peer_lo + off_flag_hi(sb, slot)),
                                                   (unsigned*)(c->peer_hi + off_flag_lo(sb, slot)), e, c->ticket);
@@ -429,6 +434,29 @@ static int p2p_wait(Grid& g, unsigned e)
     return PLBM_OK;
 }
 
+// One launch of the step kernel (pair = false) or of the two-step kernel (pair = true) over lines [x0, x1).
+template <typename T> static int lbm_range(Grid& g, LbmArgs<T> a, bool pair, int x0, int x1, int model)
+{
+    if (x1 <= x0) return PLBM_OK;
+    if (pair) return launch_lbm_pair<T>(g, a.src, a.dst, x0, x1, a.halo_lo, a.halo_hi, model, a.cp, g.stream);
+    a.x_begin = x0;
+    a.x_end = x1;
+    return launch_lbm<T>(a, model, true, g.variant, g.stream);
+}
+
+// Lattice roles after one step (index swap) or after a fused pair (two reference swaps = the indices stay,
+// the result sits in the buffer that was `inew`: the buffers trade places).
+static void finish_steps(Grid& g, bool pair)
+{
+    if (pair) {
+        std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
+        for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
+    } else {
+        std::swap(g.iold, g.inew);
+    }
+    g.comm->halo_of_lattice = g.iold;
+}
+
 template <typename T> static int p2p_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps)
 {
     Comm* c = g.comm;
@@ -440,7 +468,11 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    for (int s = 0; s < nsteps; ++s) {
+    const bool pairs = (g.variant == 0 || g.variant == 5) && lbm_pair_applicable(g);
+    for (int s = 0; s < nsteps;) {
+        // two steps per pass over HBM while at least one single step remains (the last step stays single so
+        // that lattice `inew` ends up holding state n-1 like the reference, see step_lbm_t)
+        const bool pair = pairs && s + 2 < nsteps;
         const unsigned e = c->epoch;
         const int slot = (int)(e & 1u);
         LbmArgs<T> a;
@@ -452,24 +484,20 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         a.halo_lo = (const T*)c->halo_lo[slot];
         a.halo_hi = (const T*)c->halo_hi[slot];
         a.cp = cp;
+        // two boundary lines per side first: they need the halo, and they are what the neighbours get next
+        // (a single step would need only one, but the message always carries two so that a pair may follow)
+        const int nb = g.nx >= 4 ? 2 : g.nx;
         if ((rc = p2p_wait(g, e))) return rc;  // the neighbours' lines of lattice `iold` have landed
-        a.x_begin = 0;
-        a.x_end = 1;
-        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
-        a.x_begin = g.nx - 1;
-        a.x_end = g.nx;
-        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        if ((rc = lbm_range<T>(g, a, pair, 0, nb, model))) return rc;
+        if ((rc = lbm_range<T>(g, a, pair, nb < g.nx ? g.nx - nb : g.nx, g.nx, model))) return rc;
         // push the fresh boundary lines on the second stream, overlapped with the interior update
         PLBM_CUDA(cudaEventRecord(c->ev_boundary, g.stream));
         PLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_boundary, 0));
         if ((rc = p2p_push<T>(g, a.dst, c->stream))) return rc;
-        a.x_begin = 1;
-        a.x_end = g.nx - 1;
-        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
-        int t = g.iold;
-        g.iold = g.inew;
-        g.inew = t;
-        c->halo_of_lattice = g.iold;
+        a.halo_lo = a.halo_hi = nullptr;
+        if ((rc = lbm_range<T>(g, a, pair, nb, g.nx - nb, model))) return rc;
+        finish_steps(g, pair);
+        s += pair ? 2 : 1;
     }
     return PLBM_OK;
 }
@@ -487,7 +515,9 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    for (int s = 0; s < nsteps; ++s) {
+    const bool pairs = (g.variant == 0 || g.variant == 5) && lbm_pair_applicable(g);
+    for (int s = 0; s < nsteps;) {
+        const bool pair = pairs && s + 2 < nsteps;
         const int p = c->parity;
         LbmArgs<T> a;
         a.src = g.lat<T>(g.iold);
@@ -498,29 +528,22 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         a.halo_lo = (const T*)c->halo_lo[p];
         a.halo_hi = (const T*)c->halo_hi[p];
         a.cp = cp;
-        // boundary lines first: they need the neighbours' lines, and produce what must be sent
+        const int nb = g.nx >= 4 ? 2 : g.nx;
+        // two boundary lines per side first: they need the neighbours' lines, and produce what must be sent
         PLBM_CUDA(cudaStreamWaitEvent(g.stream, c->ev_halo[p], 0));
-        a.x_begin = 0;
-        a.x_end = 1;
-        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
-        a.x_begin = g.nx - 1;
-        a.x_end = g.nx;
-        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+        if ((rc = lbm_range<T>(g, a, pair, 0, nb, model))) return rc;
+        if ((rc = lbm_range<T>(g, a, pair, nb < g.nx ? g.nx - nb : g.nx, g.nx, model))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_consumed[p], g.stream));
         if ((rc = launch_halo_pack<T>(g, a.dst, (T*)c->send_lo, (T*)c->send_hi, g.stream))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_packed, g.stream));
         if ((rc = exchange(g, p ^ 1))) return rc;
         // interior, overlapped with the exchange
-        a.x_begin = 1;
-        a.x_end = g.nx - 1;
-        if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
-        // the send buffers are re-packed next step: the exchange must have consumed them by then.
-        // (the next pack is ordered after ev_halo[p^1], recorded after the sends completed.)
-        int t = g.iold;
-        g.iold = g.inew;
-        g.inew = t;
+        // (the send buffers are re-packed next step, ordered after ev_halo[p^1], recorded after the sends completed)
+        a.halo_lo = a.halo_hi = nullptr;
+        if ((rc = lbm_range<T>(g, a, pair, nb, g.nx - nb, model))) return rc;
+        finish_steps(g, pair);
         c->parity = p ^ 1;
-        c->halo_of_lattice = g.iold;
+        s += pair ? 2 : 1;
     }
     return PLBM_OK;
 }
@@ -532,7 +555,7 @@ template <typename T> int comm_fv_exchange(Grid& g, const T* f)
 {
     Comm* c = g.comm;
     int rc;
-    const size_t bytes9 = 3 * c->bytes;
+    const size_t bytes9 = c->bytes9;
     if ((rc = launch_halo_pack9<T>(g, f, (T*)c->send9_lo, (T*)c->send9_hi, g.stream))) return rc;
     PLBM_CUDA(cudaEventRecord(c->ev9_packed, g.stream));
     PLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev9_packed, 0));

@@ -76,8 +76,8 @@ template <typename T> struct LbmArgs {
     T* dst;
     int nx, ny, ld;        // lines in this slab, rows, leading dimension
     int x_begin, x_end;    // lines updated by this launch
-    // halo lines from the ring neighbours, [3][ld] each: slots (q=1,5,8) in lo, (q=3,6,7)
-    // in hi; nullptr = periodic self-wrap by index arithmetic (single GPU)
+    // the ring neighbours' two nearest lines, all nine populations, [2][9][ld] each (lo: lines -2, -1;
+    // hi: lines nx, nx+1); nullptr = periodic self-wrap by index arithmetic (single GPU)
     const T* halo_lo;
     const T* halo_hi;
     CollideParams<T> cp;
@@ -105,7 +105,9 @@ int try_lbm_cluster_steps(const Grid& g, T* f_iold, T* f_inew, int model, const 
                           cudaStream_t s);
 // two steps per pass over HBM through a shared-memory ring (plbm_lbm2.cu)
 bool lbm_pair_applicable(const Grid& g);
-template <typename T> int launch_lbm_pair(const Grid& g, const T* src, T* dst, int model, const CollideParams<T>& cp, cudaStream_t s);
+template <typename T>
+int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
+                    const CollideParams<T>& cp, cudaStream_t s);
 // TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice
 int make_tensor_maps(Grid& g);
 template <typename T>

@@ -49,8 +49,8 @@ template <typename T, int V> __device__ __forceinline__ void st_stream(T* p, con
     }
 }
 
-// halo slot of a population inside halo_lo (cx=+1: q=1,5,8) / halo_hi (cx=-1: q=3,6,7)
-__host__ __device__ constexpr int halo_slot(int q) { return (q == 1 || q == 3) ? 0 : ((q == 5 || q == 6) ? 1 : 2); }
+// Halo layout (shared with the two-step kernel, plbm_lbm2.cu): all nine populations of the neighbours' two
+// nearest lines, [2][9][ld]; halo_lo holds lines -2, -1 and halo_hi lines nx, nx+1.
 
 // Pointer to row 0 of the source line of population q for destination line x.
 template <typename T, int Q> __device__ __forceinline__ const T* src_line(const LbmArgs<T>& a, int x)
@@ -58,11 +58,11 @@ template <typename T, int Q> __device__ __forceinline__ const T* src_line(const 
     constexpr int cx = cxi(Q);
     int xs = x - cx;
     if (cx == 1 && xs < 0) {
-        if (a.halo_lo) return a.halo_lo + (size_t)halo_slot(Q) * a.ld;
+        if (a.halo_lo) return a.halo_lo + (size_t)(9 + Q) * a.ld;  // line -1
         xs = a.nx - 1;
     }
     if (cx == -1 && xs >= a.nx) {
-        if (a.halo_hi) return a.halo_hi + (size_t)halo_slot(Q) * a.ld;
+        if (a.halo_hi) return a.halo_hi + (size_t)Q * a.ld;  // line nx
         xs = 0;
     }
     return a.src + ((size_t)Q * a.nx + xs) * (size_t)a.ld;
@@ -232,22 +232,22 @@ template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream
 template int launch_lbm<double>(const LbmArgs<double>&, int, bool, int, cudaStream_t);
 template int launch_lbm<float>(const LbmArgs<float>&, int, bool, int, cudaStream_t);
 
-// Pack the three outgoing populations of the first / last line into contiguous send buffers
-// (multi-GPU ring): send_lo <- line 0 of q = 3,6,7 (goes to the low neighbour's halo_hi),
-// send_hi <- line nx-1 of q = 1,5,8 (goes to the high neighbour's halo_lo).
+// Pack the two boundary lines of each side into contiguous send buffers (multi-GPU ring, NCCL transport):
+// send_lo <- lines 0, 1 (become the low neighbour's halo_hi), send_hi <- lines nx-2, nx-1 (the high
+// neighbour's halo_lo), all nine populations, [2][9][ld].
 template <typename T> __global__ void k_halo_pack(const T* f, T* send_lo, T* send_hi, int nx, int ld)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * ld) return;
-    const int slot = i / ld, y = i - slot * ld;
-    const int qlo[3] = {3, 6, 7}, qhi[3] = {1, 5, 8};
-    send_lo[i] = f[((size_t)qlo[slot] * nx + 0) * (size_t)ld + y];
-    send_hi[i] = f[((size_t)qhi[slot] * nx + (nx - 1)) * (size_t)ld + y];
+    if (i >= 18 * ld) return;
+    const int lq = i / ld, y = i - lq * ld;
+    const int l = lq / 9, q = lq - 9 * l;
+    send_lo[i] = f[((size_t)q * nx + l) * (size_t)ld + y];
+    send_hi[i] = f[((size_t)q * nx + (nx - 2 + l)) * (size_t)ld + y];
 }
 
 template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s)
 {
-    const int n = 3 * g.ld;
+    const int n = 18 * g.ld;
     k_halo_pack<T><<<(n + 255) / 256, 256, 0, s>>>(f, send_lo, send_hi, g.nx, g.ld);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());

@@ -11,9 +11,19 @@
 // Redundant work: V halo rows above and below the strip in phase A, two warm-up columns per
 // x segment.  The ring keeps a population only as long as phase B needs it (cx=-1: consumed in
 // the iteration it is produced, depth 2; cx=0: depth 3; cx=+1: depth 4; one __syncthreads per
-// column), 27 column slots in all.  Arithmetic per node is collide<T,MODEL> on the same operands
-// as two k_lbm launches, so the result is bit-identical.
+// column), 27 column slots in all = 54 KB per 128-thread block, four blocks per SM.  The
+// operands of phase A of the NEXT column are loaded before phase B starts, so the HBM latency
+// hides behind phase B.  Arithmetic per node is collide<T,MODEL> on the same operands as two
+// k_lbm launches, so the result is bit-identical.
 //   lbm_stream_kernel  src/periodic_lbm.f90:45-127 ;  collisions src/collision_*.F90
+//
+// Measured alternatives (B200, BGK fp64 8192^2, this kernel 64 GLUPS): threads striding over rows
+// so that every access is a contiguous run (no bank conflicts, +50 % memory instructions) 55.6;
+// two barriers per column with 18 ring slots and six blocks per SM but no prefetch 56.2; 64- or
+// 256-thread blocks 58.7 / 58.0.  The kernel is bound by memory-instruction issue (stall_mio),
+// not by bytes: ncu in profiles/.
+#include <cstdlib>
+
 #include "plbm_internal.h"
 
 namespace plbm {
@@ -36,19 +46,35 @@ template <typename T> struct Lbm2Args {
     const T* src;
     T* dst;
     int nx, ny, ld;
-    int ty;       // interior rows per strip (multiple of V)
-    int nstrips;  // strips along y
-    int seglen;   // columns per x segment
+    int x_begin, x_end;  // columns whose step-2 state this launch writes
+    int ty;              // interior rows per strip (multiple of V)
+    int nstrips;         // strips along y
+    int seglen;          // columns per x segment
+    // slab decomposition: all nine populations of the neighbours' two nearest lines, [2][9][ld]
+    // (lo: lines -2, -1; hi: lines nx, nx+1).  nullptr = periodic self-wrap.
+    const T* halo_lo;
+    const T* halo_hi;
     CollideParams<T> cp;
 };
 
-// streamed (pre-collision) populations of logical column xl, rows yp..yp+V-1
-template <typename T, int V, int Q>
-__device__ __forceinline__ void pull_global(const Lbm2Args<T>& a, int xm, int xc, int xp, int yp, T (&f)[V][9])
+// row 0 of population Q in column `col` (col in [-2, nx+1])
+template <typename T, bool HALO, int Q> __device__ __forceinline__ const T* column_of(const Lbm2Args<T>& a, int col)
 {
-    constexpr int cx = cxi(Q), cy = cyi(Q);
-    const int xs = cx == 1 ? xm : (cx == 0 ? xc : xp);
-    const T* line = a.src + ((size_t)Q * a.nx + xs) * (size_t)a.ld;
+    if (HALO) {
+        if (col < 0) return a.halo_lo + ((size_t)(col + 2) * 9 + Q) * (size_t)a.ld;
+        if (col >= a.nx) return a.halo_hi + ((size_t)(col - a.nx) * 9 + Q) * (size_t)a.ld;
+    } else {
+        col = col < 0 ? col + a.nx : (col >= a.nx ? col - a.nx : col);
+    }
+    return a.src + ((size_t)Q * a.nx + col) * (size_t)a.ld;
+}
+
+// streamed (pre-collision) populations of column xl, rows yp..yp+V-1
+template <typename T, int V, bool HALO, int Q>
+__device__ __forceinline__ void pull_global(const Lbm2Args<T>& a, int xl, int yp, T (&f)[V][9])
+{
+    constexpr int cy = cyi(Q);
+    const T* line = column_of<T, HALO, Q>(a, xl - cxi(Q));
     if (cy == 0) {
         const Vec<T, V> p = *reinterpret_cast<const Vec<T, V>*>(line + yp);
 #pragma unroll
@@ -64,21 +90,17 @@ __device__ __forceinline__ void pull_global(const Lbm2Args<T>& a, int xm, int xc
     }
 }
 
-template <typename T, int V> __device__ __forceinline__ void load_column(const Lbm2Args<T>& a, int xl, int yp, T (&f)[V][9])
+template <typename T, int V, bool HALO> __device__ __forceinline__ void load_column(const Lbm2Args<T>& a, int xl, int yp, T (&f)[V][9])
 {
-    // xl in [-1, nx]: wrap the three source columns once
-    int xc = xl < 0 ? xl + a.nx : (xl >= a.nx ? xl - a.nx : xl);
-    int xm = xc == 0 ? a.nx - 1 : xc - 1;
-    int xp = xc + 1 == a.nx ? 0 : xc + 1;
-    pull_global<T, V, 0>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 1>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 2>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 3>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 4>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 5>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 6>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 7>(a, xm, xc, xp, yp, f);
-    pull_global<T, V, 8>(a, xm, xc, xp, yp, f);
+    pull_global<T, V, HALO, 0>(a, xl, yp, f);
+    pull_global<T, V, HALO, 1>(a, xl, yp, f);
+    pull_global<T, V, HALO, 2>(a, xl, yp, f);
+    pull_global<T, V, HALO, 3>(a, xl, yp, f);
+    pull_global<T, V, HALO, 4>(a, xl, yp, f);
+    pull_global<T, V, HALO, 5>(a, xl, yp, f);
+    pull_global<T, V, HALO, 6>(a, xl, yp, f);
+    pull_global<T, V, HALO, 7>(a, xl, yp, f);
+    pull_global<T, V, HALO, 8>(a, xl, yp, f);
 }
 
 // ring slot of the column written in this iteration, one counter per depth
@@ -125,7 +147,8 @@ template <typename T, int V, int W> __device__ __forceinline__ void pull_ring(co
     }
 }
 
-template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
+template <typename T, int MODEL, int V, int NT, int MINB, bool HALO>
+__global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
 {
     constexpr int W = NT * V;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -134,30 +157,30 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
     const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
     const int y_lo = strip * a.ty;
     const int y_hi = min(y_lo + a.ty, a.ny);
-    const int xs = seg * a.seglen;
-    const int xe = min(xs + a.seglen, a.nx);
+    const int xs = a.x_begin + seg * a.seglen;
+    const int xe = min(xs + a.seglen, a.x_end);
     const int t = threadIdx.x;
-    const int yl = y_lo - V + t * V;                                       // logical first row of this thread
-    const bool act_a = yl < y_hi + V;                                      // strip + V halo rows on both sides
-    const bool act_b = yl >= y_lo && yl < y_hi;                            // strip interior
-    const int yp = yl < 0 ? yl + a.ny : (yl >= a.ny ? yl - a.ny : yl);     // ny % V == 0: a vector never straddles the wrap
+    const int yl = y_lo - V + t * V;                                    // logical first row of this thread
+    const bool act_a = yl < y_hi + V;                                   // strip + V halo rows on both sides
+    const bool act_b = yl >= y_lo && yl < y_hi;                         // strip interior
+    const int yp = yl < 0 ? yl + a.ny : (yl >= a.ny ? yl - a.ny : yl);  // ny % V == 0: a vector never straddles the wrap
 
     RingPos rp = {0, 0, 0};
     T n[V][9];
     // warm-up: step-1 state of columns xs-1 and xs
     if (act_a) {
-        load_column<T, V>(a, xs - 1, yp, n);
+        load_column<T, V, HALO>(a, xs - 1, yp, n);
 #pragma unroll
         for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
         park_column<T, V, W>(ring, rp, t, n);
     }
     rp.advance();
     if (act_a) {
-        load_column<T, V>(a, xs, yp, n);
+        load_column<T, V, HALO>(a, xs, yp, n);
 #pragma unroll
         for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
         park_column<T, V, W>(ring, rp, t, n);
-        load_column<T, V>(a, xs + 1, yp, n);
+        load_column<T, V, HALO>(a, xs + 1, yp, n);
     }
     rp.advance();
 
@@ -169,7 +192,7 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
             park_column<T, V, W>(ring, rp, t, n);
         }
         __syncthreads();
-        if (act_a && x + 1 < xe) load_column<T, V>(a, x + 2, yp, n);  // in flight during phase B
+        if (act_a && x + 1 < xe) load_column<T, V, HALO>(a, x + 2, yp, n);  // in flight during phase B
         // B: step-2 state of column x
         if (act_b) {
             T f[V][9];
@@ -188,13 +211,22 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
     }
 }
 
-template <typename T, int MODEL> int launch_pair(const Grid& g, const T* src, T* dst, const CollideParams<T>& cp, cudaStream_t s)
+int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+template <typename T, int MODEL, bool HALO>
+int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
+                cudaStream_t s)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int NT = 128, MINB = 4;
     constexpr int W = NT * V;
     constexpr size_t smem = (size_t)RING_SLOTS * W * sizeof(T);
-    auto kern = k_lbm2<T, MODEL, V, NT, MINB>;
+    if (x_end <= x_begin) return PLBM_OK;
+    auto kern = k_lbm2<T, MODEL, V, NT, MINB, HALO>;
     static bool configured[64] = {false};
     if (g.device < 64 && !configured[g.device]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -207,21 +239,63 @@ template <typename T, int MODEL> int launch_pair(const Grid& g, const T* src, T*
     a.nx = g.nx;
     a.ny = g.ny;
     a.ld = g.ld;
+    a.x_begin = x_begin;
+    a.x_end = x_end;
+    a.halo_lo = halo_lo;
+    a.halo_hi = halo_hi;
     a.cp = cp;
+    const int ncols = x_end - x_begin;
     const int ty_max = (NT - 2) * V;
-    a.nstrips = (g.ny + ty_max - 1) / ty_max;
+    const int slots = g.sm_count * MINB;  // resident blocks of one wave
+    // Strips: among the counts from the minimum upwards take the one whose busiest block has the least work
+    // when strips x segments fill one wave (a narrower strip costs 2V/ty redundant rows in phase A).
+    const int nstrips_min = (g.ny + ty_max - 1) / ty_max;
+    int best = nstrips_min;
+    double best_cost = 1e300;
+    for (int ns = nstrips_min; ns <= nstrips_min + 8; ++ns) {
+        const int ty = ((g.ny + ns - 1) / ns + V - 1) / V * V;
+        int nseg = slots / ns;
+        if (nseg < 1) nseg = 1;
+        const int seglen = (ncols + nseg - 1) / nseg;
+        const double cost = (double)(ty + 2 * V) * (seglen + 2);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = ns;
+        }
+    }
+    a.nstrips = env_int("PLBM_PAIR_NSTRIPS", best);
+    if (a.nstrips < nstrips_min) a.nstrips = nstrips_min;
     a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
-    // one wave of equally long x segments, at least 8 columns each
-    int nseg = (g.sm_count * MINB) / a.nstrips;
+    // Segments: at least one wave, and short enough (64 columns, 3 % warm-up) that the block scheduler
+    // evens out the SMs over several waves (measured +5 % over one wave of long segments).
+    int nseg = slots / a.nstrips;
+    if (nseg < (ncols + 63) / 64) nseg = (ncols + 63) / 64;
+    nseg = env_int("PLBM_PAIR_NSEG", nseg);
     if (nseg < 1) nseg = 1;
-    a.seglen = (g.nx + nseg - 1) / nseg;
-    if (a.seglen < 8) a.seglen = g.nx < 8 ? g.nx : 8;
-    nseg = (g.nx + a.seglen - 1) / a.seglen;
+    a.seglen = (ncols + nseg - 1) / nseg;
+    if (a.seglen < 8) a.seglen = ncols < 8 ? ncols : 8;
+    nseg = (ncols + a.seglen - 1) / a.seglen;
     kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
+}
+
+template <typename T, bool HALO>
+int dispatch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
+                  const CollideParams<T>& cp, cudaStream_t s)
+{
+    switch (model) {
+    case M_BGK: return launch_pair<T, M_BGK, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_TRT: return launch_pair<T, M_TRT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_RR: return launch_pair<T, M_RR, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_BGK_SPLIT: return launch_pair<T, M_BGK_SPLIT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_TRT_SPLIT: return launch_pair<T, M_TRT_SPLIT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_BGK_IMPROVED: return launch_pair<T, M_BGK_IMPROVED, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    }
+    set_error("launch_lbm_pair: unknown collision model");
+    return PLBM_ERR_ARG;
 }
 
 }  // namespace
@@ -232,22 +306,20 @@ bool lbm_pair_applicable(const Grid& g)
     return g.nx >= 4 && g.ny >= 2 * v && (g.ny % v) == 0;
 }
 
-// Two fused steps src -> dst.  The caller accounts for the lattice roles (see step_lbm_t).
-template <typename T> int launch_lbm_pair(const Grid& g, const T* src, T* dst, int model, const CollideParams<T>& cp, cudaStream_t s)
+// Two fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' two
+// nearest lines ([2][9][ld]) under a slab decomposition, nullptr = periodic self-wrap.  The caller
+// accounts for the lattice roles (see step_lbm_t).
+template <typename T>
+int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
+                    const CollideParams<T>& cp, cudaStream_t s)
 {
-    switch (model) {
-    case M_BGK: return launch_pair<T, M_BGK>(g, src, dst, cp, s);
-    case M_TRT: return launch_pair<T, M_TRT>(g, src, dst, cp, s);
-    case M_RR: return launch_pair<T, M_RR>(g, src, dst, cp, s);
-    case M_BGK_SPLIT: return launch_pair<T, M_BGK_SPLIT>(g, src, dst, cp, s);
-    case M_TRT_SPLIT: return launch_pair<T, M_TRT_SPLIT>(g, src, dst, cp, s);
-    case M_BGK_IMPROVED: return launch_pair<T, M_BGK_IMPROVED>(g, src, dst, cp, s);
-    }
-    set_error("launch_lbm_pair: unknown collision model");
-    return PLBM_ERR_ARG;
+    if (halo_lo && halo_hi) return dispatch_pair<T, true>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s);
+    return dispatch_pair<T, false>(g, src, dst, x_begin, x_end, nullptr, nullptr, model, cp, s);
 }
 
-template int launch_lbm_pair<double>(const Grid&, const double*, double*, int, const CollideParams<double>&, cudaStream_t);
-template int launch_lbm_pair<float>(const Grid&, const float*, float*, int, const CollideParams<float>&, cudaStream_t);
+template int launch_lbm_pair<double>(const Grid&, const double*, double*, int, int, const double*, const double*, int,
+                                     const CollideParams<double>&, cudaStream_t);
+template int launch_lbm_pair<float>(const Grid&, const float*, float*, int, int, const float*, const float*, int,
+                                    const CollideParams<float>&, cudaStream_t);
 
 }  // namespace plbm
