@@ -1,4 +1,4 @@
-"""Performance guard (GPU): the fused stream+collide kernel must stay at the HBM roofline.
+"""Performance guard (GPU): the fused stream+collide kernels must stay at / above the HBM roofline.
 
 A register-count regression once dropped the RR fp64 kernel from 3 to 2 resident blocks per SM
 (-24 %) without any test noticing; this test would have.  Thresholds are far below the measured
@@ -20,9 +20,16 @@ def peak_gbs():
         return 6540.8
 
 
-@pytest.mark.parametrize("prec,coll", [("f64", "collide_bgk"), ("f64", "collide_trt"), ("f64", "collide_rr"),
-                                       ("f32", "collide_bgk"), ("f32", "collide_rr")])
-def test_fused_lbm_kernel_is_at_the_hbm_roofline(plbm, prec, coll):
+# floor of the algorithmic GB/s (144 B fp64 / 72 B fp32 per update) over the measured HBM peak:
+#   one step per launch (k_lbm) measured 1.03-1.05 fp64, 0.96-1.05 fp32;
+#   two steps per pass (k_lbm2) measured 1.40 / 1.30 / 1.27 (BGK / TRT / RR fp64), 1.34 / 1.08 (BGK / RR fp32)
+CASES = [("f64", "collide_bgk", 1.20), ("f64", "collide_trt", 1.15), ("f64", "collide_rr", 1.10),
+         ("f32", "collide_bgk", 1.15), ("f32", "collide_rr", 0.95)]
+
+
+@pytest.mark.parametrize("two_step", [False, True])
+@pytest.mark.parametrize("prec,coll,floor2", CASES)
+def test_fused_lbm_kernel_is_at_the_hbm_roofline(plbm, prec, coll, floor2, two_step):
     import torch
 
     n, steps = 8192, 60
@@ -39,10 +46,15 @@ def test_fused_lbm_kernel_is_at_the_hbm_roofline(plbm, prec, coll):
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        plbm.perform_lbm_step(g, steps)
+        if two_step:
+            plbm.perform_lbm_step(g, steps)  # (steps-1)//2 launches of k_lbm2 + the closing k_lbm
+        else:
+            for _ in range(steps):           # one k_lbm launch per call
+                plbm.perform_lbm_step(g, 1)
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         best = max(best, n * n * (144 if prec == "f64" else 72) / (ms * 1e-3) / 1e9)
     plbm.dealloc_grid(g)
-    assert best / peak_gbs() > 0.85, f"{coll} {prec}: {best:.0f} GB/s = {best / peak_gbs():.2f} of the measured HBM peak"
+    floor = floor2 if two_step else 0.85
+    assert best / peak_gbs() > floor, f"{coll} {prec} two_step={two_step}: {best:.0f} GB/s = {best / peak_gbs():.2f} of the measured HBM peak"
