@@ -103,7 +103,11 @@ int plbm_set_pdf_to_equilibrium(plbm_handle grid, const void* rho, const void* u
 
 /* ---- time stepping ------------------------------------------------------------------- */
 /* perform_lbm_step (src/periodic_lbm.f90:15-29): lbm_stream + collision + swap, fused
- * into one pull-scheme kernel; nsteps >= 1 steps per call. */
+ * into one pull-scheme kernel; nsteps >= 1 steps per call.  A call of nsteps >= 3 advances two
+ * steps per pass over HBM (the intermediate lattice lives in shared memory) and closes with a
+ * single step, so that after the call BOTH lattices and the indices are bit-identical to nsteps
+ * reference steps (lattice `inew` = state nsteps-1, what the lagged update_macros reads):
+ * batch the steps between two outputs into one call. */
 int plbm_perform_lbm_step(plbm_handle grid, int collision, int nsteps);
 /* perform_step (src/fvm_bardow.F90:307-320) with streaming = stream_fvm_bardow, stream_fdm_bardow
  * or stream_fdm_sofonea (PLBM_STREAM_LBM forwards to plbm_perform_lbm_step). */
@@ -159,8 +163,10 @@ int plbm_synchronize(plbm_handle grid);
 /* kernels launched by this process through the library since load (for bench accounting) */
 long long plbm_launch_count(void);
 /* select a kernel variant (tuning / A-B measurements); 0 = default everywhere.
- *   perform_lbm_step : 0 direct 128-bit loads (+ the cluster-resident multi-step kernel when the grid fits
- *                      in shared memory), 1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints
+ *   perform_lbm_step : 0 direct 128-bit loads, two steps per pass over HBM when nsteps >= 3 (or the cluster-
+ *                      resident multi-step kernel when the grid fits in shared memory); one step per launch:
+ *                      1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints;
+ *                      5 = like 0 but never the cluster kernel (tests of the two-step kernel on small grids)
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
  *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused */
 int plbm_set_variant(plbm_handle grid, int variant);

@@ -20,7 +20,8 @@
 // Measured alternatives (B200, BGK fp64 8192^2, this kernel 64 GLUPS): threads striding over rows
 // so that every access is a contiguous run (no bank conflicts, +50 % memory instructions) 55.6;
 // two barriers per column with 18 ring slots and six blocks per SM but no prefetch 56.2; 64- or
-// 256-thread blocks 58.7 / 58.0.  The kernel is bound by memory-instruction issue (stall_mio),
+// 256-thread blocks 58.7 / 58.0; streaming-store hints, shared-memory carve-out and 32-column
+// segments: within noise.  The kernel is bound by memory-instruction issue (stall_mio),
 // not by bytes: ncu in profiles/.
 #include <cstdlib>
 
