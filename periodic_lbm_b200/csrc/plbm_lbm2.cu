@@ -21,8 +21,12 @@
 // so that every access is a contiguous run (no bank conflicts, +50 % memory instructions) 55.6;
 // two barriers per column with 18 ring slots and six blocks per SM but no prefetch 56.2; 64- or
 // 256-thread blocks 58.7 / 58.0; streaming-store hints, shared-memory carve-out and 32-column
-// segments: within noise.  The kernel is bound by memory-instruction issue (stall_mio),
-// not by bytes: ncu in profiles/.
+// segments: within noise; skewed row ownership (phase A owns rows (odd, even), phase B (even, odd), so
+// that the shifted populations become aligned vectors: 42 instead of 48 memory instructions per thread
+// and column) 63.7, i.e. no change; issuing the prefetch before the barrier 62.4; fp32 shifted
+// populations as aligned vector + one element (15 instead of 27 loads) 111.6 vs 122.  ncu: the warps wait
+// on the memory-instruction queue (stall_mio_throttle) with HBM 58 % busy and 16 warps per SM -- the
+// kernel sits on a latency/occupancy plateau set by 128 registers and 54 KB of ring per block.
 #include <cstdlib>
 
 #include "plbm_internal.h"
