@@ -45,6 +45,23 @@ void c_lw_vars(void* sim, double* rho, double* u);
 void c_lw_free(void* sim);
 double c_lw_norm(int nx, int ny, const double* u, const double* ua);
 
+/* The fourth- and sixth-order Lax-Wendroff plugins `lw4` (sim/sim_lw4.F90: lw4_stream :26-115, lw4_collision
+ * :118-195, lw4_bc :198-245, exports :370-477) and `lw6` (sim/sim_lw6.F90: lw6_stream :26-127, exports at the
+ * end of the file): same collision as `lw`, wider streaming stencils (halo 2 / 3 in the reference, periodic
+ * index arithmetic here).  liblw4.so / liblw6.so drop-ins. */
+void* c_lw4_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params);
+void c_lw4_step(void* sim, double omega);
+void c_lw4_step_n(void* sim, double omega, int n);
+void c_lw4_vars(void* sim, double* rho, double* u);
+void c_lw4_free(void* sim);
+double c_lw4_norm(int nx, int ny, const double* u, const double* ua);
+void* c_lw6_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params);
+void c_lw6_step(void* sim, double omega);
+void c_lw6_step_n(void* sim, double omega, int n);
+void c_lw6_vars(void* sim, double* rho, double* u);
+void c_lw6_free(void* sim);
+double c_lw6_norm(int nx, int ny, const double* u, const double* ua);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,12 @@ class Oracle:
         self._lw_stream = self._fn("orc_lw_stream", None, [I, I, P, P, R])
         self._lw_collision = self._fn("orc_lw_collision", None, [I, I, P, R])
         self._lw_bc = self._fn("orc_lw_bc", None, [I, I, P])
+        # lw4 / lw6 (halo width H = order / 2)
+        self._simh_eqinit = self._fn("orc_simh_eqinit", None, [I, I, I, P, P, P, P])
+        self._simh_macros = self._fn("orc_simh_macros", None, [I, I, I, P, P, P, P])
+        self._lwh_stream = self._fn("orc_lwh_stream", None, [I, I, I, P, P, R])
+        self._lwh_collision = self._fn("orc_lwh_collision", None, [I, I, I, P, R])
+        self._lwh_bc = self._fn("orc_lwh_bc", None, [I, I, I, P])
         self.lib.orc_num_threads.restype = C.c_int
         self.lib.orc_set_num_threads.argtypes = [C.c_int]
 

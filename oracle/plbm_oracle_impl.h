@@ -1089,6 +1089,139 @@ void SFX(orc_lw_bc)(int nx, int ny, REAL *f)
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* Higher-order Lax-Wendroff plugins lw4 / lw6 (sim/sim_lw4.F90, sim/sim_lw6.F90): same DDF-shifted
+ * collision as lw, wider streaming stencils, arrays (1-H:nx+H, 1-H:ny+H, 0:8) with H = 2 / 3. */
+#define HIDX(i, j, k) ((size_t)((i) + H - 1) + (size_t)(nx + 2 * H) * ((size_t)((j) + H - 1) + (size_t)(ny + 2 * H) * (size_t)(k)))
+
+/* lbm_eqinit_fields, sim/sim.F90:181-199, halo width H */
+void SFX(orc_simh_eqinit)(int nx, int ny, int H, REAL *f, const REAL *p, const REAL *u, const REAL *v)
+{
+    const REAL rho0 = R(1.0);
+    for (size_t i = 0; i < (size_t)(nx + 2 * H) * (ny + 2 * H) * 9; ++i) f[i] = R(0.0);
+    for (int j = 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) {
+            size_t m = (size_t)(i - 1) + (size_t)nx * (j - 1);
+            REAL rho = rho0 + p[m] / CSQR;
+            REAL feq[9];
+            SFX(orc_sim_equilibrium)(rho, u[m], v[m], feq);
+            for (int k = 0; k < 9; ++k) f[HIDX(i, j, k)] = feq[k];
+        }
+}
+
+/* lbm_macros, sim/sim.F90:148-179, halo width H */
+void SFX(orc_simh_macros)(int nx, int ny, int H, const REAL *fsrc, REAL *rho, REAL *u, REAL *v)
+{
+    const REAL rho0 = R(1.0);
+    for (int j = 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) {
+            REAL f[9];
+            for (int k = 0; k < 9; ++k) f[k] = fsrc[HIDX(i, j, k)];
+            size_t m = (size_t)(i - 1) + (size_t)nx * (j - 1);
+            rho[m] = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
+            rho[m] = rho[m] + rho0;
+            u[m] = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) / rho[m];
+            v[m] = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / rho[m];
+        }
+}
+
+/* sim/sim_lw4.F90:26-115 lw4_stream (order = 4, H = 2) and sim/sim_lw6.F90:26-127 lw6_stream (order = 6, H = 3) */
+void SFX(orc_lwh_stream)(int order, int nx, int ny, const REAL *fsrc, REAL *fdst, REAL dt)
+{
+    static const int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    static const int cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    const int H = order / 2;
+    for (int j = 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) fdst[HIDX(i, j, 0)] = fsrc[HIDX(i, j, 0)];
+    for (int k = 1; k < 9; ++k) {
+        REAL vx = dt * R(cx[k]), vy = dt * R(cy[k]);
+        REAL vxx = R(0.5) * vx * vx, vyy = R(0.5) * vy * vy, vxy = vx * vy;
+#define FS(di, dj) fsrc[HIDX(i + (di), j + (dj), k)]
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                REAL dfx, dfy, dfxx, dfyy, dfxy;
+                if (order == 4) {
+                    REAL fc = FS(0, 0), fe = FS(1, 0), fw = FS(-1, 0), fee = FS(2, 0), fww = FS(-2, 0);
+                    REAL fn = FS(0, 1), fs = FS(0, -1), fnn = FS(0, 2), fss = FS(0, -2);
+                    REAL fne = FS(1, 1), fnw = FS(-1, 1), fsw = FS(-1, -1), fse = FS(1, -1);
+                    REAL fne2 = FS(2, 2), fnw2 = FS(-2, 2), fsw2 = FS(-2, -2), fse2 = FS(2, -2);
+                    dfx = (R(1.0) / R(12.0)) * (fww - fee) + (R(2.0) / R(3.0)) * (fe - fw);
+                    dfy = (R(1.0) / R(12.0)) * (fss - fnn) + (R(2.0) / R(3.0)) * (fn - fs);
+                    dfxx = -(R(1.0) / R(12.0)) * fww + (R(4.0) / R(3.0)) * fw - (R(5.0) / R(2.0)) * fc + (R(4.0) / R(3.0)) * fe -
+                           (R(1.0) / R(12.0)) * fee;
+                    dfyy = -(R(1.0) / R(12.0)) * fss + (R(4.0) / R(3.0)) * fs - (R(5.0) / R(2.0)) * fc + (R(4.0) / R(3.0)) * fn -
+                           (R(1.0) / R(12.0)) * fnn;
+                    dfxy = (R(1.0) / R(3.0)) * (fne - fnw + fsw - fse) - (R(1.0) / R(48.0)) * (fne2 - fnw2 + fsw2 - fse2);
+                } else {
+                    dfx = (R(1.0) / R(60.0)) * (FS(3, 0) - FS(-3, 0)) - (R(3.0) / R(20.0)) * (FS(2, 0) - FS(-2, 0)) +
+                          (R(3.0) / R(4.0)) * (FS(1, 0) - FS(-1, 0));
+                    dfy = (R(1.0) / R(60.0)) * (FS(0, 3) - FS(0, -3)) - (R(3.0) / R(20.0)) * (FS(0, 2) - FS(0, -2)) +
+                          (R(3.0) / R(4.0)) * (FS(0, 1) - FS(0, -1));
+                    /* `1.0_wp/90_wp`: the integer literal 90 of kind wp is promoted to real */
+                    dfxx = (R(1.0) / R(90.0)) * (FS(-3, 0) + FS(3, 0)) - (R(3.0) / R(20.0)) * (FS(-2, 0) + FS(2, 0)) +
+                           (R(3.0) / R(2.0)) * (FS(-1, 0) + FS(1, 0)) - (R(49.0) / R(18.0)) * (FS(0, 0));
+                    dfyy = (R(1.0) / R(90.0)) * (FS(0, -3) + FS(0, 3)) - (R(3.0) / R(20.0)) * (FS(0, -2) + FS(0, 2)) +
+                           (R(3.0) / R(2.0)) * (FS(0, -1) + FS(0, 1)) - (R(49.0) / R(18.0)) * (FS(0, 0));
+                    dfxy = (R(3.0) / R(8.0)) * (FS(1, 1) - FS(-1, 1) + FS(-1, -1) - FS(1, -1)) -
+                           (R(3.0) / R(80.0)) * (FS(2, 2) - FS(-2, 2) + FS(-2, -2) - FS(2, -2)) +
+                           (R(1.0) / R(360.0)) * (FS(3, 3) - FS(-3, 3) + FS(-3, -3) - FS(3, -3));
+                }
+                fdst[HIDX(i, j, k)] = FS(0, 0) - vx * dfx - vy * dfy + (vxx * dfxx + vxy * dfxy + vyy * dfyy);
+            }
+#undef FS
+    }
+}
+
+/* lw4_collision / lw6_collision (sim/sim_lw4.F90:118-195): identical to lw_collision, halo width H */
+void SFX(orc_lwh_collision)(int nx, int ny, int H, REAL *pdf, REAL omega)
+{
+    const REAL rho0 = R(1.0);
+    const REAL w[9] = {W0, WS, WS, WS, WS, WD, WD, WD, WD};
+    for (int j = 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) {
+            REAL f[9], feq[9];
+            for (int k = 0; k < 9; ++k) f[k] = pdf[HIDX(i, j, k)];
+            REAL rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + rho0;
+            REAL irho = R(1.0) / rho;
+            REAL ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) * irho;
+            REAL uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) * irho;
+            REAL uxx = ux * ux, uyy = uy * uy;
+            REAL indp = -R(1.5) * (uxx + uyy);
+            feq[0] = W0 * rho * (indp);
+            feq[1] = WS * rho * (indp + R(3.0) * ux + R(4.5) * uxx);
+            feq[2] = WS * rho * (indp + R(3.0) * uy + R(4.5) * uyy);
+            feq[3] = WS * rho * (indp - R(3.0) * ux + R(4.5) * uxx);
+            feq[4] = WS * rho * (indp - R(3.0) * uy + R(4.5) * uyy);
+            REAL uxpy = ux + uy;
+            feq[5] = WD * rho * (indp + R(3.0) * uxpy + R(4.5) * uxpy * uxpy);
+            feq[7] = WD * rho * (indp - R(3.0) * uxpy + R(4.5) * uxpy * uxpy);
+            REAL uxmy = ux - uy;
+            feq[6] = WD * rho * (indp - R(3.0) * uxmy + R(4.5) * uxmy * uxmy);
+            feq[8] = WD * rho * (indp + R(3.0) * uxmy + R(4.5) * uxmy * uxmy);
+            for (int k = 0; k < 9; ++k) feq[k] = feq[k] + w[k] * (rho - rho0);
+            for (int k = 0; k < 9; ++k) pdf[HIDX(i, j, k)] = f[k] + omega * (feq[k] - f[k]);
+        }
+}
+
+/* lw4_bc (sim/sim_lw4.F90:198-245, the `#if 1` branch) / lw6_bc (sim/sim_lw6.F90): south and north halo
+ * rows of the interior columns, then west and east halo columns over ALL rows (corners included) */
+void SFX(orc_lwh_bc)(int nx, int ny, int H, REAL *f)
+{
+    for (int k = 0; k < 9; ++k) {
+        for (int h = 0; h < H; ++h)
+            for (int i = 1; i <= nx; ++i) {
+                f[HIDX(i, -h, k)] = f[HIDX(i, ny - h, k)];
+                f[HIDX(i, ny + 1 + h, k)] = f[HIDX(i, 1 + h, k)];
+            }
+        for (int j = 1 - H; j <= ny + H; ++j)
+            for (int h = 0; h < H; ++h) {
+                f[HIDX(-h, j, k)] = f[HIDX(nx - h, j, k)];
+                f[HIDX(nx + 1 + h, j, k)] = f[HIDX(1 + h, j, k)];
+            }
+    }
+}
+#undef HIDX
+
 #undef SIDX
 #undef FIDX
 #undef MIDX

@@ -23,7 +23,8 @@ struct SimState {
     double *f1, *f2;   // [9][ny][nx], DDF-shifted
     double *rho, *u;   // device staging for vars(): rho[ny][nx], u[2][ny][nx]
     cudaStream_t stream;
-    double dt;         // time step (the Lax-Wendroff plugin accepts any dt, slbm requires 1)
+    double dt;         // time step (the Lax-Wendroff plugins accept any dt, slbm requires 1)
+    int order = 2;     // Lax-Wendroff plugins: 2 (lw), 4 (lw4), 6 (lw6)
 };
 
 __device__ __forceinline__ void sim_equilibrium(double rho, double ux, double uy, double (&feq)[9])
@@ -102,18 +103,27 @@ __global__ void k_sim_macros(const double* __restrict__ fsrc, double* __restrict
     u[n + m] = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / r;
 }
 
-// The reference's `lw` plugin (sim/sim_lw.F90): second-order Lax-Wendroff streaming of every population
-// (lw_stream :24-85) followed by the DDF-shifted BGK collision (lw_collision :87-166); the periodic halo
-// copy lw_bc (:169-197) is index arithmetic here.  One fused kernel per step.
+// The reference's Lax-Wendroff plugins `lw`, `lw4`, `lw6` (sim/sim_lw.F90, sim_lw4.F90, sim_lw6.F90):
+// Lax-Wendroff streaming of every population with 2nd / 4th / 6th-order central differences (lw_stream
+// sim_lw.F90:24-85, lw4_stream sim_lw4.F90:26-115, lw6_stream sim_lw6.F90:26-127) followed by the DDF-shifted
+// BGK collision (lw_collision sim_lw.F90:87-166, identical in all three); the periodic halo copies lw*_bc
+// are index arithmetic here.  One fused kernel per step.
+template <int ORDER>
 __global__ void __launch_bounds__(256) k_lw_step(const double* __restrict__ fsrc, double* __restrict__ fdst, int nx, int ny,
                                                  double dt, double omega)
 {
+    constexpr int H = ORDER / 2;
     const size_t n = (size_t)nx * ny;
     const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n) return;
     const int j = (int)(m / nx), i = (int)(m - (size_t)j * nx);
-    const int ip = i + 1 == nx ? 0 : i + 1, im = i == 0 ? nx - 1 : i - 1;
-    const int jp = j + 1 == ny ? 0 : j + 1, jm = j == 0 ? ny - 1 : j - 1;
+    int ix[2 * H + 1], jy[2 * H + 1];  // periodic neighbours i-H..i+H, j-H..j+H (nx, ny >= H)
+#pragma unroll
+    for (int d = -H; d <= H; ++d) {
+        int ii = i + d, jj = j + d;
+        ix[d + H] = ii < 0 ? ii + nx : (ii >= nx ? ii - nx : ii);
+        jy[d + H] = jj < 0 ? jj + ny : (jj >= ny ? jj - ny : jj);
+    }
     const double w0 = 4.0 / 9.0, ws = 1.0 / 9.0, wd = 1.0 / 36.0, rho0 = 1.0;
     const double w[9] = {w0, ws, ws, ws, ws, wd, wd, wd, wd};
     double f[9], feq[9];
@@ -123,13 +133,36 @@ __global__ void __launch_bounds__(256) k_lw_step(const double* __restrict__ fsrc
         const double* fk = fsrc + k * n;
         const double vx = dt * cxi(k), vy = dt * cyi(k);
         const double vxx = 0.5 * vx * vx, vyy = 0.5 * vy * vy, vxy = vx * vy;
-#define F(ii, jj) fk[(size_t)(jj) * nx + (ii)]
-        const double dfx = 0.5 * (F(ip, j) - F(im, j));
-        const double dfy = 0.5 * (F(i, jp) - F(i, jm));
-        const double dfxx = F(ip, j) - 2.0 * F(i, j) + F(im, j);
-        const double dfyy = F(i, jp) - 2.0 * F(i, j) + F(i, jm);
-        const double dfxy = 0.25 * (F(ip, jp) - F(im, jp) + F(im, jm) - F(ip, jm));
-        f[k] = F(i, j) - vx * dfx - vy * dfy + (vxx * dfxx + vxy * dfxy + vyy * dfyy);
+#define F(di, dj) fk[(size_t)jy[(dj) + H] * nx + ix[(di) + H]]
+        double dfx, dfy, dfxx, dfyy, dfxy;
+        if (ORDER == 2) {
+            dfx = 0.5 * (F(1, 0) - F(-1, 0));
+            dfy = 0.5 * (F(0, 1) - F(0, -1));
+            dfxx = F(1, 0) - 2.0 * F(0, 0) + F(-1, 0);
+            dfyy = F(0, 1) - 2.0 * F(0, 0) + F(0, -1);
+            dfxy = 0.25 * (F(1, 1) - F(-1, 1) + F(-1, -1) - F(1, -1));
+        } else if (ORDER == 4) {
+            const double fc = F(0, 0), fe = F(1, 0), fw = F(-1, 0), fee = F(2, 0), fww = F(-2, 0);
+            const double fn = F(0, 1), fs = F(0, -1), fnn = F(0, 2), fss = F(0, -2);
+            const double fne = F(1, 1), fnw = F(-1, 1), fsw = F(-1, -1), fse = F(1, -1);
+            const double fne2 = F(2, 2), fnw2 = F(-2, 2), fsw2 = F(-2, -2), fse2 = F(2, -2);
+            dfx = (1.0 / 12.0) * (fww - fee) + (2.0 / 3.0) * (fe - fw);
+            dfy = (1.0 / 12.0) * (fss - fnn) + (2.0 / 3.0) * (fn - fs);
+            dfxx = -(1.0 / 12.0) * fww + (4.0 / 3.0) * fw - (5.0 / 2.0) * fc + (4.0 / 3.0) * fe - (1.0 / 12.0) * fee;
+            dfyy = -(1.0 / 12.0) * fss + (4.0 / 3.0) * fs - (5.0 / 2.0) * fc + (4.0 / 3.0) * fn - (1.0 / 12.0) * fnn;
+            dfxy = (1.0 / 3.0) * (fne - fnw + fsw - fse) - (1.0 / 48.0) * (fne2 - fnw2 + fsw2 - fse2);
+        } else {
+            dfx = (1.0 / 60.0) * (F(3, 0) - F(-3, 0)) - (3.0 / 20.0) * (F(2, 0) - F(-2, 0)) + (3.0 / 4.0) * (F(1, 0) - F(-1, 0));
+            dfy = (1.0 / 60.0) * (F(0, 3) - F(0, -3)) - (3.0 / 20.0) * (F(0, 2) - F(0, -2)) + (3.0 / 4.0) * (F(0, 1) - F(0, -1));
+            dfxx = (1.0 / 90.0) * (F(-3, 0) + F(3, 0)) - (3.0 / 20.0) * (F(-2, 0) + F(2, 0)) + (3.0 / 2.0) * (F(-1, 0) + F(1, 0)) -
+                   (49.0 / 18.0) * (F(0, 0));
+            dfyy = (1.0 / 90.0) * (F(0, -3) + F(0, 3)) - (3.0 / 20.0) * (F(0, -2) + F(0, 2)) + (3.0 / 2.0) * (F(0, -1) + F(0, 1)) -
+                   (49.0 / 18.0) * (F(0, 0));
+            dfxy = (3.0 / 8.0) * (F(1, 1) - F(-1, 1) + F(-1, -1) - F(1, -1)) -
+                   (3.0 / 80.0) * (F(2, 2) - F(-2, 2) + F(-2, -2) - F(2, -2)) +
+                   (1.0 / 360.0) * (F(3, 3) - F(-3, 3) + F(-3, -3) - F(3, -3));
+        }
+        f[k] = F(0, 0) - vx * dfx - vy * dfy + (vxx * dfxx + vxy * dfxy + vyy * dfyy);
 #undef F
     }
     double rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + rho0;
@@ -195,7 +228,7 @@ static void* sim_init_common(int nx, int ny, double dt, const double* rho, const
         set_error("no CUDA device available: libplbm_b200 has no CPU fallback");
         return nullptr;
     }
-    SimState* s = new SimState{nx, ny, nullptr, nullptr, nullptr, nullptr, nullptr, dt};
+    SimState* s = new SimState{nx, ny, nullptr, nullptr, nullptr, nullptr, nullptr, dt, 2};
     const size_t n = (size_t)nx * ny;
     bool ok = cudaMalloc(&s->f1, 9 * n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->f2, 9 * n * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&s->rho, n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->u, 2 * n * sizeof(double)) == cudaSuccess &&
@@ -283,18 +316,34 @@ double c_slbm_norm(int nx, int ny, const double* u, const double* ua) { return c
 
 // The reference's Lax-Wendroff plugin `lw` (sim/sim_lw.F90:295-425) under its own symbol names:
 // `ln -s libplbm_b200.so liblw.so` is a drop-in for the reference's liblw.so.  Any dt is accepted.
+static void* lw_init_order(int order, int nx, int ny, double dt, const double* rho, const double* u, const double* sigma)
+{
+    if (nx < order / 2 || ny < order / 2) {  // the reference's halo copies need nx, ny >= nhalo
+        set_error("c_lw*_init: grid smaller than the stencil halo");
+        return nullptr;
+    }
+    SimState* s = static_cast<SimState*>(sim_init_common(nx, ny, dt, rho, u, sigma, false));
+    if (s) s->order = order;
+    return s;
+}
 void* c_lw_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
 {
     (void)params;
-    return sim_init_common(nx, ny, dt, rho, u, sigma, false);
+    return lw_init_order(2, nx, ny, dt, rho, u, sigma);
 }
 void c_lw_step_n(void* sim, double omega, int n)
 {
     SimState* s = static_cast<SimState*>(sim);
     if (!s) return;
     const size_t nn = (size_t)s->nx * s->ny;
+    const unsigned nb = (unsigned)((nn + 255) / 256);
     for (int it = 0; it < n; ++it) {
-        k_lw_step<<<(unsigned)((nn + 255) / 256), 256, 0, s->stream>>>(s->f1, s->f2, s->nx, s->ny, s->dt, omega);
+        if (s->order == 6)
+            k_lw_step<6><<<nb, 256, 0, s->stream>>>(s->f1, s->f2, s->nx, s->ny, s->dt, omega);
+        else if (s->order == 4)
+            k_lw_step<4><<<nb, 256, 0, s->stream>>>(s->f1, s->f2, s->nx, s->ny, s->dt, omega);
+        else
+            k_lw_step<2><<<nb, 256, 0, s->stream>>>(s->f1, s->f2, s->nx, s->ny, s->dt, omega);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         double* t = s->f1;
         s->f1 = s->f2;
@@ -305,5 +354,29 @@ void c_lw_step(void* sim, double omega) { c_lw_step_n(sim, omega, 1); }
 void c_lw_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
 void c_lw_free(void* sim) { c_plbm_free(sim); }
 double c_lw_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
+
+// `lw4` (sim/sim_lw4.F90:370-477) and `lw6` (sim/sim_lw6.F90) under their own symbol names: the step, vars,
+// free and norm entries are shared with `lw` (the order lives in the handle).
+void* c_lw4_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    (void)params;
+    return lw_init_order(4, nx, ny, dt, rho, u, sigma);
+}
+void c_lw4_step_n(void* sim, double omega, int n) { c_lw_step_n(sim, omega, n); }
+void c_lw4_step(void* sim, double omega) { c_lw_step_n(sim, omega, 1); }
+void c_lw4_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
+void c_lw4_free(void* sim) { c_plbm_free(sim); }
+double c_lw4_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
+
+void* c_lw6_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    (void)params;
+    return lw_init_order(6, nx, ny, dt, rho, u, sigma);
+}
+void c_lw6_step_n(void* sim, double omega, int n) { c_lw_step_n(sim, omega, n); }
+void c_lw6_step(void* sim, double omega) { c_lw_step_n(sim, omega, 1); }
+void c_lw6_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
+void c_lw6_free(void* sim) { c_plbm_free(sim); }
+double c_lw6_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
 
 }  // extern "C"

@@ -363,27 +363,42 @@ def test_sim_plugin_seam(plbm):
 
 
 @pytest.mark.parametrize("dt", [1.0, 0.4])
-def test_sim_lw_plugin_seam(plbm, dt):
-    """c_lw_{init,step,vars,free}: the reference's Lax-Wendroff plugin (sim/sim_lw.F90) vs its oracle."""
+@pytest.mark.parametrize("name,order", [("lw", 2), ("lw4", 4), ("lw6", 6)])
+def test_sim_lw_plugin_seam(plbm, dt, name, order):
+    """c_lw_* / c_lw4_* / c_lw6_* {init,step,vars,free}: the reference's Lax-Wendroff plugins (sim/sim_lw.F90,
+    sim_lw4.F90, sim_lw6.F90) vs their oracle (haloed arrays + periodic halo copies), bit for bit."""
     nx, ny, steps, omega = 40, 56, 12, 1.4
+    H = order // 2
     o = Oracle("f64")
     rng = np.random.default_rng(12)
     p = 1e-3 * rng.standard_normal((ny, nx))
     u = 0.05 * rng.standard_normal((2, ny, nx))
-    f1 = np.zeros((9, ny + 2, nx + 2))
+    f1 = np.zeros((9, ny + 2 * H, nx + 2 * H))
     f2 = np.zeros_like(f1)
     P = lambda a: a.ctypes.data  # noqa: E731
-    o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
-    o._lw_bc(nx, ny, P(f1))
+    if order == 2:
+        eqinit = lambda f: o._sim_eqinit(nx, ny, P(f), P(p), P(u[0]), P(u[1]))  # noqa: E731
+        stream = lambda a, b: o._lw_stream(nx, ny, P(a), P(b), dt)  # noqa: E731
+        collide = lambda f: o._lw_collision(nx, ny, P(f), omega)  # noqa: E731
+        bc = lambda f: o._lw_bc(nx, ny, P(f))  # noqa: E731
+        macros = lambda f, r, a, b: o._sim_macros(nx, ny, P(f), P(r), P(a), P(b))  # noqa: E731
+    else:
+        eqinit = lambda f: o._simh_eqinit(nx, ny, H, P(f), P(p), P(u[0]), P(u[1]))  # noqa: E731
+        stream = lambda a, b: o._lwh_stream(order, nx, ny, P(a), P(b), dt)  # noqa: E731
+        collide = lambda f: o._lwh_collision(nx, ny, H, P(f), omega)  # noqa: E731
+        bc = lambda f: o._lwh_bc(nx, ny, H, P(f))  # noqa: E731
+        macros = lambda f, r, a, b: o._simh_macros(nx, ny, H, P(f), P(r), P(a), P(b))  # noqa: E731
+    eqinit(f1)
+    bc(f1)
     for _ in range(steps):
-        o._lw_stream(nx, ny, P(f1), P(f2), dt)
-        o._lw_collision(nx, ny, P(f2), omega)
-        o._lw_bc(nx, ny, P(f2))
+        stream(f1, f2)
+        collide(f2)
+        bc(f2)
         f1, f2 = f2, f1
     rho_w, u_w, v_w = np.zeros((ny, nx)), np.zeros((ny, nx)), np.zeros((ny, nx))
-    o._sim_macros(nx, ny, P(f1), P(rho_w), P(u_w), P(v_w))
+    macros(f1, rho_w, u_w, v_w)
 
-    sim = plbm.SimPlugin(name="lw")
+    sim = plbm.SimPlugin(name=name)
     sim.init((nx, ny), dt, p, u)
     sim.step(omega)
     sim.step(omega, n=steps - 1)

@@ -90,3 +90,58 @@ def test_vorticity_of_the_taylor_green_field():
     x = np.arange(n) + 0.5
     exact = 2 * k * 0.01 * np.cos(k * x)[:, None] * np.cos(k * x)[None, :]
     assert np.abs(om - exact).max() < 1e-3 * np.abs(exact).max()
+
+
+@pytest.mark.parametrize("order", [4, 6])
+def test_higher_order_lax_wendroff_stencils_are_exact_for_polynomials(order):
+    """lw4_stream / lw6_stream (sim/sim_lw4.F90:26-115, sim/sim_lw6.F90:26-127): the finite-difference
+    stencils differentiate polynomials of total degree <= order exactly, so one streaming step of such a field
+    equals its second-order Taylor shift  f - v.grad f + 1/2 v v : grad grad f  (the Lax-Wendroff update)."""
+    o = Oracle("f64")
+    H = order // 2
+    nx, ny, dt = 9, 7, 0.37
+    rng = np.random.default_rng(order)
+    powers = [(a, b) for a in range(order + 1) for b in range(order + 1 - a)]
+    coef = {ab: rng.standard_normal() for ab in powers}
+    # coordinates centred on the grid keep the monomials O(1..1e4); the halo is filled with the polynomial itself
+    X = (np.arange(1 - H, nx + H + 1) - (nx + 1) / 2.0)[None, :]
+    Y = (np.arange(1 - H, ny + H + 1) - (ny + 1) / 2.0)[:, None]
+
+    def poly(da=0, db=0):
+        out = np.zeros((ny + 2 * H, nx + 2 * H))
+        for (a, b), c in coef.items():
+            if a < da or b < db:
+                continue
+            ca = np.prod([a - i for i in range(da)]) if da else 1.0
+            cb = np.prod([b - i for i in range(db)]) if db else 1.0
+            out += c * ca * cb * X ** (a - da) * Y ** (b - db)
+        return out
+
+    fsrc = np.ascontiguousarray(np.broadcast_to(poly(), (9, ny + 2 * H, nx + 2 * H)))
+    fdst = np.zeros_like(fsrc)
+    o._lwh_stream(order, nx, ny, fsrc.ctypes.data, fdst.ctypes.data, dt)
+    cx = [0, 1, 0, -1, 0, 1, -1, -1, 1]
+    cy = [0, 0, 1, 0, -1, 1, 1, -1, -1]
+    fx, fy, fxx, fxy, fyy = poly(1, 0), poly(0, 1), poly(2, 0), poly(1, 1), poly(0, 2)
+    inner = (slice(H, H + ny), slice(H, H + nx))
+    scale = np.abs(fsrc[0][inner]).max()
+    for k in range(9):
+        vx, vy = dt * cx[k], dt * cy[k]
+        want = poly() - vx * fx - vy * fy + 0.5 * vx * vx * fxx + vx * vy * fxy + 0.5 * vy * vy * fyy
+        assert np.abs(fdst[k][inner] - want[inner]).max() < 1e-11 * scale, k
+
+
+@pytest.mark.parametrize("order", [4, 6])
+def test_higher_order_lax_wendroff_halo_is_the_periodic_image(order):
+    """lw4_bc / lw6_bc fill the H-wide halo (corners included) with the periodic image of the interior."""
+    o = Oracle("f64")
+    H = order // 2
+    nx, ny = 7, 5
+    rng = np.random.default_rng(3)
+    inner = rng.standard_normal((9, ny, nx))
+    f = np.full((9, ny + 2 * H, nx + 2 * H), np.nan)
+    f[:, H:H + ny, H:H + nx] = inner
+    o._lwh_bc(nx, ny, H, f.ctypes.data)
+    jj = (np.arange(-H, ny + H) % ny)[:, None]
+    ii = (np.arange(-H, nx + H) % nx)[None, :]
+    assert np.array_equal(f, inner[:, jj, ii])

@@ -52,9 +52,10 @@ sim.init((33, 21), 1.0, np.zeros((21, 33)), np.zeros((2, 21, 33)))
 sim.step(1.3, n=3)
 sim.vars()
 sim.free()
-lw = p.SimPlugin(name="lw")
-lw.init((33, 21), 0.5, np.zeros((21, 33)), np.zeros((2, 21, 33)))
-lw.step(1.3, n=3)
-lw.vars()
-lw.free()
+for name in ("lw", "lw4", "lw6"):
+    lw = p.SimPlugin(name=name)
+    lw.init((33, 21), 0.5, np.zeros((21, 33)), np.zeros((2, 21, 33)))
+    lw.step(1.3, n=3)
+    lw.vars()
+    lw.free()
 print("sanitize run complete, launches:", p.launch_count())
