@@ -170,6 +170,10 @@ long long plbm_launch_count(void);
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
  *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused */
 int plbm_set_variant(plbm_handle grid, int variant);
+/* derivative stencil of stream_fdm_bardow: the reference selects it at compile time with -DFDM_WLS,
+ * -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660); default = none of them. */
+enum plbm_fdm_stencil { PLBM_FDM_DEFAULT = 0, PLBM_FDM_WLS = 1, PLBM_FDM_WLS_GAUSS_V1 = 2, PLBM_FDM_WLS_GAUSS_V2 = 3, PLBM_FDM_ISO = 4 };
+int plbm_set_fdm_stencil(plbm_handle grid, int stencil);
 
 /* ---- flow cases (host side, O(N) input generators) ------------------------------------- */
 /* taylor_green_t%decay_time / %eval (src/benchmarks/taylor_green.f90:31-84): fills host

@@ -74,6 +74,7 @@ class Oracle:
         self._magic = self._fn("orc_magic_number", R, [R, R])
         self._fvm = self._fn("orc_stream_fvm_bardow", None, [I, I, I, P, P, R])
         self._fdm_bardow = self._fn("orc_stream_fdm_bardow", None, [I, I, I, P, P, R])
+        self._fdm_bardow_stencil = self._fn("orc_stream_fdm_bardow_stencil", None, [I, I, I, P, P, R, I])
         self._fdm_sofonea = self._fn("orc_stream_fdm_sofonea", None, [I, I, I, P, P, R])
         self._dcollide = self._fn("orc_dugks_collide", None, [I, I, I, P, P, R, R, R, I])
         self._dstream = self._fn("orc_dugks_stream", None, [I, I, I, P, P, R, R, I])
@@ -177,8 +178,15 @@ class Oracle:
     def stream_fvm_bardow(self, fold, fnew, ny, dt):
         self._fvm(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)
 
-    def stream_fdm_bardow(self, fold, fnew, ny, dt):
-        self._fdm_bardow(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)
+    FDM_STENCILS = {"default": 0, "wls": 1, "wls_gauss_v1": 2, "wls_gauss_v2": 3, "iso": 4}
+
+    def stream_fdm_bardow(self, fold, fnew, ny, dt, stencil=0):
+        """stencil: 0 default build, 1 -DFDM_WLS, 2 -DFDM_WLS_GAUSS_V1, 3 -DFDM_WLS_GAUSS_V2, 4 -DFDM_ISO"""
+        stencil = self.FDM_STENCILS.get(stencil, stencil)
+        if stencil == 0:
+            self._fdm_bardow(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)
+        else:
+            self._fdm_bardow_stencil(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt, int(stencil))
 
     def stream_fdm_sofonea(self, fold, fnew, ny, dt):
         self._fdm_sofonea(fold.shape[1], ny, fold.shape[2], self._p(self._chk(fold)), self._p(self._chk(fnew)), dt)

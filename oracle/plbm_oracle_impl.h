@@ -607,6 +607,75 @@ void SFX(orc_stream_fdm_bardow)(int nx, int ny, int ld, const REAL *fold, REAL *
     }
 }
 
+/* stream_fdm_bardow built with -DFDM_WLS (stencil 1), -DFDM_WLS_GAUSS_V1 (2), -DFDM_WLS_GAUSS_V2 (3) or
+ * -DFDM_ISO (4): src/fvm_bardow.F90:591-660.  stencil 0 is the default build (orc_stream_fdm_bardow). */
+void SFX(orc_stream_fdm_bardow_stencil)(int nx, int ny, int ld, const REAL *fold, REAL *fnew, REAL dt, int stencil)
+{
+    const REAL p2 = R(0.5);
+    const REAL two_thirds = R(2.0) / R(3.0), one_sixth = R(1.0) / R(6.0);
+    const REAL five_sixths = R(10.0) / R(12.0), one_twelth = R(1.0) / R(12.0);
+    const REAL one_third = R(1.0) / R(3.0);
+    REAL p1s = R(0.0), p1d = R(0.0), p2c = R(0.0), p2d1 = R(0.0), p2d2 = R(0.0), p2d = R(0.0);
+    if (stencil == 2) {
+        p1s = R(0.2880584423829145035434), p1d = R(0.1059707788085427065949);
+        p2c = R(-1.152233769531658458263), p2d1 = R(0.5761168847658292291314);
+        p2d2 = R(-0.4238831152341712149578), p2d = R(0.2119415576170855242122);
+    } else if (stencil == 3) {
+        p1s = R(0.3934930210807994210853), p1d = R(0.05325348945960039354075);
+        p2c = R(-1.573972084323197018207), p2d1 = R(0.7869860421615988421706);
+        p2d2 = R(-0.2130139578384016019186), p2d = R(0.1065069789192007732037);
+    }
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y) fnew[FIDX(y, x, 0)] = fold[FIDX(y, x, 0)];
+    for (int q = 1; q < 9; ++q) {
+        REAL cxq = dt * R(SFX(ocx)[q]);
+        REAL cyq = dt * R(SFX(ocy)[q]);
+        REAL cxxq = R(0.5) * cxq * cxq;
+        REAL cyyq = R(0.5) * cyq * cyq;
+        REAL cxyq = cxq * cyq;
+        const REAL *fq = fold + FIDX(0, 0, q);
+#define FQ(yy, xx) fq[(size_t)(yy) + (size_t)ld * (size_t)(xx)]
+        for (int x = 0; x < nx; ++x) {
+            int xp1 = WRAP_P1(x, nx);
+            int xm1 = WRAP_M1(x, nx);
+            for (int y = 0; y < ny; ++y) {
+                int yp1 = WRAP_P1(y, ny);
+                int ym1 = WRAP_M1(y, ny);
+                REAL fc = FQ(y, x), fe = FQ(y, xp1), fn = FQ(yp1, x), fw = FQ(y, xm1), fs = FQ(ym1, x);
+                REAL fne = FQ(yp1, xp1), fnw = FQ(yp1, xm1), fsw = FQ(ym1, xm1), fse = FQ(ym1, xp1);
+                REAL dfx, dfy, dfxx, dfyy, dfxy;
+                if (stencil == 1) {
+                    dfx = one_sixth * ((fne - fnw) + (fe - fw) + (fse - fsw));
+                    dfy = one_sixth * ((fne - fse) + (fn - fs) + (fnw - fsw));
+                    dfxx = one_third * (fne - R(2.0) * fn + fnw) + one_third * (fe - R(2.0) * fc + fw) + one_third * (fse - R(2.0) * fs + fsw);
+                    dfyy = one_third * (fne - R(2.0) * fe + fse) + one_third * (fn - R(2.0) * fc + fs) + one_third * (fnw - R(2.0) * fw + fsw);
+                    dfxy = R(0.25) * (fne - fnw + fsw - fse);
+                } else if (stencil == 2 || stencil == 3) {
+                    dfx = p1s * (fe - fw) + p1d * (fne - fnw) + p1d * (fse - fsw);
+                    dfy = p1s * (fn - fs) + p1d * (fne - fse) + p1d * (fnw - fsw);
+                    dfxx = p2c * fc + p2d1 * (fe + fw) + p2d2 * (fn + fs) + p2d * (fne + fnw + fsw + fse);
+                    dfyy = p2c * fc + p2d2 * (fe + fw) + p2d1 * (fn + fs) + p2d * (fne + fnw + fsw + fse);
+                    dfxy = R(0.25) * (fne - fnw + fsw - fse);
+                } else if (stencil == 4) {
+                    dfx = p2 * (one_sixth * (fne - fnw) + two_thirds * (fe - fw) + one_sixth * (fse - fsw));
+                    dfy = p2 * (one_sixth * (fne - fse) + two_thirds * (fn - fs) + one_sixth * (fnw - fsw));
+                    dfxx = one_twelth * (fne - R(2.0) * fn + fnw) + five_sixths * (fe - R(2.0) * fc + fw) + one_twelth * (fse - R(2.0) * fs + fsw);
+                    dfyy = one_twelth * (fne - R(2.0) * fe + fse) + five_sixths * (fn - R(2.0) * fc + fs) + one_twelth * (fnw - R(2.0) * fw + fsw);
+                    dfxy = R(0.25) * (fne - fse - fnw + fsw);
+                } else {
+                    dfx = p2 * (fe - fw);
+                    dfy = p2 * (fn - fs);
+                    dfxx = fe - R(2.0) * fc + fw;
+                    dfyy = fn - R(2.0) * fc + fs;
+                    dfxy = R(0.25) * (fne - fse - fnw + fsw);
+                }
+                fnew[FIDX(y, x, q)] = fc - cxq * dfx - cyq * dfy + (cxxq * dfxx + cxyq * dfxy + cyyq * dfyy);
+            }
+        }
+#undef FQ
+    }
+}
+
 /* src/fvm_bardow.F90:702-891 fdm_sofonea_kernel: per population, 1-D Lax-Wendroff along its own
  * characteristic; fu = f(x + c_q), fd = f(x - c_q).  (Loop bounds swapped in the reference, F9.) */
 void SFX(orc_stream_fdm_sofonea)(int nx, int ny, int ld, const REAL *fold, REAL *fnew, REAL dt)

@@ -185,6 +185,17 @@ template <typename T> int fv_sweep(Grid& g, int streaming, int model, const Coll
     const int mode = fv_mode(streaming);
     const bool fusable = model == M_NONE || mode == 2 || model <= PLBM_RR;
     const int kmodel = fusable ? model : (int)M_NONE;
+    if (streaming == PLBM_STREAM_FDM_BARDOW && g.fdm_stencil != 0) {
+        // the reference's -DFDM_WLS* / -DFDM_ISO builds of stream_fdm_bardow: plain-load tile kernel, collision as a second launch
+        if (g.comm) {
+            set_error("stream_fdm_bardow: the alternative stencils are not available under a slab decomposition");
+            return PLBM_ERR_ARG;
+        }
+        rc = launch_fvm_bardow<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, M_NONE, cp, g.stream, 5 + g.fdm_stencil);
+        if (rc || model == M_NONE) return rc;
+        LbmArgs<T> c = lbm_args<T>(g, g.inew, g.inew, model);
+        return launch_lbm<T>(c, model, false, g.variant, g.stream);
+    }
     if (g.comm && (rc = comm_fv_exchange<T>(g, g.lat<T>(g.iold)))) return rc;  // slab: neighbours' boundary lines
     if ((g.variant == 0 || g.comm) && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
         rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), mode, kmodel, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
@@ -778,6 +789,18 @@ int plbm_synchronize(plbm_handle g)
     int rc = check(g);
     if (rc) return rc;
     PLBM_CUDA(cudaStreamSynchronize(g->stream));
+    return PLBM_OK;
+}
+
+int plbm_set_fdm_stencil(plbm_handle g, int stencil)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (stencil < PLBM_FDM_DEFAULT || stencil > PLBM_FDM_ISO) {
+        set_error("set_fdm_stencil: unknown stencil");
+        return PLBM_ERR_ARG;
+    }
+    g->fdm_stencil = stencil;
     return PLBM_OK;
 }
 

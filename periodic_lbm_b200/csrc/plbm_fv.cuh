@@ -167,4 +167,58 @@ template <typename T, bool SOFONEA, int PITCH, int PLANE> __device__ __forceinli
 #undef PLBM_FDM_Q
 }
 
+// stream_fdm_bardow built with -DFDM_WLS (STENCIL 1), -DFDM_WLS_GAUSS_V1 (2), -DFDM_WLS_GAUSS_V2 (3) or -DFDM_ISO (4):
+// the cpp alternatives of the derivative stencils, src/fvm_bardow.F90:591-660, evaluated in full in the
+// reference's operation order (every population uses all eight neighbours here).
+template <typename T, int Q, int PITCH, int STENCIL> __device__ __forceinline__ T fdm_bardow_stencil_pop(const T* c, T dt)
+{
+    const T cxq = dt * T(cxi(Q)), cyq = dt * T(cyi(Q));
+    const T cxxq = T(0.5) * cxq * cxq, cyyq = T(0.5) * cyq * cyq, cxyq = cxq * cyq;
+    const T fc = c[0], fe = c[PITCH], fw = c[-PITCH], fn = c[1], fs = c[-1];
+    const T fne = c[PITCH + 1], fnw = c[-PITCH + 1], fse = c[PITCH - 1], fsw = c[-PITCH - 1];
+    const T one_sixth = T(1) / T(6), two_thirds = T(2) / T(3), five_sixths = T(10) / T(12), one_twelth = T(1) / T(12);
+    const T one_third = T(1) / T(3);
+    T dfx, dfy, dfxx, dfyy, dfxy;
+    if (STENCIL == 1) {
+        dfx = one_sixth * ((fne - fnw) + (fe - fw) + (fse - fsw));
+        dfy = one_sixth * ((fne - fse) + (fn - fs) + (fnw - fsw));
+        dfxx = one_third * (fne - T(2) * fn + fnw) + one_third * (fe - T(2) * fc + fw) + one_third * (fse - T(2) * fs + fsw);
+        dfyy = one_third * (fne - T(2) * fe + fse) + one_third * (fn - T(2) * fc + fs) + one_third * (fnw - T(2) * fw + fsw);
+        dfxy = T(0.25) * (fne - fnw + fsw - fse);
+    } else if (STENCIL == 2 || STENCIL == 3) {
+        const T p1s = STENCIL == 2 ? T(0.2880584423829145035434) : T(0.3934930210807994210853);
+        const T p1d = STENCIL == 2 ? T(0.1059707788085427065949) : T(0.05325348945960039354075);
+        const T p2c = STENCIL == 2 ? T(-1.152233769531658458263) : T(-1.573972084323197018207);
+        const T p2d1 = STENCIL == 2 ? T(0.5761168847658292291314) : T(0.7869860421615988421706);
+        const T p2d2 = STENCIL == 2 ? T(-0.4238831152341712149578) : T(-0.2130139578384016019186);
+        const T p2d = STENCIL == 2 ? T(0.2119415576170855242122) : T(0.1065069789192007732037);
+        dfx = p1s * (fe - fw) + p1d * (fne - fnw) + p1d * (fse - fsw);
+        dfy = p1s * (fn - fs) + p1d * (fne - fse) + p1d * (fnw - fsw);
+        dfxx = p2c * fc + p2d1 * (fe + fw) + p2d2 * (fn + fs) + p2d * (fne + fnw + fsw + fse);
+        dfyy = p2c * fc + p2d2 * (fe + fw) + p2d1 * (fn + fs) + p2d * (fne + fnw + fsw + fse);
+        dfxy = T(0.25) * (fne - fnw + fsw - fse);
+    } else {
+        dfx = T(0.5) * (one_sixth * (fne - fnw) + two_thirds * (fe - fw) + one_sixth * (fse - fsw));
+        dfy = T(0.5) * (one_sixth * (fne - fse) + two_thirds * (fn - fs) + one_sixth * (fnw - fsw));
+        dfxx = one_twelth * (fne - T(2) * fn + fnw) + five_sixths * (fe - T(2) * fc + fw) + one_twelth * (fse - T(2) * fs + fsw);
+        dfyy = one_twelth * (fne - T(2) * fe + fse) + five_sixths * (fn - T(2) * fc + fs) + one_twelth * (fnw - T(2) * fw + fsw);
+        dfxy = T(0.25) * (fne - fse - fnw + fsw);
+    }
+    return fc - cxq * dfx - cyq * dfy + (cxxq * dfxx + cxyq * dfxy + cyyq * dfyy);
+}
+
+template <typename T, int STENCIL, int PITCH, int PLANE> __device__ __forceinline__ void fdm_stencil_update(const T* c0, T dt, T (&fp)[9])
+{
+#define PLBM_FDM_Q(Q) fp[Q] = fdm_bardow_stencil_pop<T, Q, PITCH, STENCIL>(c0 + Q * PLANE, dt)
+    PLBM_FDM_Q(1);
+    PLBM_FDM_Q(2);
+    PLBM_FDM_Q(3);
+    PLBM_FDM_Q(4);
+    PLBM_FDM_Q(5);
+    PLBM_FDM_Q(6);
+    PLBM_FDM_Q(7);
+    PLBM_FDM_Q(8);
+#undef PLBM_FDM_Q
+}
+
 }  // namespace plbm

@@ -43,7 +43,8 @@ constexpr int NHALO = GX * GY - FX * FY; // 84 ring nodes
 //   stage 2: faces from the tile, face relaxation (DUGKS), flux update, collision (Bardow), store.
 // fbar^+ of the previous step (what the reference leaves in lattice `inew`, read by the lagged
 // update_macros) is not stored: it is recomputed on demand from fin, bit-identically.
-enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2, MODE_FDM_BARDOW = 4, MODE_FDM_SOFONEA = 5 };
+// MODE_FDM_STENCIL + k (k = 1..4): stream_fdm_bardow with the reference's -DFDM_WLS / _GAUSS_V1 / _GAUSS_V2 / -DFDM_ISO stencils
+enum { MODE_DUGKS = 0, MODE_DUGKS_OFF = 1, MODE_BARDOW = 2, MODE_FDM_BARDOW = 4, MODE_FDM_SOFONEA = 5, MODE_FDM_STENCIL = 5 };
 
 template <typename T, int MODE, int MODEL>
 __global__ void __launch_bounds__(FY* FX, 2)
@@ -98,7 +99,9 @@ __global__ void __launch_bounds__(FY* FX, 2)
     if (!active) return;
 
     const T* c0 = sm + (tx + 1) * PITCH + (ty + 1);
-    if (MODE == MODE_FDM_BARDOW || MODE == MODE_FDM_SOFONEA)
+    if (MODE > MODE_FDM_STENCIL)
+        fdm_stencil_update<T, MODE - MODE_FDM_STENCIL, PITCH, GX * PITCH>(c0, dt, fp);
+    else if (MODE == MODE_FDM_BARDOW || MODE == MODE_FDM_SOFONEA)
         fdm_update<T, MODE == MODE_FDM_SOFONEA, PITCH, GX * PITCH>(c0, dt, fp);
     else
         flux_update<T, MODE == MODE_DUGKS, PITCH, GX * PITCH>(c0, dt, omega_face, fp);
@@ -121,6 +124,20 @@ static int launch_fv(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T o
 template <typename T>
 int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s, int mode)
 {
+    if (mode > MODE_FDM_STENCIL) {  // alternative derivative stencils of stream_fdm_bardow: streaming only
+        if (model != M_NONE) {
+            set_error("fdm stencil variants: the collision is a separate launch");
+            return PLBM_ERR_ARG;
+        }
+        switch (mode - MODE_FDM_STENCIL) {
+        case 1: return launch_fv<T, MODE_FDM_STENCIL + 1, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        case 2: return launch_fv<T, MODE_FDM_STENCIL + 2, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        case 3: return launch_fv<T, MODE_FDM_STENCIL + 3, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        case 4: return launch_fv<T, MODE_FDM_STENCIL + 4, M_NONE>(g, fold, fnew, dt, T(0), T(0), T(0), cp, s);
+        }
+        set_error("fdm stencil variants: unknown stencil");
+        return PLBM_ERR_ARG;
+    }
     if (mode == MODE_FDM_BARDOW || mode == MODE_FDM_SOFONEA) {  // plain-load fallback of the FDM schemes
         const bool sof = mode == MODE_FDM_SOFONEA;
         switch (model) {

@@ -44,6 +44,7 @@ struct Grid {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int variant = 0;
+    int fdm_stencil = 0;  // stream_fdm_bardow derivative stencil: 0 default, 1 WLS, 2/3 WLS-Gauss v1/v2, 4 isotropic
     int sm_count = 148;
     Comm* comm = nullptr;
     // After a fused DUGKS step lattice `inew` still holds ftilde^n, whereas the reference leaves

@@ -184,8 +184,22 @@ contains
       call plbm_check(plbm_stream_fvm_bardow(grid%dev), "stream_fvm_bardow")
    end subroutine
 
+   !> The reference selects the derivative stencil at compile time (src/fvm_bardow.F90:591-660);
+   !! compile this shim with the same macro and the library uses the same stencil.
    subroutine stream_fdm_bardow(grid)
       class(lattice_grid), intent(inout) :: grid
+#if defined(FDM_WLS)
+      integer(c_int), parameter :: stencil = 1
+#elif defined(FDM_WLS_GAUSS_V1)
+      integer(c_int), parameter :: stencil = 2
+#elif defined(FDM_WLS_GAUSS_V2)
+      integer(c_int), parameter :: stencil = 3
+#elif defined(FDM_ISO)
+      integer(c_int), parameter :: stencil = 4
+#else
+      integer(c_int), parameter :: stencil = 0
+#endif
+      call plbm_check(plbm_set_fdm_stencil(grid%dev, stencil), "set_fdm_stencil")
       call plbm_check(plbm_stream_fdm_bardow(grid%dev), "stream_fdm_bardow")
    end subroutine
 

@@ -2,7 +2,7 @@
 !! One interface per exported entry point; names and argument order are those of the header.
 !! SOURCE ONLY: no Fortran compiler exists in the image this library was developed in
 !! (SURVEY.md F1), so these modules have not been compiled there.  Build line on a machine with
-!! gfortran:  gfortran -c -cpp precision.F90 plbm_c.f90 fvm_bardow.f90 periodic_lbm.f90 ...
+!! gfortran:  gfortran -c -cpp precision.F90 plbm_c.f90 fvm_bardow.F90 periodic_lbm.F90 ...
 !!            gfortran app.f90 *.o -L<repo>/periodic_lbm_b200 -lplbm_b200
 module plbm_c
    use, intrinsic :: iso_c_binding
@@ -92,6 +92,12 @@ module plbm_c
       function plbm_stream_fdm_bardow(grid) bind(c, name="plbm_stream_fdm_bardow") result(stat)
          import :: c_ptr, c_int
          type(c_ptr), value :: grid
+         integer(c_int) :: stat
+      end function
+      function plbm_set_fdm_stencil(grid, stencil) bind(c, name="plbm_set_fdm_stencil") result(stat)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: grid
+         integer(c_int), value :: stencil
          integer(c_int) :: stat
       end function
       function plbm_stream_fdm_sofonea(grid) bind(c, name="plbm_stream_fdm_sofonea") result(stat)

@@ -113,6 +113,13 @@ class LatticeGrid:
     def set_variant(self, variant):
         check(lib.plbm_set_variant(self._h, int(variant)), "set_variant")
 
+    FDM_STENCILS = {"default": 0, "wls": 1, "wls_gauss_v1": 2, "wls_gauss_v2": 3, "iso": 4}
+
+    def set_fdm_stencil(self, stencil):
+        """Derivative stencil of stream_fdm_bardow; the reference picks it at compile time with -DFDM_WLS,
+        -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660)."""
+        check(lib.plbm_set_fdm_stencil(self._h, int(self.FDM_STENCILS.get(stencil, stencil))), "set_fdm_stencil")
+
     def diagnostics(self):
         """max/min |u|, sum(rho), kinetic energy of the device-resident macroscopic fields."""
         out = (C.c_double * capi.DIAG_COUNT)()

@@ -200,6 +200,28 @@ def test_fdm_streaming_schemes(plbm, nx, ny, prec, scheme):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("stencil", ["wls", "wls_gauss_v1", "wls_gauss_v2", "iso"])
+@pytest.mark.parametrize("nx,ny", [(64, 64), (67, 53), (5, 3)])
+def test_fdm_bardow_cpp_stencils(plbm, nx, ny, prec, stencil):
+    """stream_fdm_bardow as built with -DFDM_WLS / -DFDM_WLS_GAUSS_V1 / -DFDM_WLS_GAUSS_V2 / -DFDM_ISO
+    (src/fvm_bardow.F90:591-660): the streaming entry alone, then 4 x perform_step with collide_bgk."""
+    og, g = make_pair(plbm, nx, ny, prec, nu=0.02, dt=0.4)
+    g.set_fdm_stencil(stencil)
+    plbm.stream_fdm_bardow(g)
+    og.o.stream_fdm_bardow(og.lattice(og.iold), og.lattice(og.inew), ny, og.props["dt"], stencil)
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    g.collision, g.streaming = plbm.collide_bgk, plbm.stream_fdm_bardow
+    plbm.perform_step(g, 4)
+    for _ in range(4):
+        og.o.stream_fdm_bardow(og.lattice(og.iold), og.lattice(og.inew), ny, og.props["dt"], stencil)
+        og.o.collide_bgk(og.lattice(og.inew), ny, og.props["omega"])
+        og.idx[:] = og.idx[::-1].copy()  # swap(iold, inew)
+    assert (g.iold, g.inew) == (og.iold, og.inew)
+    assert_same_lattice(g, og, g.iold, og.iold, ny)
+    plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("scheme", ["lbm", "fvm"])
 def test_perform_triple_step(plbm, prec, scheme):
     """perform_triple_step (src/fvm_bardow.F90:322-340): post-collision in iold, pre-collision in imid."""

@@ -32,6 +32,10 @@ for prec in ("f64", "f32"):
                     g.collision, g.streaming = p.collide_rr, stream
                     p.perform_step(g, 2)
                     stream(g)
+                for stencil in ("wls", "wls_gauss_v1", "wls_gauss_v2", "iso", "default"):
+                    g.set_fdm_stencil(stencil)
+                    g.collision, g.streaming = p.collide_trt, p.stream_fdm_bardow
+                    p.perform_step(g, 1)
                 g.collision, g.streaming = p.collide_bgk, p.lbm_stream
                 p.perform_triple_step(g, 2)
             if variant in (0, 1, 2):
