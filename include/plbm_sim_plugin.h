@@ -62,6 +62,15 @@ void c_lw6_vars(void* sim, double* rho, double* u);
 void c_lw6_free(void* sim);
 double c_lw6_norm(int nx, int ny, const double* u, const double* ua);
 
+/* The Heun finite-volume plugin `fvm` (sim/sim_fvm.F90: fvm_predict_hc :67-100, fvm_correct_hc :103-136,
+ * fvm_collision :139-188, fvm_bc :191-218, sim_fvm%step :282-322, exports :340-432): three kernels per step. */
+void* c_fvm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params);
+void c_fvm_step(void* sim, double omega);
+void c_fvm_step_n(void* sim, double omega, int n);
+void c_fvm_vars(void* sim, double* rho, double* u);
+void c_fvm_free(void* sim);
+double c_fvm_norm(int nx, int ny, const double* u, const double* ua);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,8 @@ class Oracle:
         self._lwh_stream = self._fn("orc_lwh_stream", None, [I, I, I, P, P, R])
         self._lwh_collision = self._fn("orc_lwh_collision", None, [I, I, I, P, R])
         self._lwh_bc = self._fn("orc_lwh_bc", None, [I, I, I, P])
+        # Heun finite-volume plugin (sim/sim_fvm.F90); the caller swaps f1 <-> fc after a step
+        self._simfvm_step = self._fn("orc_simfvm_step", None, [I, I, P, P, P, R, R])
         self.lib.orc_num_threads.restype = C.c_int
         self.lib.orc_set_num_threads.argtypes = [C.c_int]
 

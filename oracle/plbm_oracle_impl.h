@@ -1289,6 +1289,77 @@ void SFX(orc_lwh_bc)(int nx, int ny, int H, REAL *f)
             }
     }
 }
+/* ---- Heun finite-volume plugin `fvm` (sim/sim_fvm.F90), arrays (-1:nx+2, -1:ny+2, 0:8), H = 2 ---- */
+/* fvm_collision, sim/sim_fvm.F90:139-188: the halo layer is collided too; velocity by division */
+void SFX(orc_simfvm_collision)(int nx, int ny, REAL *pdf, REAL omega)
+{
+    const int H = 2;
+    const REAL rho0 = R(1.0);
+    for (int j = -1; j <= ny + 2; ++j)
+        for (int i = -1; i <= nx + 2; ++i) {
+            REAL f[9], feq[9];
+            for (int k = 0; k < 9; ++k) f[k] = pdf[HIDX(i, j, k)];
+            REAL rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + rho0;
+            REAL ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) / rho;
+            REAL uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / rho;
+            SFX(orc_sim_equilibrium)(rho, ux, uy, feq);
+            for (int k = 0; k < 9; ++k) pdf[HIDX(i, j, k)] = f[k] + omega * (feq[k] - f[k]);
+        }
+}
+
+#define FVM_FLUX(a, i, j, k)                                                                                              \
+    (cx[k] * (R(0.5) * (a[HIDX((i) + 1, j, k)] + a[HIDX(i, j, k)]) - R(0.5) * (a[HIDX(i, j, k)] + a[HIDX((i)-1, j, k)])) + \
+     cy[k] * (R(0.5) * (a[HIDX(i, (j) + 1, k)] + a[HIDX(i, j, k)]) - R(0.5) * (a[HIDX(i, j, k)] + a[HIDX(i, (j)-1, k)])))
+
+/* fvm_predict_hc, sim/sim_fvm.F90:67-100 */
+void SFX(orc_simfvm_predict)(int nx, int ny, const REAL *fsrc, REAL *fdst, REAL dt)
+{
+    const int H = 2;
+    const REAL cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    const REAL cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    for (int j = -1; j <= ny + 2; ++j)
+        for (int i = -1; i <= nx + 2; ++i) fdst[HIDX(i, j, 0)] = fsrc[HIDX(i, j, 0)];
+    for (int k = 1; k < 9; ++k)
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                REAL flux = FVM_FLUX(fsrc, i, j, k);
+                fdst[HIDX(i, j, k)] = fdst[HIDX(i, j, k)] - dt * flux;
+            }
+}
+
+/* fvm_correct_hc, sim/sim_fvm.F90:103-136 */
+void SFX(orc_simfvm_correct)(int nx, int ny, const REAL *fp, const REAL *fsrc, REAL *fdst, REAL dt)
+{
+    const int H = 2;
+    const REAL cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    const REAL cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    for (int k = 1; k < 9; ++k)
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                REAL flux = FVM_FLUX(fsrc, i, j, k);
+                REAL fluxp = FVM_FLUX(fp, i, j, k);
+                fdst[HIDX(i, j, k)] = fdst[HIDX(i, j, k)] - dt * R(0.5) * (flux + fluxp);
+            }
+}
+#undef FVM_FLUX
+
+/* sim_fvm%step, sim/sim_fvm.F90:282-322 (fvm_bc :191-218 is orc_lwh_bc with H = 2).  f1, f2, fc are the three
+ * haloed buffers; on return f1 holds the new state and fc the half-collided old one (the move_alloc swap is
+ * done by exchanging contents through the caller's pointers: `swapped` tells the caller to swap f1 and fc). */
+void SFX(orc_simfvm_step)(int nx, int ny, REAL *f1, REAL *f2, REAL *fc, REAL dt, REAL omega)
+{
+    const size_t n = (size_t)(nx + 4) * (ny + 4) * 9;
+    for (size_t i = 0; i < n; ++i) fc[i] = f1[i];
+    SFX(orc_simfvm_collision)(nx, ny, fc, omega);
+    for (size_t i = 0; i < n; ++i) f2[i] = fc[i];
+    SFX(orc_simfvm_collision)(nx, ny, f1, R(0.5) * omega);
+    SFX(orc_simfvm_predict)(nx, ny, f1, f2, dt);
+    SFX(orc_lwh_bc)(nx, ny, 2, f2);
+    SFX(orc_simfvm_collision)(nx, ny, f2, R(0.5) * omega);
+    SFX(orc_simfvm_correct)(nx, ny, f2, f1, fc, dt);
+    SFX(orc_lwh_bc)(nx, ny, 2, fc);
+    /* caller swaps f1 <-> fc */
+}
 #undef HIDX
 
 #undef SIDX

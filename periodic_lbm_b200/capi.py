@@ -78,7 +78,7 @@ SIGNATURES = {
     "c_lw_vars": (None, [_P, _P, _P]),
     "c_lw_free": (None, [_P]),
     "c_lw_norm": (_D, [_I, _I, _P, _P]),
-    **{f"c_{n}_{e}": sig for n in ("lw4", "lw6")
+    **{f"c_{n}_{e}": sig for n in ("lw4", "lw6", "fvm")
        for e, sig in (("init", (_P, [_I, _I, _D, _P, _P, _P, _P])), ("step", (None, [_P, _D])), ("step_n", (None, [_P, _D, _I])),
                       ("vars", (None, [_P, _P, _P])), ("free", (None, [_P])), ("norm", (_D, [_I, _I, _P, _P])))},
     "c_slbm_init": (_P, [_I, _I, _D, _P, _P, _P, _P]),

@@ -21,6 +21,7 @@ namespace {
 struct SimState {
     int nx, ny;
     double *f1, *f2;   // [9][ny][nx], DDF-shifted
+    double* f3 = nullptr;  // third buffer of the Heun finite-volume plugin (fc)
     double *rho, *u;   // device staging for vars(): rho[ny][nx], u[2][ny][nx]
     cudaStream_t stream;
     double dt;         // time step (the Lax-Wendroff plugins accept any dt, slbm requires 1)
@@ -188,11 +189,100 @@ __global__ void __launch_bounds__(256) k_lw_step(const double* __restrict__ fsrc
     for (int k = 0; k < 9; ++k) fdst[k * n + m] = f[k] + omega * (feq[k] - f[k]);
 }
 
+// ---- Heun finite-volume plugin `fvm` (sim/sim_fvm.F90) ------------------------------------------------------
+// One step (sim_fvm%step, :282-322) on the periodic grid = three kernels; the reference's halo copies
+// (fvm_bc :191-218) and its collisions of the halo layer are periodic index arithmetic here.
+//   k_fvm_collide2: fc = collide(f1, omega), f1 = collide(f1, omega/2)                       (:297-302)
+//   k_fvm_predict : f2 = collide(fc - dt flux(f1) [q > 0], f1 [q = 0]; omega/2)             (:304-310, 67-100)
+//   k_fvm_correct : fc = fc - dt/2 (flux(f1) + flux(f2))  [q > 0]                             (:311-312, 103-136)
+__device__ __forceinline__ void fvm_collide(double (&f)[9], double omega)
+{
+    double feq[9];
+    double rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + 1.0;
+    double ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) / rho;
+    double uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / rho;
+    sim_equilibrium(rho, ux, uy, feq);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = f[k] + omega * (feq[k] - f[k]);
+}
+
+__global__ void __launch_bounds__(256) k_fvm_collide2(double* __restrict__ f1, double* __restrict__ fc, int nx, int ny, double omega)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    double a[9], b[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = b[k] = f1[k * n + m];
+    fvm_collide(a, omega);
+    fvm_collide(b, 0.5 * omega);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        fc[k * n + m] = a[k];
+        f1[k * n + m] = b[k];
+    }
+}
+
+// central flux of population k at (i, j), sim/sim_fvm.F90:91-92
+template <int K> __device__ __forceinline__ double fvm_flux(const double* __restrict__ fk, int nx, int i, int j, int ip, int im, int jp, int jm)
+{
+    const double c = fk[(size_t)j * nx + i];
+    const double cx = (double)cxi(K), cy = (double)cyi(K);
+    return cx * (0.5 * (fk[(size_t)j * nx + ip] + c) - 0.5 * (c + fk[(size_t)j * nx + im])) +
+           cy * (0.5 * (fk[(size_t)jp * nx + i] + c) - 0.5 * (c + fk[(size_t)jm * nx + i]));
+}
+
+__global__ void __launch_bounds__(256) k_fvm_predict(const double* __restrict__ f1, const double* __restrict__ fc, double* __restrict__ f2,
+                                                     int nx, int ny, double dt, double omega)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int j = (int)(m / nx), i = (int)(m - (size_t)j * nx);
+    const int ip = i + 1 == nx ? 0 : i + 1, im = i == 0 ? nx - 1 : i - 1;
+    const int jp = j + 1 == ny ? 0 : j + 1, jm = j == 0 ? ny - 1 : j - 1;
+    double g[9];
+    g[0] = f1[m];
+#define PLBM_P(K) g[K] = fc[K * n + m] - dt * fvm_flux<K>(f1 + K * n, nx, i, j, ip, im, jp, jm)
+    PLBM_P(1);
+    PLBM_P(2);
+    PLBM_P(3);
+    PLBM_P(4);
+    PLBM_P(5);
+    PLBM_P(6);
+    PLBM_P(7);
+    PLBM_P(8);
+#undef PLBM_P
+    fvm_collide(g, 0.5 * omega);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f2[k * n + m] = g[k];
+}
+
+__global__ void __launch_bounds__(256) k_fvm_correct(const double* __restrict__ f1, const double* __restrict__ f2, double* __restrict__ fc,
+                                                     int nx, int ny, double dt)
+{
+    const size_t n = (size_t)nx * ny;
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int j = (int)(m / nx), i = (int)(m - (size_t)j * nx);
+    const int ip = i + 1 == nx ? 0 : i + 1, im = i == 0 ? nx - 1 : i - 1;
+    const int jp = j + 1 == ny ? 0 : j + 1, jm = j == 0 ? ny - 1 : j - 1;
+#define PLBM_C(K)                                                                         \
+    {                                                                                     \
+        const double flux = fvm_flux<K>(f1 + K * n, nx, i, j, ip, im, jp, jm);            \
+        const double fluxp = fvm_flux<K>(f2 + K * n, nx, i, j, ip, im, jp, jm);           \
+        fc[K * n + m] = fc[K * n + m] - dt * 0.5 * (flux + fluxp);                        \
+    }
+    PLBM_C(1) PLBM_C(2) PLBM_C(3) PLBM_C(4) PLBM_C(5) PLBM_C(6) PLBM_C(7) PLBM_C(8)
+#undef PLBM_C
+}
+
 void sim_destroy(SimState* s)
 {
     if (!s) return;
     if (s->f1) cudaFree(s->f1);
     if (s->f2) cudaFree(s->f2);
+    if (s->f3) cudaFree(s->f3);
     if (s->rho) cudaFree(s->rho);
     if (s->u) cudaFree(s->u);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -228,7 +318,12 @@ static void* sim_init_common(int nx, int ny, double dt, const double* rho, const
         set_error("no CUDA device available: libplbm_b200 has no CPU fallback");
         return nullptr;
     }
-    SimState* s = new SimState{nx, ny, nullptr, nullptr, nullptr, nullptr, nullptr, dt, 2};
+    SimState* s = new SimState();
+    s->nx = nx;
+    s->ny = ny;
+    s->f1 = s->f2 = s->rho = s->u = nullptr;
+    s->stream = nullptr;
+    s->dt = dt;
     const size_t n = (size_t)nx * ny;
     bool ok = cudaMalloc(&s->f1, 9 * n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->f2, 9 * n * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&s->rho, n * sizeof(double)) == cudaSuccess && cudaMalloc(&s->u, 2 * n * sizeof(double)) == cudaSuccess &&
@@ -378,5 +473,42 @@ void c_lw6_step(void* sim, double omega) { c_lw_step_n(sim, omega, 1); }
 void c_lw6_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
 void c_lw6_free(void* sim) { c_plbm_free(sim); }
 double c_lw6_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
+
+// The Heun finite-volume plugin `fvm` (sim/sim_fvm.F90:340-432) under its own symbol names (libfvm.so drop-in).
+void* c_fvm_init(int nx, int ny, double dt, const double* rho, const double* u, const double* sigma, void* params)
+{
+    (void)params;
+    if (nx < 2 || ny < 2) {
+        set_error("c_fvm_init: grid smaller than the stencil halo");
+        return nullptr;
+    }
+    SimState* s = static_cast<SimState*>(sim_init_common(nx, ny, dt, rho, u, sigma, false));
+    if (s && cudaMalloc(&s->f3, 9 * (size_t)nx * ny * sizeof(double)) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "c_fvm_init");
+        sim_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+void c_fvm_step_n(void* sim, double omega, int n)
+{
+    SimState* s = static_cast<SimState*>(sim);
+    if (!s || !s->f3) return;
+    const size_t nn = (size_t)s->nx * s->ny;
+    const unsigned nb = (unsigned)((nn + 255) / 256);
+    for (int it = 0; it < n; ++it) {
+        k_fvm_collide2<<<nb, 256, 0, s->stream>>>(s->f1, s->f3, s->nx, s->ny, omega);
+        k_fvm_predict<<<nb, 256, 0, s->stream>>>(s->f1, s->f3, s->f2, s->nx, s->ny, s->dt, omega);
+        k_fvm_correct<<<nb, 256, 0, s->stream>>>(s->f1, s->f2, s->f3, s->nx, s->ny, s->dt);
+        g_launches.fetch_add(3, std::memory_order_relaxed);
+        double* t = s->f1;  // move_alloc swap of f1 and fc
+        s->f1 = s->f3;
+        s->f3 = t;
+    }
+}
+void c_fvm_step(void* sim, double omega) { c_fvm_step_n(sim, omega, 1); }
+void c_fvm_vars(void* sim, double* rho, double* u) { c_plbm_vars(sim, rho, u); }
+void c_fvm_free(void* sim) { c_plbm_free(sim); }
+double c_fvm_norm(int nx, int ny, const double* u, const double* ua) { return c_plbm_norm(nx, ny, u, ua); }
 
 }  // extern "C"

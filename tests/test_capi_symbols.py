@@ -15,7 +15,7 @@ def header_symbols():
         if fn.endswith(".h"):
             src = open(os.path.join(ROOT, "include", fn)).read()
             src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-            names |= set(re.findall(r"\b((?:plbm|c_plbm|c_slbm|c_lw[46]?)_\w+)\s*\(", src))
+            names |= set(re.findall(r"\b((?:plbm|c_plbm|c_slbm|c_lw[46]?|c_fvm)_\w+)\s*\(", src))
     return names
 
 

@@ -429,6 +429,29 @@ def test_sim_lw_plugin_seam(plbm, dt, name, order):
     sim.free()
 
 
+@pytest.mark.parametrize("dt", [1.0, 0.3])
+def test_sim_fvm_plugin_seam(plbm, dt):
+    """c_fvm_{init,step,vars,free}: the reference's Heun finite-volume plugin (sim/sim_fvm.F90) vs its oracle."""
+    from test_oracle_properties import _simfvm_run
+    nx, ny, steps, omega, H = 40, 56, 9, 1.3, 2
+    o = Oracle("f64")
+    rng = np.random.default_rng(21)
+    p = 1e-3 * rng.standard_normal((ny, nx))
+    u = 0.05 * rng.standard_normal((2, ny, nx))
+    f1 = _simfvm_run(o, nx, ny, p, u, dt, omega, steps)
+    rho_w, u_w, v_w = np.zeros((ny, nx)), np.zeros((ny, nx)), np.zeros((ny, nx))
+    P = lambda a: a.ctypes.data  # noqa: E731
+    o._simh_macros(nx, ny, H, P(f1), P(rho_w), P(u_w), P(v_w))
+
+    sim = plbm.SimPlugin(name="fvm")
+    sim.init((nx, ny), dt, p, u)
+    sim.step(omega)
+    sim.step(omega, n=steps - 1)
+    rho, uu = sim.vars()
+    assert np.array_equal(rho, rho_w) and np.array_equal(uu[0], u_w) and np.array_equal(uu[1], v_w)
+    sim.free()
+
+
 def test_output_npy_and_checkpoint_roundtrip(plbm, tmp_path):
     """output_npy writes mf(ny,nx,3) in Fortran order like the reference; a PDF checkpoint restores a run
     bit for bit (continuing from the checkpoint == never stopping)."""

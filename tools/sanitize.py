@@ -56,7 +56,7 @@ sim.init((33, 21), 1.0, np.zeros((21, 33)), np.zeros((2, 21, 33)))
 sim.step(1.3, n=3)
 sim.vars()
 sim.free()
-for name in ("lw", "lw4", "lw6"):
+for name in ("lw", "lw4", "lw6", "fvm"):
     lw = p.SimPlugin(name=name)
     lw.init((33, 21), 0.5, np.zeros((21, 33)), np.zeros((2, 21, 33)))
     lw.step(1.3, n=3)
