@@ -59,6 +59,7 @@ int main(int argc, char** argv)
         lattice_grid grid;
         alloc_grid(grid, nx, ny, 2);
         grid.filename = "results";
+        set_output_folder(grid, "taylor_green");                                                                 // :37
         grid.collision = coll == "bgk" ? collide_bgk : coll == "trt" ? collide_trt : collide_rr;               // :39
         grid.streaming = scheme == "fvm" ? stream_fvm_bardow : scheme == "fdm" ? stream_fdm_bardow
                        : scheme == "sofonea" ? stream_fdm_sofonea : lbm_stream;                                  // :40
@@ -82,6 +83,8 @@ int main(int argc, char** argv)
 
         wp t = 0;
         apply_initial_condition(tg, grid);
+        output_gnuplot(grid, 0);  // :91-92
+        output_vtk(grid, 0);
         grid.logger(grid, 0);
 
         const auto sbegin = std::chrono::steady_clock::now();
@@ -106,6 +109,8 @@ int main(int argc, char** argv)
             if (done % nprint == 0 || t >= tmax) {
                 std::printf(" step =  %ld\n", done);
                 update_macros(grid);
+                output_gnuplot(grid, (int)done);  // :107-108, :114-115
+                output_vtk(grid, (int)done);
                 grid.logger(grid, (int)done);
             }
             if (t >= tmax) break;

@@ -38,6 +38,7 @@ int main(int argc, char** argv)
         lattice_grid grid;
         alloc_grid(grid, nx, ny, 2);
         grid.filename = "results";
+        set_output_folder(grid, "vortex");  // :41
         grid.collision = coll == "trt" ? collide_trt : coll == "rr" ? collide_rr : collide_bgk;
         grid.streaming = scheme == "lbm" ? lbm_stream : scheme == "fdm" ? stream_fdm_bardow
                        : scheme == "sofonea" ? stream_fdm_sofonea : stream_fvm_bardow;
@@ -67,6 +68,9 @@ int main(int argc, char** argv)
         wp t = 0;
         vcase.eval(grid.nx, grid.ny, grid.rho, grid.ux, grid.uy);  // apply_initial_condition (:144-154)
         set_pdf_to_equilibrium(grid);
+        output_gnuplot(grid, 0);  // :104-106
+        output_npy(grid, 0);
+        output_vtk(grid, 0);
         grid.logger(grid, 0);
 
         const auto sbegin = std::chrono::steady_clock::now();
@@ -83,6 +87,9 @@ int main(int argc, char** argv)
             if (step % nprint == 0) {
                 std::printf(" step =  %ld\n", step);
                 update_macros(grid);
+                output_gnuplot(grid, (int)step);  // :122-124
+                output_npy(grid, (int)step);
+                output_vtk(grid, (int)step);
                 grid.logger(grid, (int)step);
             }
         }

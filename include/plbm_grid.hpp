@@ -22,6 +22,8 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -177,6 +179,118 @@ inline void collide_bgk_improved(lattice_grid& grid)
     push_omega(grid);
     check(plbm_collide(grid.dev, PLBM_BGK_IMPROVED), "collide_bgk_improved");
 }
+
+// ---- host output of the macroscopic fields (src/fvm_bardow.F90:895-1025, src/output/*) --------------------
+// grid.rho/ux/uy are what the last update_macros left on the host; nothing below touches the device.
+inline void set_output_folder(lattice_grid& grid, const std::string& foldername, bool verbose = false)
+{
+    const std::string cmd = std::string("mkdir -p ") + (verbose ? "-v " : "") + foldername;
+    if (std::system(cmd.c_str()) != 0) throw error("[set_output_folder] error making directory " + foldername);
+    grid.foldername = foldername;
+}
+
+namespace detail {
+// the reference's edit descriptors: ES24.16E3 (double) / ES15.8E2 (single); buf holds 48 chars
+inline void fmt_real(char* buf, wp v)
+{
+    if (sizeof(wp) == 4) {
+        std::snprintf(buf, 48, "%15.8E", (double)v);
+        return;
+    }
+    char t[40];
+    std::snprintf(t, sizeof(t), "%.16E", (double)v);
+    char* e = std::strchr(t, 'E');
+    const int ex = std::atoi(e + 2);
+    std::snprintf(e + 2, 8, "%03d", ex);  // C prints two exponent digits, the descriptor has three
+    std::snprintf(buf, 48, "%24s", t);
+}
+inline std::string output_name(const lattice_grid& grid, const int* step, const char* ext)
+{
+    char istr[16] = "";
+    if (step) std::snprintf(istr, sizeof(istr), "%09d", *step);
+    return grid.foldername + "/" + grid.filename + istr + ext;
+}
+}  // namespace detail
+
+// output_gnuplot -> output_gnuplot_grid (src/output/gnuplot.F90:21-39): "x y rho ux uy" per node, a blank line
+// after every line x.  The reference never assigns its `ry` (it assigns `rx` twice), so its second column is
+// undefined; the cell centres (x - 1/2, y - 1/2) it evidently intends are written here.
+inline void output_gnuplot(const lattice_grid& grid, const int* step = nullptr)
+{
+    const std::string name = detail::output_name(grid, step, ".txt");
+    std::FILE* fh = std::fopen(name.c_str(), "w");
+    if (!fh) throw error("output_gnuplot: cannot open " + name);
+    char b[5][48];
+    for (int x = 0; x < grid.nx; ++x) {
+        detail::fmt_real(b[0], wp(x) + wp(0.5));
+        for (int y = 0; y < grid.ny; ++y) {
+            const size_t m = (size_t)x * grid.ny + y;
+            detail::fmt_real(b[1], wp(y) + wp(0.5));
+            detail::fmt_real(b[2], grid.rho[m]);
+            detail::fmt_real(b[3], grid.ux[m]);
+            detail::fmt_real(b[4], grid.uy[m]);
+            std::fprintf(fh, "%s %s %s %s %s\n", b[0], b[1], b[2], b[3], b[4]);
+        }
+        std::fputc('\n', fh);
+    }
+    std::fclose(fh);
+}
+inline void output_gnuplot(const lattice_grid& grid, int step) { output_gnuplot(grid, &step); }
+
+// output_vtk -> output_vtk_structuredPoints (src/fvm_bardow.F90:960-997, src/output/vtk.F90:150-196)
+inline void output_vtk(const lattice_grid& grid, const int* step = nullptr, bool binary = false)
+{
+    if (binary) {
+        std::printf(" binary output not implemented\n");
+        return;
+    }
+    const std::string name = detail::output_name(grid, step, ".vtk");
+    std::FILE* fh = std::fopen(name.c_str(), "w");
+    if (!fh) throw error("output_vtk: cannot open " + name);
+    char z[48], o[48], a[48], b[48];
+    detail::fmt_real(z, wp(0));
+    detail::fmt_real(o, wp(1));
+    std::fprintf(fh, "# vtk DataFile Version 3.0\nfluid\nASCII\nDATASET STRUCTURED_POINTS\n");
+    std::fprintf(fh, "DIMENSIONS %d %d 2 \n", grid.nx + 1, grid.ny + 1);
+    std::fprintf(fh, "ORIGIN  %s%s%s\nSPACING %s%s%s\n\n", z, z, z, o, o, o);
+    std::fprintf(fh, "CELL_DATA %lld\nSCALARS Density float 1\nLOOKUP_TABLE default\n", (long long)grid.nx * grid.ny);
+    for (int y = 0; y < grid.ny; ++y)
+        for (int x = 0; x < grid.nx; ++x) {
+            detail::fmt_real(a, grid.rho[(size_t)x * grid.ny + y]);
+            std::fprintf(fh, "%s\n", a);
+        }
+    std::fprintf(fh, "\nVECTORS Velocity float\n");
+    for (int y = 0; y < grid.ny; ++y)
+        for (int x = 0; x < grid.nx; ++x) {
+            detail::fmt_real(a, grid.ux[(size_t)x * grid.ny + y]);
+            detail::fmt_real(b, grid.uy[(size_t)x * grid.ny + y]);
+            std::fprintf(fh, "%s%s%s\n", a, b, z);
+        }
+    std::fclose(fh);
+}
+inline void output_vtk(const lattice_grid& grid, int step, bool binary = false) { output_vtk(grid, &step, binary); }
+
+// output_npy -> output_fluid_npy (src/fvm_bardow.F90:929-958, src/output/npy.f90:14-29): mf(ny,nx,3) in Fortran
+// order as a NumPy v1.0 file, what stdlib's save_npy writes
+inline void output_npy(const lattice_grid& grid, const int* step = nullptr)
+{
+    const std::string name = detail::output_name(grid, step, ".npy");
+    std::FILE* fh = std::fopen(name.c_str(), "wb");
+    if (!fh) throw error("output_npy: cannot open " + name);
+    char dict[160];
+    std::snprintf(dict, sizeof(dict), "{'descr': '<f%d', 'fortran_order': True, 'shape': (%d, %d, 3), }", (int)sizeof(wp), grid.ny, grid.nx);
+    std::string header(dict);
+    while ((10 + header.size() + 1) % 64 != 0) header.push_back(' ');
+    header.push_back('\n');
+    const unsigned char magic[8] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+    const unsigned short hlen = (unsigned short)header.size();
+    std::fwrite(magic, 1, 8, fh);
+    std::fwrite(&hlen, 2, 1, fh);  // little endian hosts only (x86-64, aarch64)
+    std::fwrite(header.data(), 1, header.size(), fh);
+    std::fwrite(grid.mf.data(), sizeof(wp), grid.mf.size(), fh);
+    std::fclose(fh);
+}
+inline void output_npy(const lattice_grid& grid, int step) { output_npy(grid, &step); }
 
 namespace detail {
 inline int collision_id(collision_interface c)

@@ -9,7 +9,7 @@ from . import capi  # noqa: F401  (raises ImportError when libplbm_b200.so is mi
 from .capi import BGK, BGK_IMPROVED, BGK_SPLIT, F32, F64, RR, TRT, TRT_SPLIT, PlbmError  # noqa: F401
 from .cases import TaylorGreen, VortexCase, steps_until, taylor_green_params, vortex_params  # noqa: F401
 from .lattice import *  # noqa: F401,F403
-from .output import load_checkpoint, output_npy, save_checkpoint, set_output_folder  # noqa: F401
+from .output import load_checkpoint, output_gnuplot, output_npy, output_vtk, save_checkpoint, set_output_folder  # noqa: F401
 from .plugin import SimPlugin  # noqa: F401
 from .slab import Slab, slab_of  # noqa: F401
 

@@ -164,19 +164,34 @@ def test_full_size_properties_8192(plbm):
         plbm.dealloc_grid(g)
 
 
-def test_cpp_drivers_over_the_cpp_module_mirror():
+def test_cpp_drivers_over_the_cpp_module_mirror(tmp_path):
     """app/main_taylor_green.cpp and app/main_vortex.cpp: the reference drivers written against
-    include/plbm_grid.hpp (the C++ host-side mirror of the Fortran modules) over the C ABI."""
+    include/plbm_grid.hpp (the C++ host-side mirror of the Fortran modules) over the C ABI, including the
+    files they leave behind (output_gnuplot / output_vtk / output_npy, src/fvm_bardow.F90:895-997)."""
     app = os.path.join(ROOT, "app")
     subprocess.run(["make", "-C", app], check=True, capture_output=True)
-    out = subprocess.run([os.path.join(app, "main_taylor_green"), "r50", "64", "dugks"], check=True, capture_output=True, text=True).stdout
+    run = lambda *a: subprocess.run(list(a), check=True, capture_output=True, text=True, cwd=tmp_path).stdout  # noqa: E731
+    out = run(os.path.join(app, "main_taylor_green"), "r50", "64", "dugks")
     l2 = float(re.search(r"L2-norm =\s*([0-9.E+-]+)", out).group(1))
     assert abs(l2 - 2.2824885e-02) < 1e-9, out          # graphs/fvm_dugks_64.txt, dt/tau = 50
-    out = subprocess.run([os.path.join(app, "main_taylor_green"), "r50", "64", "fvm", "bgk"], check=True, capture_output=True, text=True).stdout
+    out = run(os.path.join(app, "main_taylor_green"), "r50", "64", "fvm", "bgk")
     l2 = float(re.search(r"L2-norm =\s*([0-9.E+-]+)", out).group(1))
     assert abs(l2 - 6.7097665e-02) < 1e-9, out          # graphs/fvm_bardow_64.txt, dt/tau = 50
+    files = sorted(os.listdir(tmp_path / "taylor_green"))
+    assert "results000000000.txt" in files and "results000000000.vtk" in files and len(files) == 4, files  # step 0 + final step
+    vtk = open(tmp_path / "taylor_green" / "results000000000.vtk").read().split("\n")
+    assert vtk[3] == "DATASET STRUCTURED_POINTS" and vtk[4] == "DIMENSIONS 65 65 2 " and vtk[8] == "CELL_DATA 4096"
+    rho0 = np.array([float(v) for v in vtk[11:11 + 4096]]).reshape(64, 64)          # [y][x]
+    gp = np.loadtxt(tmp_path / "taylor_green" / "results000000000.txt")              # x outer, y inner
+    assert gp.shape == (4096, 5) and np.array_equal(gp[:, 2].reshape(64, 64).T, rho0)
+    assert np.array_equal(gp[:64, 1], np.arange(64) + 0.5) and np.all(gp[:64, 0] == 0.5)
+    assert abs(rho0.mean() - 1.0) < 1e-6
     # reference defaults of main_vortex (128^2, collide_bgk + stream_fvm_bardow), first 2000 steps
-    out = subprocess.run([os.path.join(app, "main_vortex"), "0.05", "128", "fvm", "bgk", "2000"], check=True, capture_output=True, text=True).stdout
+    out = run(os.path.join(app, "main_vortex"), "0.05", "128", "fvm", "bgk", "2000")
     speed = float(re.search(r"max\|u\| =\s*([0-9.e+-]+)", out).group(1))
     mass = float(re.search(r"sum\(rho\) =\s*([0-9.e+-]+)", out).group(1))
     assert 0.05 < speed < 0.2 and abs(mass / 128**2 - 1.0) < 5e-3, out
+    mf = np.load(tmp_path / "vortex" / "results000000000.npy")                       # mf(ny,nx,3), Fortran order
+    assert mf.shape == (128, 128, 3) and mf.dtype == np.float64 and np.isfortran(mf)
+    vt = open(tmp_path / "vortex" / "results000000000.vtk").read().split("\n")
+    assert np.array_equal(np.array([float(v) for v in vt[11:11 + 128 * 128]]).reshape(128, 128), mf[:, :, 0])

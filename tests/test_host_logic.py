@@ -128,3 +128,35 @@ def test_slab_halo_protocol_world_size_n_gloo(world, nxg, ny, coll):
         p_.join(timeout=60)
         assert p_.exitcode == 0
     assert ok, "slab-decomposed run differs from the single-domain run"
+
+
+def test_text_writers_use_the_reference_edit_descriptors(tmp_path):
+    """output_vtk / output_gnuplot (src/output/vtk.F90:150-196, gnuplot.F90:21-39): ES24.16E3 reals, the
+    reference's record structure and loop order (VTK: y outer, x inner; gnuplot: x outer, blank line per x)."""
+    import types
+
+    from periodic_lbm_b200 import output
+
+    assert output._fmt_real(np.array([1.0, -0.5, 0.0, 1.2345678901234567e-105])) == [
+        " 1.0000000000000000E+000", "-5.0000000000000000E-001", " 0.0000000000000000E+000", " 1.2345678901234567E-105"]
+    assert output._fmt_real(np.array([1.0, -0.5], dtype=np.float32)) == [" 1.00000000E+00", "-5.00000000E-01"]
+
+    nx, ny = 3, 2
+    g = types.SimpleNamespace(nx=nx, ny=ny, dtype=np.float64, foldername=str(tmp_path), filename="results",
+                              rho=np.arange(6.0).reshape(nx, ny) + 1, ux=np.full((nx, ny), 0.25), uy=np.full((nx, ny), -0.125))
+    vtk = open(output.output_vtk(g, step=7)).read().split("\n")
+    assert vtk[:5] == ["# vtk DataFile Version 3.0", "fluid", "ASCII", "DATASET STRUCTURED_POINTS", "DIMENSIONS 4 3 2 "]
+    assert vtk[5] == "ORIGIN  " + " 0.0000000000000000E+000" * 3 and vtk[6] == "SPACING " + " 1.0000000000000000E+000" * 3
+    assert vtk[7] == "" and vtk[8] == "CELL_DATA 6" and vtk[9:11] == ["SCALARS Density float 1", "LOOKUP_TABLE default"]
+    # rho(j,i), j = y outer, i = x inner: rho[x][y] = 2x + y + 1
+    assert [float(v) for v in vtk[11:17]] == [1.0, 3.0, 5.0, 2.0, 4.0, 6.0]
+    assert vtk[17] == "" and vtk[18] == "VECTORS Velocity float"
+    assert vtk[19] == " 2.5000000000000000E-001-1.2500000000000000E-001 0.0000000000000000E+000"
+    assert output.output_vtk(g, binary=True) is None
+    assert os.path.basename(output.output_vtk(g, step=7)) == "results000000007.vtk"
+
+    txt = open(output.output_gnuplot(g)).read().split("\n")
+    assert len(txt) == nx * (ny + 1) + 1 and txt[ny] == "" and txt[2 * ny + 1] == ""
+    first = [float(v) for v in txt[0].split()]
+    assert first == [0.5, 0.5, 1.0, 0.25, -0.125]
+    assert [float(v) for v in txt[ny + 1].split()][:3] == [1.5, 0.5, 3.0]
