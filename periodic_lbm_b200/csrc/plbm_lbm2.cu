@@ -24,9 +24,12 @@
 // segments: within noise; skewed row ownership (phase A owns rows (odd, even), phase B (even, odd), so
 // that the shifted populations become aligned vectors: 42 instead of 48 memory instructions per thread
 // and column) 63.7, i.e. no change; issuing the prefetch before the barrier 62.4; fp32 shifted
-// populations as aligned vector + one element (15 instead of 27 loads) 111.6 vs 122.  ncu: the warps wait
-// on the memory-instruction queue (stall_mio_throttle) with HBM 58 % busy and 16 warps per SM -- the
-// kernel sits on a latency/occupancy plateau set by 128 registers and 54 KB of ring per block.
+// populations as aligned vector + one element (15 instead of 27 loads) 111.6 vs 122; one row per thread
+// with 256-thread blocks = 32 warps per SM at 64 registers 58.1 (59.6 without the prefetch); adjacent
+// strips co-scheduled as clusters of 2/4/8 61.2/59.9/59.6; non-power-of-two grids: no change.  With the
+// collision REMOVED the kernel runs 66 (fp32: 126 vs 122): it is bound by the global -> register -> shared
+// -> register -> global data path at ~4.7 TB/s of HBM traffic, not by arithmetic, occupancy, instruction
+// count or DRAM locality (ncu: stall_mio_throttle dominates, HBM 58 % busy).
 #include <cstdlib>
 
 #include "plbm_internal.h"
