@@ -131,6 +131,7 @@ struct Comm {
     size_t bytes9 = 0;  // one FVM / DUGKS halo message
     int parity = 0;        // halo slot holding the neighbours' lines of lattice `iold`
     bool halo_valid = false;
+    bool pairs_ok = false;  // every slab of the ring can run the two-step kernel (agreed at init)
     int halo_of_lattice = 0;
 };
 
@@ -205,6 +206,18 @@ static int quiesce(Grid& g)
     return PLBM_OK;
 }
 
+// Ring-wide minimum of a flag (every rank must call it).
+static int agree_min(Grid& g, int* value)
+{
+    Comm* c = g.comm;
+    int* flag = (int*)c->send9_hi;  // scratch device memory
+    PLBM_CUDA(cudaMemcpy(flag, value, sizeof(int), cudaMemcpyHostToDevice));
+    PLBM_NCCL(g_nccl.AllReduce(flag, flag, 1, kNcclInt32, kNcclMin, c->comm, c->stream));
+    PLBM_CUDA(cudaStreamSynchronize(c->stream));
+    PLBM_CUDA(cudaMemcpy(value, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    return PLBM_OK;
+}
+
 // Try to set up the p2p transport; on any failure (on ANY rank: agreed by an all-reduce) stay on NCCL.
 static int p2p_setup(Grid& g)
 {
@@ -253,12 +266,14 @@ static int p2p_setup(Grid& g)
         }
     }
     // agreement: p2p only if it works everywhere
-    int* flag = (int*)c->send9_hi;
-    PLBM_CUDA(cudaMemcpy(flag, &ok, sizeof(int), cudaMemcpyHostToDevice));
-    PLBM_NCCL(g_nccl.AllReduce(flag, flag, 1, kNcclInt32, kNcclMin, c->comm, c->stream));
-    PLBM_CUDA(cudaStreamSynchronize(c->stream));
-    PLBM_CUDA(cudaMemcpy(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    int rc = agree_min(g, &ok);
+    if (rc) return rc;
     c->p2p = ok != 0;
+    // fused pairs of steps only if every slab of the ring can run them: the ranks must issue the same
+    // sequence of launches (one halo message per launch)
+    int pairs = lbm_pair_applicable(g) ? 1 : 0;
+    if ((rc = agree_min(g, &pairs))) return rc;
+    c->pairs_ok = pairs != 0;
     if (c->p2p) {
         for (int p = 0; p < 2; ++p) {  // the halo slots now live inside the exported block
             cudaFree(c->halo_lo[p]);
@@ -468,7 +483,7 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    const bool pairs = (g.variant == 0 || g.variant == 5) && lbm_pair_applicable(g);
+    const bool pairs = (g.variant == 0 || g.variant == 5) && c->pairs_ok;
     for (int s = 0; s < nsteps;) {
         // two steps per pass over HBM while at least one single step remains (the last step stays single so
         // that lattice `inew` ends up holding state n-1 like the reference, see step_lbm_t)
@@ -515,7 +530,7 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    const bool pairs = (g.variant == 0 || g.variant == 5) && lbm_pair_applicable(g);
+    const bool pairs = (g.variant == 0 || g.variant == 5) && c->pairs_ok;
     for (int s = 0; s < nsteps;) {
         const bool pair = pairs && s + 2 < nsteps;
         const int p = c->parity;

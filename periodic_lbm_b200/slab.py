@@ -2,9 +2,12 @@
 GPUs of one box -- host-side bookkeeping only (the reference is single-process).
 
 Rank r owns lines [x_offset, x_offset + nx_local) of every population and forms a periodic ring
-with its neighbours.  Per LBM step it needs the last line of q = 1,5,8 (cx = +1) from rank r-1
-and the first line of q = 3,6,7 (cx = -1) from rank r+1; the y shift of the diagonal populations
-is applied locally on the received line, so no corner exchange exists.
+with its neighbours.  One LBM step needs the last line of q = 1,5,8 (cx = +1) from rank r-1
+and the first line of q = 3,6,7 (cx = -1) from rank r+1; a fused pair of steps (the library's
+two-step kernel) recomputes step 1 on the neighbours' nearest line and therefore needs their TWO
+nearest lines of all nine populations.  The halo message always carries HALO_LINES = 2 lines x 9
+populations per direction, so that either kind of launch can follow; the y shift of the diagonal
+populations is applied locally on the received lines, so no corner exchange exists.
 """
 from __future__ import annotations
 
@@ -47,6 +50,21 @@ def slab_of(rank: int, nranks: int, nx_global: int) -> Slab:
     return Slab(rank, nranks, nx_global, x_offset, nx_local)
 
 
+HALO_LINES = 2  # lines per direction in one halo message
+
+
 def halo_message_bytes(ny: int, itemsize: int) -> int:
-    """bytes per direction per step: 3 populations x ld reals (ld = ny padded to 16)."""
-    return 3 * ((ny + 15) // 16 * 16) * itemsize
+    """bytes per direction per launch: HALO_LINES lines x 9 populations x ld reals (ld = ny padded to 16)."""
+    return HALO_LINES * 9 * ((ny + 15) // 16 * 16) * itemsize
+
+
+def launch_schedule(nsteps: int, pairs: bool = True) -> list:
+    """Steps advanced by each launch of one perform_lbm_step(nsteps) call: fused pairs while at least one
+    single step remains (the last step stays single so that lattice `inew` ends up holding state nsteps-1
+    exactly like the reference), then single steps."""
+    out, s = [], 0
+    while s < nsteps:
+        n = 2 if pairs and s + 2 < nsteps else 1
+        out.append(n)
+        s += n
+    return out

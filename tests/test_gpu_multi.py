@@ -57,12 +57,12 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-@pytest.mark.parametrize("nxg,ny,steps,coll_id", [(64, 64, 9, 0), (37, 53, 8, 2), (130, 128, 11, 1), (4, 32, 5, 0),
+@pytest.mark.parametrize("nxg,ny,steps,coll_id", [(64, 64, 9, 0), (37, 53, 8, 2), (130, 128, 11, 1), (4, 32, 5, 0), (7, 32, 7, 0),
                                                   (64, 64, 6, 20), (37, 53, 5, 20), (70, 96, 5, 12)])
 def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec, halo):
     if halo == "nccl" and (coll_id >= 10 or prec == "f32"):
         pytest.skip("the NCCL fallback transport is covered by the fp64 LBM cases")
-    world = min(plbm.device_count(), 4 if nxg >= 8 else 2)
+    world = min(plbm.device_count(), 4 if nxg >= 8 else 2)  # (7, 32): slabs of 4 and 3 lines -> no fused pairs anywhere
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp

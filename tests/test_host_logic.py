@@ -23,7 +23,7 @@ def test_slab_partition_covers_grid():
         slab_of(0, 8, 15)
     assert [q for q in range(9) if cx[q] == 1] == list(Q_FROM_LO)
     assert [q for q in range(9) if cx[q] == -1] == sorted(Q_FROM_HI)
-    assert halo_message_bytes(32768, 8) == 786432
+    assert halo_message_bytes(32768, 8) == 2 * 9 * 32768 * 8  # two lines of all nine populations (a fused pair of steps may follow)
 
 
 def test_driver_recipe_matches_oracle_recipe():
@@ -61,14 +61,14 @@ def _free_port():
 
 
 def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
-    """One rank of the ring: owns a slab, exchanges the three-population halo lines with gloo, and
-    advances its slab with the ORACLE kernels on a halo-extended copy.  This exercises exactly the
-    protocol libplbm_b200's NCCL ring implements (which lines, which populations, which neighbour,
-    double buffering by step parity) without a GPU."""
+    """One rank of the ring: owns a slab, exchanges the halo message (two lines of all nine populations per
+    direction) with gloo, and advances its slab with the ORACLE kernels on a halo-extended copy -- one step
+    or a fused pair per launch, in the library's own schedule.  This exercises exactly the protocol
+    libplbm_b200's ring implements (which lines, which neighbour, what a pair needs) without a GPU."""
     import torch
     import torch.distributed as dist
 
-    from periodic_lbm_b200.slab import Q_FROM_HI, Q_FROM_LO, slab_of
+    from periodic_lbm_b200.slab import HALO_LINES, launch_schedule, slab_of
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -81,23 +81,30 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
     fglob[:, :, :ny] = 0.1 + 0.01 * rng.random((9, nxg, ny))
     f = fglob[:, sl.x_offset:sl.x_end].copy()
     nxl = sl.nx_local
-    for _ in range(steps):
-        send_lo = torch.from_numpy(f[list(Q_FROM_HI), 0].copy())    # my first line of q=3,6,7 -> rank lo (its halo_hi)
-        send_hi = torch.from_numpy(f[list(Q_FROM_LO), -1].copy())   # my last line of q=1,5,8  -> rank hi (its halo_lo)
+    H = HALO_LINES
+    collide = {0: lambda a: o.collide_bgk(a, ny, 1.7), 2: lambda a: o.collide_rr(a, ny, 1.7)}[coll]
+    can_pair = torch.tensor([int(nxl >= 4)])
+    dist.all_reduce(can_pair, op=dist.ReduceOp.MIN)  # every rank must issue the same sequence of launches
+    for nfused in launch_schedule(steps, pairs=bool(can_pair.item())):
+        send_lo = torch.from_numpy(f[:, :H].copy())    # my first two lines -> rank lo (its lines nx, nx+1)
+        send_hi = torch.from_numpy(f[:, -H:].copy())   # my last two lines  -> rank hi (its lines -2, -1)
         halo_lo, halo_hi = torch.empty_like(send_hi), torch.empty_like(send_lo)
         ops = [dist.P2POp(dist.isend, send_lo, sl.lo), dist.P2POp(dist.isend, send_hi, sl.hi),
                dist.P2POp(dist.irecv, halo_hi, sl.hi), dist.P2POp(dist.irecv, halo_lo, sl.lo)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        ext = np.zeros((9, nxl + 2, ld))
-        ext[:, 1:-1] = f
-        ext[list(Q_FROM_LO), 0] = halo_lo.numpy()
-        ext[list(Q_FROM_HI), -1] = halo_hi.numpy()
-        dst = np.zeros_like(ext)
-        o.lbm_stream(ext, dst, ny)  # periodic wrap of the extended slab only pollutes the two halo lines
-        fn = np.ascontiguousarray(dst[:, 1:-1])
-        {0: lambda: o.collide_bgk(fn, ny, 1.7), 2: lambda: o.collide_rr(fn, ny, 1.7)}[coll]()
-        f = fn
+        ext = np.zeros((9, nxl + 2 * H, ld))
+        ext[:, H:-H] = f
+        ext[:, :H] = halo_lo.numpy()
+        ext[:, -H:] = halo_hi.numpy()
+        # every step on the extended slab pollutes one more ghost line from each end (its periodic wrap is
+        # wrong there): two ghost lines per side keep the owned lines exact for up to two steps
+        for _ in range(nfused):
+            dst = np.zeros_like(ext)
+            o.lbm_stream(ext, dst, ny)
+            collide(dst)
+            ext = dst
+        f = np.ascontiguousarray(ext[:, H:-H])
     gathered = [None] * world
     dist.all_gather_object(gathered, (sl.x_offset, f))
     if rank == 0:
@@ -106,21 +113,21 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
         a, b = fglob.copy(), np.zeros_like(fglob)
         for _ in range(steps):
             o.lbm_stream(a, b, ny)
-            {0: lambda: o.collide_bgk(b, ny, 1.7), 2: lambda: o.collide_rr(b, ny, 1.7)}[coll]()
+            collide(b)
             a, b = b, a
         out.put(bool(np.array_equal(full[:, :, :ny], a[:, :, :ny])))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nxg,ny,coll", [(2, 12, 10, 0), (2, 9, 16, 2), (3, 11, 7, 0)])
+@pytest.mark.parametrize("world,nxg,ny,coll", [(2, 12, 10, 0), (2, 9, 16, 2), (3, 13, 7, 0), (2, 7, 8, 0)])
 def test_slab_halo_protocol_world_size_n_gloo(world, nxg, ny, coll):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, nxg, ny, 6, coll, q)) for r in range(world)]
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, nxg, ny, 7, coll, q)) for r in range(world)]
     for p_ in procs:
         p_.start()
     ok = q.get(timeout=120)
