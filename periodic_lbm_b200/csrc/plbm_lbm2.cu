@@ -29,7 +29,13 @@
 // strips co-scheduled as clusters of 2/4/8 61.2/59.9/59.6; non-power-of-two grids: no change.  With the
 // collision REMOVED the kernel runs 66 (fp32: 126 vs 122): it is bound by the global -> register -> shared
 // -> register -> global data path at ~4.7 TB/s of HBM traffic, not by arithmetic, occupancy, instruction
-// count or DRAM locality (ncu: stall_mio_throttle dominates, HBM 58 % busy).
+// count or DRAM locality (ncu: stall_mio_throttle dominates, HBM 58 % busy).  Legs of that path at 8192^2,
+// per pair launch: ring only (no global loads, no stores) 0.47 ms; loads + ring 1.14 ms (4.2 TB/s of
+// reads); ring + stores 0.89 ms (5.5 TB/s of writes); everything 2.08 ms ~ the SUM of the two legs: loads
+// and stores do not overlap.  The load leg is bound by bytes in flight: one column per thread in
+// registers = 73 KB per SM whatever the block shape (which is why 32 warps of one row each change nothing).
+// Next step (round 2): land the raw columns in shared memory with bulk async copies two columns ahead
+// (18-slot ring with two barriers + two 18.7 KB stages, three blocks per SM) so that loads never wait.
 #include <cstdlib>
 
 #include "plbm_internal.h"
