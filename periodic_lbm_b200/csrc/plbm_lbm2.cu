@@ -32,10 +32,11 @@
 // count or DRAM locality (ncu: stall_mio_throttle dominates, HBM 58 % busy).  Legs of that path at 8192^2,
 // per pair launch: ring only (no global loads, no stores) 0.47 ms; loads + ring 1.14 ms (4.2 TB/s of
 // reads); ring + stores 0.89 ms (5.5 TB/s of writes); everything 2.08 ms ~ the SUM of the two legs: loads
-// and stores do not overlap.  The load leg is bound by bytes in flight: one column per thread in
-// registers = 73 KB per SM whatever the block shape (which is why 32 warps of one row each change nothing).
-// Next step (round 2): land the raw columns in shared memory with bulk async copies two columns ahead
-// (18-slot ring with two barriers + two 18.7 KB stages, three blocks per SM) so that loads never wait.
+// and stores do not overlap.  More bytes in flight do not help either: two columns of operands in two
+// register sets (168 registers, three blocks per SM, 110 KB in flight) 63.0.  Every structure tried moves
+// ~4.7 TB/s of HBM traffic; what caps the mixed load/store stream of this kernel below the 6.5 TB/s of a
+// plain copy is the open question for round 2 (candidates: bulk async copies for the raw columns and for
+// the result columns, so that neither passes through per-thread LDG/STG).
 #include <cstdlib>
 
 #include "plbm_internal.h"
