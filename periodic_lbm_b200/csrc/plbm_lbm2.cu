@@ -37,6 +37,7 @@
 // ~4.7 TB/s of HBM traffic; what caps the mixed load/store stream of this kernel below the 6.5 TB/s of a
 // plain copy is the open question for round 2 (candidates: bulk async copies for the raw columns and for
 // the result columns, so that neither passes through per-thread LDG/STG).
+#include <cstdint>
 #include <cstdlib>
 
 #include "plbm_internal.h"
@@ -226,6 +227,217 @@ __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
     }
 }
 
+// ---- experiment: raw columns land in shared memory by bulk async copies, two columns ahead ------------------
+// Ring of 18 slots (two barriers per column) + two stages of nine raw population columns; no per-thread LDG.
+__host__ __device__ constexpr int ringb_depth(int q) { return cxi(q) == -1 ? 1 : (cxi(q) == 0 ? 2 : 3); }
+__host__ __device__ constexpr int ringb_base(int q)
+{
+    return q == 3 ? 0 : q == 6 ? 1 : q == 7 ? 2 : q == 0 ? 3 : q == 2 ? 5 : q == 4 ? 7 : q == 1 ? 9 : q == 5 ? 12 : 15;
+}
+constexpr int RINGB_SLOTS = 18;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    long long spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1ll << 26)) __trap();  // a lost copy must fail loudly, never hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_lbm2_bulk(const Lbm2Args<T> a)
+{
+    constexpr int W = NT * V;       // rows of one ring column: logical rows y_lo - V .. y_lo - V + W - 1
+    constexpr int WS = W + 2 * V;   // rows of one staged raw column: logical rows y_lo - 2V .. (one extra vector each side)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* ring = reinterpret_cast<T*>(smem_raw);
+    T* stage = ring + RINGB_SLOTS * W;  // [2][9][WS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * 9 * WS);
+    const uint32_t bar[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+
+    const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
+    const int y_lo = strip * a.ty;
+    const int y_hi = min(y_lo + a.ty, a.ny);
+    const int xs = a.x_begin + seg * a.seglen;
+    const int xe = min(xs + a.seglen, a.x_end);
+    const int t = threadIdx.x;
+    const int yl = y_lo - V + t * V;
+    const bool act_a = yl < y_hi + V;
+    const bool act_b = yl >= y_lo && yl < y_hi;
+    const int yp = yl < 0 ? yl + a.ny : (yl >= a.ny ? yl - a.ny : yl);
+    // staged logical rows [r0, r1): what phase A reads, rounded to whole vectors
+    const int r0 = y_lo - 2 * V, r1 = y_hi + 2 * V;
+
+    if (t == 0) {
+        mbar_init(bar[0], 1);
+        mbar_init(bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // one raw column (all nine populations, pulled: population q from column xl - cx_q) into stage s
+    auto issue = [&](int xl, int s) {
+        mbar_expect_tx(bar[s], (uint32_t)(9 * (r1 - r0) * sizeof(T)));
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            int col = xl - cxi(q);
+            col = col < 0 ? col + a.nx : (col >= a.nx ? col - a.nx : col);
+            const T* line = a.src + ((size_t)q * a.nx + col) * (size_t)a.ld;
+            T* dst = stage + (s * 9 + q) * WS;
+            // periodic pieces of [r0, r1): below 0, inside, beyond ny (all multiples of V rows = 16 bytes)
+            if (r0 < 0) bulk_load(smem_u32(dst), line + (a.ny + r0), (uint32_t)(-r0 * sizeof(T)), bar[s]);
+            const int m0 = max(r0, 0), m1 = min(r1, a.ny);
+            bulk_load(smem_u32(dst + (m0 - r0)), line + m0, (uint32_t)((m1 - m0) * sizeof(T)), bar[s]);
+            if (r1 > a.ny) bulk_load(smem_u32(dst + (a.ny - r0)), line, (uint32_t)((r1 - a.ny) * sizeof(T)), bar[s]);
+        }
+    };
+    int w2 = 0, w3 = 0;  // ring slot of the column being written (depth 2 / depth 3 groups)
+    auto phase_a = [&](int s, uint32_t parity) {
+        mbar_wait(bar[s], parity);
+        if (act_a) {
+            T n[V][9];
+            const int i = V + t * V;  // stage row of this thread's first row
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const T* col = stage + (s * 9 + q) * WS + i;
+                const int cy = cyi(q);
+                if (cy == 0) {
+                    const Vec<T, V> p = *reinterpret_cast<const Vec<T, V>*>(col);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) n[v][q] = p.v[v];
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) n[v][q] = col[v - cy];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int slot = ringb_depth(q) == 1 ? 0 : (ringb_depth(q) == 2 ? w2 : w3);
+                Vec<T, V> p;
+#pragma unroll
+                for (int v = 0; v < V; ++v) p.v[v] = n[v][q];
+                *reinterpret_cast<Vec<T, V>*>(ring + (ringb_base(q) + slot) * W + t * V) = p;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // stage reads before the async refill
+    };
+    auto advance = [&]() {
+        w2 ^= 1;
+        w3 = w3 == 2 ? 0 : w3 + 1;
+    };
+
+    // columns are numbered k = xl - (xs - 1); column k uses stage k & 1 with parity (k >> 1) & 1
+    if (t == 0) {
+        issue(xs - 1, 0);
+        issue(xs, 1);
+    }
+    phase_a(0, 0);  // A(xs - 1)
+    advance();
+    __syncthreads();
+    if (t == 0) issue(xs + 1, 0);
+    phase_a(1, 0);  // A(xs)
+    advance();
+    __syncthreads();
+    if (t == 0 && xs + 2 <= xe) issue(xs + 2, 1);
+
+    for (int x = xs; x < xe; ++x) {
+        const int k = x + 1 - (xs - 1);  // column x + 1
+        phase_a(k & 1, (uint32_t)((k >> 1) & 1));
+        __syncthreads();
+        if (t == 0 && x + 3 <= xe) issue(x + 3, k & 1);  // lands during phase B of this and A/B of the next column
+        if (act_b) {
+            T f[V][9];
+            const int r2 = w2 ^ 1;                // column x
+            const int r3 = w3 == 2 ? 0 : w3 + 1;  // column x - 1
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int slot = ringb_depth(q) == 1 ? 0 : (ringb_depth(q) == 2 ? r2 : r3);
+                const T* col = ring + (ringb_base(q) + slot) * W + t * V;
+                const int cy = cyi(q);
+                if (cy == 0) {
+                    const Vec<T, V> p = *reinterpret_cast<const Vec<T, V>*>(col);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) f[v][q] = p.v[v];
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) f[v][q] = col[v - cy];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) collide<T, MODEL>(f[v], a.cp);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                Vec<T, V> p;
+#pragma unroll
+                for (int v = 0; v < V; ++v) p.v[v] = f[v][q];
+                *reinterpret_cast<Vec<T, V>*>(a.dst + ((size_t)q * a.nx + x) * (size_t)a.ld + yp) = p;
+            }
+        }
+        advance();
+        __syncthreads();
+    }
+}
+
+template <typename T, int MODEL> int launch_pair_bulk(const Grid& g, const T* src, T* dst, const CollideParams<T>& cp, cudaStream_t s)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int NT = 128, MINB = 3;
+    constexpr int W = NT * V, WS = W + 2 * V;
+    constexpr size_t smem = ((size_t)RINGB_SLOTS * W + 2 * 9 * WS) * sizeof(T) + 16;
+    auto kern = k_lbm2_bulk<T, MODEL, V, NT, MINB>;
+    static bool configured = false;
+    if (!configured) {
+        PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    Lbm2Args<T> a;
+    a.src = src;
+    a.dst = dst;
+    a.nx = g.nx;
+    a.ny = g.ny;
+    a.ld = g.ld;
+    a.x_begin = 0;
+    a.x_end = g.nx;
+    a.halo_lo = a.halo_hi = nullptr;
+    a.cp = cp;
+    const int ty_max = (NT - 2) * V;
+    a.nstrips = (g.ny + ty_max - 1) / ty_max;
+    a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
+    a.nstrips = (g.ny + a.ty - 1) / a.ty;
+    int nseg = (g.nx + 63) / 64;
+    a.seglen = (g.nx + nseg - 1) / nseg;
+    nseg = (g.nx + a.seglen - 1) / a.seglen;
+    kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    return PLBM_OK;
+}
+
 int env_int(const char* name, int dflt)
 {
     const char* e = getenv(name);
@@ -328,6 +540,10 @@ template <typename T>
 int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
                     const CollideParams<T>& cp, cudaStream_t s)
 {
+    if (!halo_lo && x_begin == 0 && x_end == g.nx && g.ny >= 8 * (16 / (int)sizeof(T)) && (model == M_BGK || model == M_RR)) {  // experiment
+        static const int bulk = env_int("PLBM_PAIR_BULK", 0);
+        if (bulk) return model == M_BGK ? launch_pair_bulk<T, M_BGK>(g, src, dst, cp, s) : launch_pair_bulk<T, M_RR>(g, src, dst, cp, s);
+    }
     if (halo_lo && halo_hi) return dispatch_pair<T, true>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s);
     return dispatch_pair<T, false>(g, src, dst, x_begin, x_end, nullptr, nullptr, model, cp, s);
 }
