@@ -166,10 +166,16 @@ long long plbm_launch_count(void);
  *   perform_lbm_step : 0 direct 128-bit loads, two steps per pass over HBM when nsteps >= 3 (or the cluster-
  *                      resident multi-step kernel when the grid fits in shared memory); one step per launch:
  *                      1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints;
- *                      5 = like 0 but never the cluster kernel (tests of the two-step kernel on small grids)
+ *                      5 = like 0 but never the cluster kernel (tests of the two-step kernel on small grids);
+ *                      6 / 7 = like 5 with the two-step kernel's raw columns fetched by per-thread loads (k_lbm2) /
+ *                      by bulk async copies (k_lbm2_bulk); 8 = 7 issued as the three line ranges of the slab schedule
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
  *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused */
 int plbm_set_variant(plbm_handle grid, int variant);
+/* which kernel perform_lbm_step(nsteps >= 3) advances this grid with: 0 = one step per launch (k_lbm),
+ * 1 = two steps per launch, raw columns by per-thread loads (k_lbm2), 2 = two steps per launch, raw columns by
+ * bulk async copies (k_lbm2_bulk).  For bench accounting; < 0 on error. */
+int plbm_lbm_pair_kernel(plbm_handle grid);
 /* derivative stencil of stream_fdm_bardow: the reference selects it at compile time with -DFDM_WLS,
  * -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660); default = none of them. */
 enum plbm_fdm_stencil { PLBM_FDM_DEFAULT = 0, PLBM_FDM_WLS = 1, PLBM_FDM_WLS_GAUSS_V1 = 2, PLBM_FDM_WLS_GAUSS_V2 = 3, PLBM_FDM_ISO = 4 };

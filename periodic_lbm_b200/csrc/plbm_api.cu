@@ -145,13 +145,24 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         }
     }
     int s = 0;
-    if ((g.variant == 0 || g.variant == 5) && lbm_pair_applicable(g)) {  // 5: also on grids the cluster kernel would take
+    if (lbm_pair_variant(g.variant) && lbm_pair_applicable(g)) {  // 5..8: also on grids the cluster kernel would take
         // two steps per pass over HBM.  The last step stays single so that lattice `inew` ends up holding
         // state n-1 exactly as in the reference (what the lagged update_macros reads).  A pair leaves its
         // result in the buffer that was `inew`; two reference swaps leave the indices unchanged, so the
         // buffers trade places instead.
+        const CollideParams<T> cp = collide_params<T>(g, model);
         for (; s + 2 < nsteps; s += 2) {
-            int rc = launch_lbm_pair<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, nullptr, nullptr, model, collide_params<T>(g, model), g.stream);
+            const T* src = g.lat<T>(g.iold);
+            T* dst = g.lat<T>(g.inew);
+            int rc;
+            if (g.variant == 8 && g.nx >= 8) {
+                // test knob: the launch sequence of the slab decomposition (boundary lines, then the interior) on one GPU
+                rc = launch_lbm_pair<T>(g, src, dst, 0, 2, nullptr, nullptr, model, cp, g.stream);
+                if (!rc) rc = launch_lbm_pair<T>(g, src, dst, g.nx - 2, g.nx, nullptr, nullptr, model, cp, g.stream);
+                if (!rc) rc = launch_lbm_pair<T>(g, src, dst, 2, g.nx - 2, nullptr, nullptr, model, cp, g.stream);
+            } else {
+                rc = launch_lbm_pair<T>(g, src, dst, 0, g.nx, nullptr, nullptr, model, cp, g.stream);
+            }
             if (rc) return rc;
             std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
             for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
@@ -812,6 +823,16 @@ int plbm_set_variant(plbm_handle g, int variant)
     }
     g->variant = variant;
     return PLBM_OK;
+}
+
+int plbm_lbm_pair_kernel(plbm_handle g)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return -1;
+    }
+    if (g->comm && !comm_pairs_agreed(*g)) return 0;
+    return lbm_pair_flavour(*g);
 }
 
 int plbm_comm_unique_id(void* id128) { return comm_unique_id(id128); }

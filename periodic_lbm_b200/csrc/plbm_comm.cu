@@ -286,6 +286,7 @@ static int p2p_setup(Grid& g)
 }
 
 int comm_transport_is_p2p(const Grid& g) { return g.comm && g.comm->p2p ? 1 : 0; }
+bool comm_pairs_agreed(const Grid& g) { return g.comm && g.comm->pairs_ok; }
 
 int comm_unique_id(void* id128)
 {
@@ -483,7 +484,7 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    const bool pairs = (g.variant == 0 || g.variant == 5) && c->pairs_ok;
+    const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
     for (int s = 0; s < nsteps;) {
         // two steps per pass over HBM while at least one single step remains (the last step stays single so
         // that lattice `inew` ends up holding state n-1 like the reference, see step_lbm_t)
@@ -530,7 +531,7 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    const bool pairs = (g.variant == 0 || g.variant == 5) && c->pairs_ok;
+    const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
     for (int s = 0; s < nsteps;) {
         const bool pair = pairs && s + 2 < nsteps;
         const int p = c->parity;

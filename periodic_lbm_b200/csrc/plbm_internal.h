@@ -106,6 +106,10 @@ int try_lbm_cluster_steps(const Grid& g, T* f_iold, T* f_inew, int model, const 
                           cudaStream_t s);
 // two steps per pass over HBM through a shared-memory ring (plbm_lbm2.cu)
 bool lbm_pair_applicable(const Grid& g);
+// variants of perform_lbm_step that advance two steps per launch: 0 default, 5 never the cluster kernel,
+// 6 per-thread loads forced, 7 bulk async copies forced, 8 = 7 issued as the slab schedule's three x ranges
+inline bool lbm_pair_variant(int variant) { return variant == 0 || (variant >= 5 && variant <= 8); }
+int lbm_pair_flavour(const Grid& g);  // 0 one step per launch, 1 k_lbm2, 2 k_lbm2_bulk
 template <typename T>
 int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
                     const CollideParams<T>& cp, cudaStream_t s);
@@ -121,6 +125,7 @@ int comm_unique_id(void* id128);
 int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, int x_offset);
 int comm_finalize(Grid& g);
 int comm_transport_is_p2p(const Grid& g);
+bool comm_pairs_agreed(const Grid& g);  // every slab of the ring can run the two-step kernel
 void comm_invalidate_halo(Grid& g);  // the lattices were modified behind the ring's back
 template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps);
 // one FVM/DUGKS halo exchange: all nine populations of lines 0 and nx-1 of `f` -> g.fv_halo_lo/hi

@@ -167,7 +167,7 @@ template <typename T, int MODEL, int V, int NT, int MINB, bool HALO>
 __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
 {
     constexpr int W = NT * V;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ring = reinterpret_cast<T*>(smem_raw);
 
     const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
@@ -275,7 +275,8 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
     T* ring = reinterpret_cast<T*>(smem_raw);
     T* stage = ring + RINGB_SLOTS * W;  // [2][9][WS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * 9 * WS);
-    const uint32_t bar[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };  // one mbarrier per stage
 
     const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
     const int y_lo = strip * a.ty;
@@ -291,15 +292,15 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
     const int r0 = y_lo - 2 * V, r1 = y_hi + 2 * V;
 
     if (t == 0) {
-        mbar_init(bar[0], 1);
-        mbar_init(bar[1], 1);
+        mbar_init(bar(0), 1);
+        mbar_init(bar(1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // one raw column (all nine populations, pulled: population q from column xl - cx_q) into stage s
     auto issue = [&](int xl, int s) {
-        mbar_expect_tx(bar[s], (uint32_t)(9 * (r1 - r0) * sizeof(T)));
+        mbar_expect_tx(bar(s), (uint32_t)(9 * (r1 - r0) * sizeof(T)));
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
             int col = xl - cxi(q);
@@ -307,15 +308,15 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
             const T* line = a.src + ((size_t)q * a.nx + col) * (size_t)a.ld;
             T* dst = stage + (s * 9 + q) * WS;
             // periodic pieces of [r0, r1): below 0, inside, beyond ny (all multiples of V rows = 16 bytes)
-            if (r0 < 0) bulk_load(smem_u32(dst), line + (a.ny + r0), (uint32_t)(-r0 * sizeof(T)), bar[s]);
+            if (r0 < 0) bulk_load(smem_u32(dst), line + (a.ny + r0), (uint32_t)(-r0 * sizeof(T)), bar(s));
             const int m0 = max(r0, 0), m1 = min(r1, a.ny);
-            bulk_load(smem_u32(dst + (m0 - r0)), line + m0, (uint32_t)((m1 - m0) * sizeof(T)), bar[s]);
-            if (r1 > a.ny) bulk_load(smem_u32(dst + (a.ny - r0)), line, (uint32_t)((r1 - a.ny) * sizeof(T)), bar[s]);
+            bulk_load(smem_u32(dst + (m0 - r0)), line + m0, (uint32_t)((m1 - m0) * sizeof(T)), bar(s));
+            if (r1 > a.ny) bulk_load(smem_u32(dst + (a.ny - r0)), line, (uint32_t)((r1 - a.ny) * sizeof(T)), bar(s));
         }
     };
     int w2 = 0, w3 = 0;  // ring slot of the column being written (depth 2 / depth 3 groups)
     auto phase_a = [&](int s, uint32_t parity) {
-        mbar_wait(bar[s], parity);
+        mbar_wait(bar(s), parity);
         if (act_a) {
             T n[V][9];
             const int i = V + t * V;  // stage row of this thread's first row
@@ -402,18 +403,20 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
     }
 }
 
-template <typename T, int MODEL> int launch_pair_bulk(const Grid& g, const T* src, T* dst, const CollideParams<T>& cp, cudaStream_t s)
+template <typename T, int MODEL>
+int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int NT = 128, MINB = 3;
     constexpr int W = NT * V, WS = W + 2 * V;
     constexpr size_t smem = ((size_t)RINGB_SLOTS * W + 2 * 9 * WS) * sizeof(T) + 16;
+    if (x_end <= x_begin) return PLBM_OK;
     auto kern = k_lbm2_bulk<T, MODEL, V, NT, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (g.device < 64 && !configured[g.device]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+        configured[g.device] = true;
     }
     Lbm2Args<T> a;
     a.src = src;
@@ -421,22 +424,45 @@ template <typename T, int MODEL> int launch_pair_bulk(const Grid& g, const T* sr
     a.nx = g.nx;
     a.ny = g.ny;
     a.ld = g.ld;
-    a.x_begin = 0;
-    a.x_end = g.nx;
+    a.x_begin = x_begin;
+    a.x_end = x_end;
     a.halo_lo = a.halo_hi = nullptr;
     a.cp = cp;
+    // the fewest strips (2V redundant rows each), 64-column segments (two warm-up columns each): ~19 waves
+    // of 148 x 3 blocks at 32768 x 4096, so the block scheduler evens out the SMs
+    const int ncols = x_end - x_begin;
     const int ty_max = (NT - 2) * V;
     a.nstrips = (g.ny + ty_max - 1) / ty_max;
     a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
-    int nseg = (g.nx + 63) / 64;
-    a.seglen = (g.nx + nseg - 1) / nseg;
-    nseg = (g.nx + a.seglen - 1) / a.seglen;
+    int nseg = (ncols + 63) / 64;
+    a.seglen = (ncols + nseg - 1) / nseg;
+    nseg = (ncols + a.seglen - 1) / a.seglen;
     kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
 }
+
+template <typename T>
+int dispatch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, cudaStream_t s)
+{
+    switch (model) {
+    case M_BGK: return launch_pair_bulk<T, M_BGK>(g, src, dst, x_begin, x_end, cp, s);
+    case M_TRT: return launch_pair_bulk<T, M_TRT>(g, src, dst, x_begin, x_end, cp, s);
+    case M_RR: return launch_pair_bulk<T, M_RR>(g, src, dst, x_begin, x_end, cp, s);
+    case M_BGK_SPLIT: return launch_pair_bulk<T, M_BGK_SPLIT>(g, src, dst, x_begin, x_end, cp, s);
+    case M_TRT_SPLIT: return launch_pair_bulk<T, M_TRT_SPLIT>(g, src, dst, x_begin, x_end, cp, s);
+    case M_BGK_IMPROVED: return launch_pair_bulk<T, M_BGK_IMPROVED>(g, src, dst, x_begin, x_end, cp, s);
+    }
+    set_error("launch_lbm_pair: unknown collision model");
+    return PLBM_ERR_ARG;
+}
+
+// default flavour of the two-step kernel where both apply: 1 = bulk async copies (k_lbm2_bulk), 0 = per-thread loads
+#ifndef PLBM_PAIR_BULK_DEFAULT
+#define PLBM_PAIR_BULK_DEFAULT 0
+#endif
 
 int env_int(const char* name, int dflt)
 {
@@ -533,6 +559,18 @@ bool lbm_pair_applicable(const Grid& g)
     return g.nx >= 4 && g.ny >= 2 * v && (g.ny % v) == 0;
 }
 
+// Which kernel advances a pair of steps on this grid: 0 none (one step per launch), 1 k_lbm2 (raw columns by
+// per-thread loads), 2 k_lbm2_bulk (raw columns by bulk async copies).
+int lbm_pair_flavour(const Grid& g)
+{
+    if (!lbm_pair_variant(g.variant) || !lbm_pair_applicable(g)) return 0;
+    if (g.ny < 8 * (16 / (int)g.esize())) return 1;
+    static const int bulk_default = env_int("PLBM_PAIR_BULK", PLBM_PAIR_BULK_DEFAULT);
+    if (g.variant == 6) return 1;
+    if (g.variant == 7 || g.variant == 8) return 2;
+    return bulk_default != 0 ? 2 : 1;
+}
+
 // Two fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' two
 // nearest lines ([2][9][ld]) under a slab decomposition, nullptr = periodic self-wrap.  The caller
 // accounts for the lattice roles (see step_lbm_t).
@@ -540,10 +578,8 @@ template <typename T>
 int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
                     const CollideParams<T>& cp, cudaStream_t s)
 {
-    if (!halo_lo && x_begin == 0 && x_end == g.nx && g.ny >= 8 * (16 / (int)sizeof(T)) && (model == M_BGK || model == M_RR)) {  // experiment
-        static const int bulk = env_int("PLBM_PAIR_BULK", 0);
-        if (bulk) return model == M_BGK ? launch_pair_bulk<T, M_BGK>(g, src, dst, cp, s) : launch_pair_bulk<T, M_RR>(g, src, dst, cp, s);
-    }
+    // The launches that read the neighbours' halo lines (two boundary lines per side of a slab) stay on k_lbm2.
+    if (!halo_lo && lbm_pair_flavour(g) == 2) return dispatch_pair_bulk<T>(g, src, dst, x_begin, x_end, model, cp, s);
     if (halo_lo && halo_hi) return dispatch_pair<T, true>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s);
     return dispatch_pair<T, false>(g, src, dst, x_begin, x_end, nullptr, nullptr, model, cp, s);
 }

@@ -115,6 +115,14 @@ class LatticeGrid:
 
     FDM_STENCILS = {"default": 0, "wls": 1, "wls_gauss_v1": 2, "wls_gauss_v2": 3, "iso": 4}
 
+    def pair_kernel(self):
+        """Kernel a perform_lbm_step call of >= 3 steps uses on this grid: 'k_lbm' (one step per launch),
+        'k_lbm2' or 'k_lbm2_bulk' (two steps per launch)."""
+        k = lib.plbm_lbm_pair_kernel(self._h)
+        if k < 0:
+            check(k, "lbm_pair_kernel")
+        return ("k_lbm", "k_lbm2", "k_lbm2_bulk")[k]
+
     def set_fdm_stencil(self, stencil):
         """Derivative stencil of stream_fdm_bardow; the reference picks it at compile time with -DFDM_WLS,
         -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660)."""

@@ -55,7 +55,7 @@ def oracle_collide(o, f, ny, p, ocoll):
 def assert_same_lattice(g, og, which_g, which_o, ny):
     got = g.download_f(which_g)[:, :, :ny]
     want = og.lattice(which_o)[:, :, :ny]
-    assert np.array_equal(got, want), f"max abs diff {np.abs(got - want).max():.3e}"
+    assert np.array_equal(got, want), f"max abs diff {np.abs(got - want).max():.3e} in {int((got != want).sum())} values"
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -126,24 +126,33 @@ def test_fused_lbm_steps(plbm, nx, ny, prec, variant):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("nx,ny", [(64, 64), (16, 132), (4, 8), (9, 4), (40, 516), (300, 260), (5, 1024), (37, 2048)])
+@pytest.mark.parametrize("nx,ny", [(64, 64), (16, 132), (4, 8), (9, 4), (40, 516), (300, 260), (5, 1024), (37, 2048), (70, 16), (8, 32)])
 def test_two_step_kernel(plbm, nx, ny, prec):
-    """The temporal-blocking kernel (two steps per pass over HBM, plbm_lbm2.cu; variant 5 forces it on grids
-    the cluster kernel would take): several strips / x segments, ragged last strip, odd step counts, both
-    lattices and the lagged macros bit-identical to the oracle."""
+    """The temporal-blocking kernels (two steps per pass over HBM, plbm_lbm2.cu) on grids the cluster kernel
+    would otherwise take: several strips / x segments, ragged last strip, odd step counts, both lattices and
+    the lagged macros bit-identical to the oracle.  Variant 5 = the library's default flavour, 6 = raw columns
+    by per-thread loads (k_lbm2), 7 = by bulk async copies (k_lbm2_bulk), 8 = 7 issued as the three x ranges
+    of the slab schedule (boundary lines, then the interior)."""
     for nsteps, (coll, ocoll) in zip((3, 4, 5, 8, 9, 6), collisions(plbm)):
-        og, g = make_pair(plbm, nx, ny, prec)
-        g.set_variant(5)
-        g.collision, g.streaming = coll, plbm.lbm_stream
-        plbm.perform_lbm_step(g, nsteps)
+        og, g0 = make_pair(plbm, nx, ny, prec)
+        f0 = g0.download_f(g0.iold)
+        plbm.dealloc_grid(g0)
         og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
-        assert (g.iold, g.inew) == (og.iold, og.inew)
-        assert_same_lattice(g, og, g.iold, og.iold, ny)
-        assert_same_lattice(g, og, g.inew, og.inew, ny)
-        plbm.update_macros(g)
         r, u, v = og.update_macros(lagged=True)
-        assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v)
-        plbm.dealloc_grid(g)
+        for variant in (5, 6, 7, 8):
+            g = plbm.alloc_grid(nx, ny, precision=prec)
+            plbm.set_properties(g, 0.02, 1.0, 0.25)
+            g.upload_f(g.iold, f0)
+            g.upload_f(g.inew, np.zeros_like(f0))
+            g.set_variant(variant)
+            g.collision, g.streaming = coll, plbm.lbm_stream
+            plbm.perform_lbm_step(g, nsteps)
+            assert (g.iold, g.inew) == (og.iold, og.inew), f"variant {variant}"
+            assert_same_lattice(g, og, g.iold, og.iold, ny)
+            assert_same_lattice(g, og, g.inew, og.inew, ny)
+            plbm.update_macros(g)
+            assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v), f"variant {variant}"
+            plbm.dealloc_grid(g)
 
 
 @pytest.mark.parametrize("prec", PRECS)
