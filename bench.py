@@ -59,12 +59,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_lup(workload):
+def ncu_traffic_per_lup(workload, kernel="k_lbm2"):
     """dram bytes (read+write) per lattice update of the dominant kernel, from the committed ncu
-    --set full capture summarised in profiles/ncu_summary.json (None when not captured)."""
+    --set full capture summarised in profiles/ncu_summary.json (None when that kernel was not captured
+    on this workload).  Keys: `<workload>` for k_lbm2, `<workload>@<kernel>` for the others."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as fh:
-            return float(json.load(fh)[workload]["dram_bytes_per_lup"])
+            return float(json.load(fh)[workload if kernel == "k_lbm2" else f"{workload}@{kernel}"]["dram_bytes_per_lup"])
     except Exception:
         return None
 
@@ -338,7 +339,8 @@ def run_ours(args):
         nodes_local = nxl * ny
         pair_ms, single_ms = pair_kernel_ms
         achieved = 2 * nodes_local * bpl / (pair_ms * 1e-3) / 1e9
-        tr = ncu_traffic_per_lup(args.workload)
+        pair_kernel = g.pair_kernel()  # k_lbm2 (raw columns by per-thread loads) or k_lbm2_bulk (by bulk async copies)
+        tr = ncu_traffic_per_lup(args.workload, pair_kernel)
         traffic = None if tr is None else round(tr * 2 * nodes_local)
         line = {
             "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS (1e6 lattice updates/s)", "n_gpus": world, "steps": K, "warmup": W,
@@ -357,7 +359,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 2 * nodes_local * bpl, "kernel": "k_lbm2<two fused stream+collide steps>",
+                         "algorithmic_bytes_per_launch": 2 * nodes_local * bpl, "kernel": f"{pair_kernel}<two fused stream+collide steps>",
                          "launch_ms": round(pair_ms, 4), "per_gpu": True,
                          "dram_frac": None if traffic is None else round(traffic / (pair_ms * 1e-3) / 1e9 / peak, 4),
                          "single_step_kernel": {"kernel": "k_lbm<fused stream+collide>", "launch_ms": round(single_ms, 4),

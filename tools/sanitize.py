@@ -13,7 +13,9 @@ import periodic_lbm_b200 as p  # noqa: E402
 rng = np.random.default_rng(1)
 for prec in ("f64", "f32"):
     for nx, ny in ((67, 53), (5, 3), (64, 64), (40, 130), (36, 520)):
-        for variant in (0, 1, 2, 3, 4, 5):  # 5: the two-step ring kernel also on grids the cluster kernel would take
+        # 5..8: the two-step kernels also on grids the cluster kernel would take (6 per-thread loads, 7 bulk async
+        # copies, 8 = 7 over the slab schedule's line ranges)
+        for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):
             g = p.alloc_grid(nx, ny, nf=3, precision=prec)
             p.set_properties(g, 0.02, 0.3, 0.25)
             g.rho[:] = 1.0 + 0.01 * rng.random((nx, ny))
