@@ -35,8 +35,12 @@
 // and stores do not overlap.  More bytes in flight do not help either: two columns of operands in two
 // register sets (168 registers, three blocks per SM, 110 KB in flight) 63.0.  Every structure tried moves
 // ~4.7 TB/s of HBM traffic; what caps the mixed load/store stream of this kernel below the 6.5 TB/s of a
-// plain copy is the open question for round 2 (candidates: bulk async copies for the raw columns and for
-// the result columns, so that neither passes through per-thread LDG/STG).
+// plain copy was the open question -- answered by k_lbm2_bulk below: with the raw columns delivered by bulk
+// async copies (cp.async.bulk + mbarrier, issued by one thread two columns ahead) no thread issues an LDG,
+// the memory-instruction queue only carries the ring traffic and the result stores (stall_mio_throttle 3.5 ->
+// 0.28 per issue), and the kernel moves 6.2-6.4 TB/s of DRAM traffic = 0.95-0.97 of the measured copy peak:
+// BGK / TRT / RR fp64 83.0 / 82.7 / 68.5 GLUPS at 8192^2 (k_lbm2: 63.9 / 64.1 / 58.5), fp32 BGK 147 (119).
+// k_lbm2_bulk is the default; k_lbm2 serves the launches that read a neighbour's halo lines and tiny ny.
 #include <cstdint>
 #include <cstdlib>
 
@@ -227,8 +231,14 @@ __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
     }
 }
 
-// ---- experiment: raw columns land in shared memory by bulk async copies, two columns ahead ------------------
-// Ring of 18 slots (two barriers per column) + two stages of nine raw population columns; no per-thread LDG.
+// ---- k_lbm2_bulk: raw columns land in shared memory by bulk async copies, two columns ahead -----------------
+// Ring of 18 slots (a population is kept 1 / 2 / 3 columns for cx = -1 / 0 / +1; two barriers per column) + two
+// stages of nine raw population lines, each guarded by one mbarrier: thread 0 arms the barrier with the byte
+// count of the column (arrive.expect_tx) and issues one cp.async.bulk per population line -- up to three pieces
+// where the staged rows [y_lo - 2V, y_hi + 2V) wrap around y; every piece starts and ends on a 16-byte boundary
+// because y_lo, y_hi, ny and ld are multiples of V.  Column k of a segment uses stage k & 1 and completes phase
+// (k >> 1) & 1 of its barrier; the refill of a stage is issued right after the barrier that ends its last read
+// (fence.proxy.async orders those generic reads before the async writes).  No per-thread LDG.
 __host__ __device__ constexpr int ringb_depth(int q) { return cxi(q) == -1 ? 1 : (cxi(q) == 0 ? 2 : 3); }
 __host__ __device__ constexpr int ringb_base(int q)
 {
