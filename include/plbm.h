@@ -163,8 +163,9 @@ int plbm_synchronize(plbm_handle grid);
 /* kernels launched by this process through the library since load (for bench accounting) */
 long long plbm_launch_count(void);
 /* select a kernel variant (tuning / A-B measurements); 0 = default everywhere.
- *   perform_lbm_step : 0 direct 128-bit loads, two steps per pass over HBM when nsteps >= 3 (or the cluster-
- *                      resident multi-step kernel when the grid fits in shared memory); one step per launch:
+ *   perform_lbm_step : 0 direct 128-bit loads, two steps per pass over HBM when nsteps >= 3 (k_lbm2_bulk on large
+ *                      grids, k_lbm2 on smaller ones; or the cluster-resident multi-step kernel when the grid fits
+ *                      in shared memory; env PLBM_PAIR_BULK=0 / 2: k_lbm2 / k_lbm2_bulk everywhere); one step per launch:
  *                      1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints;
  *                      5 = like 0 but never the cluster kernel (tests of the two-step kernel on small grids);
  *                      6 / 7 = like 5 with the two-step kernel's raw columns fetched by per-thread loads (k_lbm2) /

@@ -575,11 +575,18 @@ bool lbm_pair_applicable(const Grid& g)
 int lbm_pair_flavour(const Grid& g)
 {
     if (!lbm_pair_variant(g.variant) || !lbm_pair_applicable(g)) return 0;
-    if (g.ny < 8 * (16 / (int)g.esize())) return 1;
+    const int v = 16 / (int)g.esize();
+    if (g.ny < 8 * v) return 1;
     static const int bulk_default = env_int("PLBM_PAIR_BULK", PLBM_PAIR_BULK_DEFAULT);
     if (g.variant == 6) return 1;
     if (g.variant == 7 || g.variant == 8) return 2;
-    return bulk_default != 0 ? 2 : 1;
+    if (bulk_default == 0) return 1;
+    if (bulk_default >= 2) return 2;  // PLBM_PAIR_BULK=2: on every grid (A/B measurements)
+    // k_lbm2_bulk walks 64-column segments of full-height strips, three blocks per SM: measured on grids that give it
+    // many waves (8192^2: 9.5, the bench slab: 18.9).  Grids with fewer than two waves of such blocks stay on k_lbm2,
+    // whose launcher cuts strips and segments to fill one wave (measured 48 GLUPS at 1024^2).
+    const long long strips = (g.ny + 126 * v - 1) / (126 * v), segs = (g.nx + 63) / 64;
+    return strips * segs >= 2LL * 3 * g.sm_count ? 2 : 1;
 }
 
 // Two fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' two
