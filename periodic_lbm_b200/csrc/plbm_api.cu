@@ -145,7 +145,25 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         }
     }
     int s = 0;
-    if (lbm_pair_variant(g.variant) && lbm_pair_applicable(g)) {  // 5..8: also on grids the cluster kernel would take
+    if ((g.variant == 9 || g.variant == 10) && lbm_multi_applicable(g, model, g.variant == 9 ? 2 : 3)) {
+        // EXPERIMENTAL (plbm_lbmn.cu): the depth-generic multi-step kernel.  9: pairs through its NSTEP = 2 instance;
+        // 10: triples (three reference swaps = one swap of the indices; the result sits in lattice `inew`), then pairs.
+        const CollideParams<T> cp = collide_params<T>(g, model);
+        if (g.variant == 10) {
+            for (; s + 3 < nsteps; s += 3) {
+                int rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 3, g.stream);
+                if (rc) return rc;
+                swap_lattices(g);
+            }
+        }
+        for (; s + 2 < nsteps; s += 2) {
+            int rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 2, g.stream);
+            if (rc) return rc;
+            std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
+            for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
+        }
+    }
+    if (lbm_pair_variant(g.variant) && lbm_pair_applicable(g)) {  // 5..10: also on grids the cluster kernel would take
         // two steps per pass over HBM.  The last step stays single so that lattice `inew` ends up holding
         // state n-1 exactly as in the reference (what the lagged update_macros reads).  A pair leaves its
         // result in the buffer that was `inew`; two reference swaps leave the indices unchanged, so the

@@ -4,6 +4,8 @@ Bar: fp64 AND fp32 results are BIT-IDENTICAL to the oracle (the library is compi
 -fmad=false and evaluates every node in the reference's operation order), which is stronger than
 the north-star tolerance (1e-12 relative fp64, 1e-5 fp32).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -140,6 +142,35 @@ def test_two_step_kernel(plbm, nx, ny, prec):
         og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
         r, u, v = og.update_macros(lagged=True)
         for variant in (5, 6, 7, 8):
+            g = plbm.alloc_grid(nx, ny, precision=prec)
+            plbm.set_properties(g, 0.02, 1.0, 0.25)
+            g.upload_f(g.iold, f0)
+            g.upload_f(g.inew, np.zeros_like(f0))
+            g.set_variant(variant)
+            g.collision, g.streaming = coll, plbm.lbm_stream
+            plbm.perform_lbm_step(g, nsteps)
+            assert (g.iold, g.inew) == (og.iold, og.inew), f"variant {variant}"
+            assert_same_lattice(g, og, g.iold, og.iold, ny)
+            assert_same_lattice(g, og, g.inew, og.inew, ny)
+            plbm.update_macros(g)
+            assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v), f"variant {variant}"
+            plbm.dealloc_grid(g)
+
+
+@pytest.mark.skipif(os.environ.get("PLBM_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="experimental depth-generic multi-step kernel (csrc/plbm_lbmn.cu): set PLBM_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("nx,ny", [(64, 64), (16, 132), (40, 516), (300, 260), (5, 1024), (37, 2048), (70, 16), (8, 32), (4, 48)])
+def test_multi_step_kernel_experimental(plbm, nx, ny, prec):
+    """k_lbmn_bulk: variant 9 = pairs through its NSTEP = 2 instance, variant 10 = triples (+ pairs for the rest);
+    the schedule itself is pinned on the CPU by tests/test_multi_step_schedule.py."""
+    for nsteps, (coll, ocoll) in zip((3, 4, 5, 8, 9, 11), collisions(plbm)[:3] * 2):
+        og, g0 = make_pair(plbm, nx, ny, prec)
+        f0 = g0.download_f(g0.iold)
+        plbm.dealloc_grid(g0)
+        og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
+        r, u, v = og.update_macros(lagged=True)
+        for variant in (9, 10):
             g = plbm.alloc_grid(nx, ny, precision=prec)
             plbm.set_properties(g, 0.02, 1.0, 0.25)
             g.upload_f(g.iold, f0)

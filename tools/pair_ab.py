@@ -1,6 +1,7 @@
 """A/B of the two flavours of the two-step kernel (development tool, no torch: starts in a second).
 
-variant 6 = raw columns by per-thread loads (k_lbm2), 7 = by bulk async copies (k_lbm2_bulk).  Timed by the
+variant 6 = raw columns by per-thread loads (k_lbm2), 7 = by bulk async copies (k_lbm2_bulk); 9 / 10 = the experimental
+depth-generic kernel k_lbmn_bulk with two / three steps per pass (bgk, trt, rr).  Timed by the
 host clock around one perform_lbm_step(K) call with a device synchronize on both sides (K - 1 steps in pair
 launches + the closing single step), best of `reps`; one JSON line per case.  `--once` runs a single short
 call per case instead (for `ncu`)."""
