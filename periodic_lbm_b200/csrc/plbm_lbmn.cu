@@ -225,11 +225,19 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
     }
 }
 
-template <typename T, int MODEL, int NSTEP>
+int env_knob(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// NT = 128: 74 KB (NSTEP 2, three blocks per SM) / 111 KB (NSTEP 3, two blocks per SM) of shared memory per block;
+// NT = 256 (NSTEP 3 only, PLBM_MULTI_NT=256): one 222 KB block of eight warps per SM, strips of up to 504 rows (fp64)
+template <typename T, int MODEL, int NSTEP, int NT>
 int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
 {
     constexpr int V = 16 / (int)sizeof(T);
-    constexpr int NT = 128, MINB = NSTEP == 2 ? 3 : 2;
+    constexpr int MINB = NT == 256 ? 1 : (NSTEP == 2 ? 3 : 2);
     constexpr int W = NT * V, WS = W + 2 * V;
     constexpr size_t smem = ((size_t)(NSTEP - 1) * RN_SLOTS * W + 2 * 9 * WS) * sizeof(T) + 16;
     static_assert(smem <= 227 * 1024, "shared memory of one block");
@@ -256,11 +264,7 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     a.nstrips = (g.ny + ty_max - 1) / ty_max;
     a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
-    static const int seg_cols = []() {
-        const char* e = getenv("PLBM_MULTI_SEGLEN");
-        const int v = e && *e ? atoi(e) : 64;
-        return v < 1 ? 64 : v;
-    }();
+    static const int seg_cols = env_knob("PLBM_MULTI_SEGLEN", 64) < 1 ? 64 : env_knob("PLBM_MULTI_SEGLEN", 64);
     int nseg = (ncols + seg_cols - 1) / seg_cols;
     a.seglen = (ncols + nseg - 1) / nseg;
     nseg = (ncols + a.seglen - 1) / a.seglen;
@@ -270,13 +274,13 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     return PLBM_OK;
 }
 
-template <typename T, int NSTEP>
+template <typename T, int NSTEP, int NT>
 int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, cudaStream_t s)
 {
     switch (model) {
-    case M_BGK: return launch_n<T, M_BGK, NSTEP>(g, src, dst, x_begin, x_end, cp, s);
-    case M_TRT: return launch_n<T, M_TRT, NSTEP>(g, src, dst, x_begin, x_end, cp, s);
-    case M_RR: return launch_n<T, M_RR, NSTEP>(g, src, dst, x_begin, x_end, cp, s);
+    case M_BGK: return launch_n<T, M_BGK, NSTEP, NT>(g, src, dst, x_begin, x_end, cp, s);
+    case M_TRT: return launch_n<T, M_TRT, NSTEP, NT>(g, src, dst, x_begin, x_end, cp, s);
+    case M_RR: return launch_n<T, M_RR, NSTEP, NT>(g, src, dst, x_begin, x_end, cp, s);
     }
     set_error("launch_lbm_multi: collision model not instantiated for the experimental multi-step kernel");
     return PLBM_ERR_ARG;
@@ -302,7 +306,10 @@ int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end
         set_error("launch_lbm_multi: not applicable to this grid / collision / depth");
         return PLBM_ERR_ARG;
     }
-    return nstep == 2 ? dispatch_n<T, 2>(g, src, dst, x_begin, x_end, model, cp, s) : dispatch_n<T, 3>(g, src, dst, x_begin, x_end, model, cp, s);
+    if (nstep == 2) return dispatch_n<T, 2, 128>(g, src, dst, x_begin, x_end, model, cp, s);
+    static const int nt = env_knob("PLBM_MULTI_NT", 128);
+    if (nt == 256) return dispatch_n<T, 3, 256>(g, src, dst, x_begin, x_end, model, cp, s);
+    return dispatch_n<T, 3, 128>(g, src, dst, x_begin, x_end, model, cp, s);
 }
 
 template int launch_lbm_multi<double>(const Grid&, const double*, double*, int, int, int, const CollideParams<double>&, int, cudaStream_t);
