@@ -28,7 +28,7 @@ def run(nx, ny, prec, coll, variant, steps, reps, once=False):
     g.set_variant(variant)
     g.collision, g.streaming = getattr(p, "collide_" + coll), p.lbm_stream
     if once:
-        p.perform_lbm_step(g, 3)
+        p.perform_lbm_step(g, 4)  # one pair + two single steps; variant 10: one triple + one single step
         g.synchronize()
         p.dealloc_grid(g)
         return dict(nx=nx, ny=ny, prec=prec, coll=coll, variant=variant, once=True)
