@@ -176,7 +176,9 @@ long long plbm_launch_count(void);
 int plbm_set_variant(plbm_handle grid, int variant);
 /* which kernel perform_lbm_step(nsteps >= 3) advances this grid with: 0 = one step per launch (k_lbm),
  * 1 = two steps per launch, raw columns by per-thread loads (k_lbm2), 2 = two steps per launch, raw columns by
- * bulk async copies (k_lbm2_bulk).  For bench accounting; < 0 on error. */
+ * bulk async copies (k_lbm2_bulk).  Grids that fit in the shared memory of one cluster are advanced by the cluster-
+ * resident kernel instead when variant == 0 and nsteps >= 4; this query does not look at that.  For bench accounting;
+ * -1 on a null handle. */
 int plbm_lbm_pair_kernel(plbm_handle grid);
 /* derivative stencil of stream_fdm_bardow: the reference selects it at compile time with -DFDM_WLS,
  * -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660); default = none of them. */

@@ -31,6 +31,13 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert set(capi.SIGNATURES) == declared, set(capi.SIGNATURES) ^ declared
 
 
+def test_pair_kernel_query_rejects_a_null_handle():
+    from periodic_lbm_b200 import capi
+
+    assert capi.lib.plbm_lbm_pair_kernel(None) == -1
+    assert b"null grid handle" in capi.lib.plbm_last_error()
+
+
 def test_library_is_sm100a_only():
     from periodic_lbm_b200 import capi
 
