@@ -109,6 +109,15 @@ int plbm_set_pdf_to_equilibrium(plbm_handle grid, const void* rho, const void* u
  * reference steps (lattice `inew` = state nsteps-1, what the lagged update_macros reads):
  * batch the steps between two outputs into one call. */
 int plbm_perform_lbm_step(plbm_handle grid, int collision, int nsteps);
+/* Deferred stepping, for callers that keep the reference's call pattern of ONE step per call
+ * (app/main_taylor_green.f90:98-119: `call perform_lbm_step(grid)` in a do loop, update_macros every nprint
+ * steps).  With max_pending > 0, perform_lbm_step calls of fewer than max_pending steps are only counted; the
+ * steps run as one batched call -- two steps per pass over HBM -- when max_pending steps have accumulated, when
+ * the collision operator changes, or when ANY other entry point looks at or changes the grid (update_macros,
+ * download_f, diagnostics, set_properties, a changed set_omega, synchronize, ...).  Results, lattice roles and
+ * plbm_get_indices are those of eager stepping; only the moment the kernels are launched moves.  0 (default)
+ * = eager.  Not applied under a slab decomposition. */
+int plbm_set_step_deferral(plbm_handle grid, int max_pending);
 /* perform_step (src/fvm_bardow.F90:307-320) with streaming = stream_fvm_bardow, stream_fdm_bardow
  * or stream_fdm_sofonea (PLBM_STREAM_LBM forwards to plbm_perform_lbm_step). */
 int plbm_perform_step(plbm_handle grid, int streaming, int collision, int nsteps);

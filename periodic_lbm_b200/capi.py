@@ -56,6 +56,7 @@ SIGNATURES = {
     "plbm_synchronize": (_I, [_H]),
     "plbm_launch_count": (C.c_longlong, []),
     "plbm_set_variant": (_I, [_H, _I]),
+    "plbm_set_step_deferral": (_I, [_H, _I]),
     "plbm_lbm_pair_kernel": (_I, [_H]),
     "plbm_set_fdm_stencil": (_I, [_H, _I]),
     "plbm_comm_unique_id": (_I, [_P]),

@@ -22,7 +22,7 @@ int cuda_fail(cudaError_t e, const char* what)
 
 namespace {
 
-int check(plbm_handle g)
+int check_noflush(plbm_handle g)
 {
     if (!g) {
         set_error("null grid handle");
@@ -31,6 +31,18 @@ int check(plbm_handle g)
     cudaError_t e = cudaSetDevice(g->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     return PLBM_OK;
+}
+
+// Deferred stepping (plbm_set_step_deferral): perform_lbm_step calls are only counted; the steps run, batched into
+// one stepping call (two steps per pass over HBM), as soon as any other entry point looks at or changes the grid.
+int flush_deferred(Grid& g);
+
+// prologue of every entry point except the deferring ones: valid handle, its device current, no steps pending
+int check(plbm_handle g)
+{
+    int rc = check_noflush(g);
+    if (rc) return rc;
+    return flush_deferred(*g);
 }
 
 int need_props(plbm_handle g)
@@ -200,6 +212,28 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         swap_lattices(g);
     }
     return PLBM_OK;
+}
+
+int flush_deferred(Grid& g)
+{
+    if (g.deferred_steps == 0) return PLBM_OK;
+    const int n = g.deferred_steps, model = g.deferred_model;
+    g.deferred_steps = 0;
+    return g.prec == PLBM_F64 ? step_lbm_t<double>(g, model, n) : step_lbm_t<float>(g, model, n);
+}
+
+// perform_lbm_step behind the deferral: count the steps, run them when the budget is reached or the collision changes
+int lbm_steps_entry(Grid& g, int collision, int nsteps)
+{
+    int rc;
+    if (g.defer_max > 0 && !g.comm && nsteps > 0 && nsteps < g.defer_max) {
+        if (g.deferred_steps > 0 && g.deferred_model != collision && (rc = flush_deferred(g))) return rc;
+        g.deferred_model = collision;
+        g.deferred_steps += nsteps;
+        return g.deferred_steps >= g.defer_max ? flush_deferred(g) : PLBM_OK;
+    }
+    if ((rc = flush_deferred(g))) return rc;
+    return g.prec == PLBM_F64 ? step_lbm_t<double>(g, collision, nsteps) : step_lbm_t<float>(g, collision, nsteps);
 }
 
 // kernel mode of a finite-volume / finite-difference streaming scheme (plbm_fvm*.cu)
@@ -457,8 +491,10 @@ int plbm_get_indices(plbm_handle g, int* iold, int* inew, int* imid)
         set_error("null grid handle");
         return PLBM_ERR_ARG;
     }
-    if (iold) *iold = g->iold;
-    if (inew) *inew = g->inew;
+    // an odd number of deferred steps swaps the roles of the two lattices, like the steps themselves will
+    const bool odd = (g->deferred_steps & 1) != 0;
+    if (iold) *iold = odd ? g->inew : g->iold;
+    if (inew) *inew = odd ? g->iold : g->inew;
     if (imid) *imid = g->imid;
     return PLBM_OK;
 }
@@ -468,6 +504,10 @@ int plbm_set_properties(plbm_handle g, double nu, double dt, double magic, int h
     if (!g) {
         set_error("null grid handle");
         return PLBM_ERR_ARG;
+    }
+    if (g->deferred_steps > 0) {  // pending steps use the old relaxation rates
+        int rc = check(g);
+        if (rc) return rc;
     }
     if (!(dt > 0) || !(nu >= 0)) {
         set_error("set_properties: need dt > 0 and nu >= 0");
@@ -499,7 +539,12 @@ int plbm_set_omega(plbm_handle g, double omega)
         set_error("null grid handle");
         return PLBM_ERR_ARG;
     }
-    g->omega = g->prec == PLBM_F64 ? omega : (double)(float)omega;
+    const double w = g->prec == PLBM_F64 ? omega : (double)(float)omega;
+    if (w != g->omega && g->deferred_steps > 0) {  // pending steps use the old rate (the Fortran shim re-sends omega before every step)
+        int rc = check(g);
+        if (rc) return rc;
+    }
+    g->omega = w;
     return PLBM_OK;
 }
 
@@ -522,14 +567,26 @@ int plbm_set_pdf_to_equilibrium(plbm_handle g, const void* rho, const void* ux, 
 
 int plbm_perform_lbm_step(plbm_handle g, int collision, int nsteps)
 {
-    int rc = check(g);
+    int rc = check_noflush(g);
     if (rc) return rc;
     if ((rc = need_props(g))) return rc;
     if (!valid_model(collision) || nsteps < 0) {
         set_error("perform_lbm_step: bad collision id or nsteps");
         return PLBM_ERR_ARG;
     }
-    return DISPATCH(g, step_lbm_t<double>(*g, collision, nsteps), step_lbm_t<float>(*g, collision, nsteps));
+    return lbm_steps_entry(*g, collision, nsteps);
+}
+
+int plbm_set_step_deferral(plbm_handle g, int max_pending)
+{
+    int rc = check(g);  // runs what is pending under the old setting
+    if (rc) return rc;
+    if (max_pending < 0) {
+        set_error("set_step_deferral: max_pending must be >= 0");
+        return PLBM_ERR_ARG;
+    }
+    g->defer_max = max_pending;
+    return PLBM_OK;
 }
 
 int plbm_perform_step(plbm_handle g, int streaming, int collision, int nsteps)
@@ -838,6 +895,10 @@ int plbm_set_variant(plbm_handle g, int variant)
     if (!g) {
         set_error("null grid handle");
         return PLBM_ERR_ARG;
+    }
+    if (g->deferred_steps > 0) {
+        int rc = check(g);
+        if (rc) return rc;
     }
     g->variant = variant;
     return PLBM_OK;

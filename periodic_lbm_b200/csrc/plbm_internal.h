@@ -44,6 +44,9 @@ struct Grid {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int variant = 0;
+    // deferred stepping (plbm_set_step_deferral): perform_lbm_step calls of fewer than defer_max steps are only
+    // counted; they run as ONE batched call when defer_max is reached or any other entry point touches the grid
+    int defer_max = 0, deferred_steps = 0, deferred_model = -1;
     int fdm_stencil = 0;  // stream_fdm_bardow derivative stencil: 0 default, 1 WLS, 2/3 WLS-Gauss v1/v2, 4 isotropic
     int sm_count = 148;
     Comm* comm = nullptr;

@@ -86,6 +86,10 @@ contains
       grid%ux  => grid%mf(:,:,2)
       grid%uy  => grid%mf(:,:,3)
       call plbm_check(plbm_alloc_grid(grid%dev, int(nx,c_int), int(ny,c_int), int(nf_,c_int), plbm_precision), "alloc_grid")
+      ! the drivers call perform_lbm_step once per time step (app/main_taylor_green.f90:98-119): let the library
+      ! batch up to 64 of those calls into one launch sequence (two steps per pass over HBM); anything that
+      ! looks at the grid (update_macros, ...) runs the pending steps first, so the drivers see no difference
+      call plbm_check(plbm_set_step_deferral(grid%dev, 64_c_int), "set_step_deferral")
       call sync_indices(grid)
       log_ = .true.
       if (present(log)) log_ = log

@@ -49,6 +49,12 @@ module plbm_c
          real(c_double), intent(out) :: props(6)   ! nu, dt, tau, omega, trt_magic, csqr
          integer(c_int) :: stat
       end function
+      function plbm_set_step_deferral(grid, max_pending) bind(c, name="plbm_set_step_deferral") result(stat)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: grid
+         integer(c_int), value :: max_pending
+         integer(c_int) :: stat
+      end function
       function plbm_set_omega(grid, omega) bind(c, name="plbm_set_omega") result(stat)
          import :: c_ptr, c_int, c_double
          type(c_ptr), value :: grid

@@ -113,6 +113,11 @@ class LatticeGrid:
     def set_variant(self, variant):
         check(lib.plbm_set_variant(self._h, int(variant)), "set_variant")
 
+    def set_step_deferral(self, max_pending):
+        """Deferred stepping: single perform_lbm_step calls are counted and run batched (two steps per pass over
+        HBM) once `max_pending` have accumulated or anything else touches the grid; 0 = eager (default)."""
+        check(lib.plbm_set_step_deferral(self._h, int(max_pending)), "set_step_deferral")
+
     FDM_STENCILS = {"default": 0, "wls": 1, "wls_gauss_v1": 2, "wls_gauss_v2": 3, "iso": 4}
 
     def pair_kernel(self):

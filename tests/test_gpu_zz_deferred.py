@@ -1,0 +1,102 @@
+"""Deferred stepping (plbm_set_step_deferral): the reference drivers call perform_lbm_step ONCE per time step
+(app/main_taylor_green.f90:98-119); with deferral on, the library counts those calls and runs them batched -- two
+steps per pass over HBM -- when the budget is reached or anything else touches the grid.  Results, lattice roles
+and indices must be exactly those of eager stepping (which tests/test_gpu_parity.py pins to the oracle)."""
+import numpy as np
+import pytest
+
+from conftest import random_state
+from oracle.oracle import Oracle, OracleGrid
+
+pytestmark = pytest.mark.gpu
+
+
+def make(plbm, nx, ny, prec, f0, defer):
+    g = plbm.alloc_grid(nx, ny, precision=prec)
+    plbm.set_properties(g, 0.02, 1.0, 0.25)
+    g.upload_f(g.iold, f0)
+    g.upload_f(g.inew, np.zeros_like(f0))
+    g.set_variant(5)  # never the cluster kernel: single steps -> k_lbm, batches -> the two-step kernels
+    g.set_step_deferral(defer)
+    g.streaming = plbm.lbm_stream
+    return g
+
+
+def state(plbm, g):
+    io, inw = g.iold, g.inew  # reported BEFORE anything flushes: must already be the final roles
+    plbm.update_macros(g)
+    return (io, inw, g.iold, g.inew, g.download_f(g.iold), g.download_f(g.inew), g.rho.copy(), g.ux.copy(), g.uy.copy())
+
+
+def same(a, b):
+    return a[:4] == b[:4] and all(np.array_equal(x, y) for x, y in zip(a[4:], b[4:]))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("nx,ny,nsteps,defer", [(40, 516, 37, 16), (64, 64, 9, 64), (16, 132, 16, 16), (9, 4, 7, 4)])
+def test_deferred_single_steps_equal_eager_single_steps(plbm, nx, ny, nsteps, defer, prec):
+    o = Oracle(prec)
+    f0 = np.nan_to_num(random_state(o, nx, ny), nan=0.0)
+    for coll in (plbm.collide_bgk, plbm.collide_trt, plbm.collide_rr):
+        res, launches = [], []
+        for d in (0, defer):
+            g = make(plbm, nx, ny, prec, f0, d)
+            g.collision = coll
+            l0 = plbm.launch_count()
+            for _ in range(nsteps):
+                plbm.perform_lbm_step(g, 1)
+            res.append(state(plbm, g))
+            launches.append(plbm.launch_count() - l0)
+            plbm.dealloc_grid(g)
+        assert same(res[0], res[1])
+        assert res[0][0:2] == res[0][2:4] and res[1][0:2] == res[1][2:4]  # indices reported before == after the flush
+        if ny >= 8:
+            assert launches[1] < launches[0], launches  # batched: fewer launches than one per step
+
+
+def test_deferred_steps_match_the_oracle(plbm):
+    nx, ny, nsteps = 40, 516, 21
+    og = OracleGrid(nx, ny, "f64")
+    og.set_properties(0.02, 1.0, 0.25)
+    f0 = random_state(og.o, nx, ny)
+    og.lattice(og.iold)[...] = f0
+    og.lattice(og.inew)[...] = 0
+    og.run(Oracle.SCHEME_LBM, Oracle.TRT, nsteps)
+    g = make(plbm, nx, ny, "f64", np.nan_to_num(f0, nan=0.0), 8)
+    g.collision = plbm.collide_trt
+    for _ in range(nsteps):
+        plbm.perform_lbm_step(g, 1)
+    assert (g.iold, g.inew) == (og.iold, og.inew)
+    assert np.array_equal(g.download_f(g.iold)[:, :, :ny], og.lattice(og.iold)[:, :, :ny])
+    assert np.array_equal(g.download_f(g.inew)[:, :, :ny], og.lattice(og.inew)[:, :, :ny])
+    plbm.dealloc_grid(g)
+
+
+def test_changes_between_deferred_steps_take_effect_in_order(plbm):
+    """a new omega, a new collision operator, new properties and an explicit batch in the middle of a run"""
+    nx, ny = 24, 260
+    o = Oracle("f64")
+    f0 = np.nan_to_num(random_state(o, nx, ny), nan=0.0)
+    res = []
+    for d in (0, 32):
+        g = make(plbm, nx, ny, "f64", f0, d)
+        g.collision = plbm.collide_bgk
+        for _ in range(5):
+            plbm.perform_lbm_step(g, 1)
+        g.omega = 1.25                      # pending steps must run with the old rate
+        for _ in range(4):
+            plbm.perform_lbm_step(g, 1)
+        g.omega = 1.25                      # unchanged value (what the Fortran shim sends before every step): no flush needed
+        plbm.perform_lbm_step(g, 2)
+        g.collision = plbm.collide_rr       # operator switch
+        for _ in range(3):
+            plbm.perform_lbm_step(g, 1)
+        plbm.set_properties(g, 0.05, 1.0, 0.25)
+        plbm.perform_lbm_step(g, 1)
+        plbm.perform_lbm_step(g, 40)        # >= the budget: runs at once, after what was pending
+        plbm.perform_lbm_step(g, 1)
+        st = state(plbm, g)                 # update_macros is an observer: it sees all 57 steps
+        d0 = g.diagnostics()
+        res.append((st, d0["sum_rho"], d0["kinetic_energy"]))
+        plbm.dealloc_grid(g)
+    assert same(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
