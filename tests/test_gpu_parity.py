@@ -157,21 +157,6 @@ def test_two_step_kernel(plbm, nx, ny, prec):
             plbm.dealloc_grid(g)
 
 
-def test_pair_kernel_selection(plbm):
-    """plbm_lbm_pair_kernel: which kernel a call of >= 3 steps uses (bench accounting).  Large grids (>= 2 waves of
-    k_lbm2_bulk blocks) get the bulk-copy flavour, smaller ones k_lbm2; the variants force either."""
-    if os.environ.get("PLBM_PAIR_BULK", "") not in ("", "1"):
-        pytest.skip("PLBM_PAIR_BULK overrides the default selection")
-    for shape, prec, variant, want in (((64, 64), "f64", 0, "k_lbm2"), ((64, 64), "f64", 7, "k_lbm2_bulk"), ((64, 64), "f64", 6, "k_lbm2"),
-                                       ((64, 64), "f64", 1, "k_lbm"), ((64, 8), "f64", 7, "k_lbm2"), ((64, 16), "f32", 7, "k_lbm2"),
-                                       ((64, 67), "f64", 0, "k_lbm"), ((1024, 1024), "f64", 0, "k_lbm2"), ((4096, 4096), "f64", 0, "k_lbm2_bulk"),
-                                       ((4096, 4096), "f32", 0, "k_lbm2"), ((8192, 8192), "f32", 0, "k_lbm2_bulk")):
-        g = plbm.alloc_grid(*shape, precision=prec)
-        g.set_variant(variant)
-        assert g.pair_kernel() == want, (shape, prec, variant, g.pair_kernel())
-        plbm.dealloc_grid(g)
-
-
 @pytest.mark.skipif(os.environ.get("PLBM_TEST_EXPERIMENTAL", "0") == "0",
                     reason="experimental depth-generic multi-step kernel (csrc/plbm_lbmn.cu): set PLBM_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("prec", PRECS)

@@ -2,6 +2,8 @@
 (app/main_taylor_green.f90:98-119); with deferral on, the library counts those calls and runs them batched -- two
 steps per pass over HBM -- when the budget is reached or anything else touches the grid.  Results, lattice roles
 and indices must be exactly those of eager stepping (which tests/test_gpu_parity.py pins to the oracle)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -100,3 +102,18 @@ def test_changes_between_deferred_steps_take_effect_in_order(plbm):
         res.append((st, d0["sum_rho"], d0["kinetic_energy"]))
         plbm.dealloc_grid(g)
     assert same(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+
+
+def test_pair_kernel_selection(plbm):
+    """plbm_lbm_pair_kernel: which kernel a call of >= 3 steps uses (bench accounting).  Large grids (>= 2 waves of
+    k_lbm2_bulk blocks) get the bulk-copy flavour, smaller ones k_lbm2; the variants force either."""
+    if os.environ.get("PLBM_PAIR_BULK", "") not in ("", "1"):
+        pytest.skip("PLBM_PAIR_BULK overrides the default selection")
+    for shape, prec, variant, want in (((64, 64), "f64", 0, "k_lbm2"), ((64, 64), "f64", 7, "k_lbm2_bulk"), ((64, 64), "f64", 6, "k_lbm2"),
+                                       ((64, 64), "f64", 1, "k_lbm"), ((64, 8), "f64", 7, "k_lbm2"), ((64, 16), "f32", 7, "k_lbm2"),
+                                       ((64, 67), "f64", 0, "k_lbm"), ((1024, 1024), "f64", 0, "k_lbm2"), ((4096, 4096), "f64", 0, "k_lbm2_bulk"),
+                                       ((4096, 4096), "f32", 0, "k_lbm2"), ((8192, 8192), "f32", 0, "k_lbm2_bulk")):
+        g = plbm.alloc_grid(*shape, precision=prec)
+        g.set_variant(variant)
+        assert g.pair_kernel() == want, (shape, prec, variant, g.pair_kernel())
+        plbm.dealloc_grid(g)
