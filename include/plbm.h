@@ -181,7 +181,9 @@ long long plbm_launch_count(void);
  *                      by bulk async copies (k_lbm2_bulk); 8 = 7 issued as the three line ranges of the slab schedule;
  *                      9 / 10 = EXPERIMENTAL depth-generic kernel k_lbmn_bulk (bgk/trt/rr, one GPU): pairs / triples
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
- *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused */
+ *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused
+ *   both                   : 3 = EXPERIMENTAL the TMA-pipelined kernel compiled with FMA contraction (fewer fp64
+ *                            instructions; within 1e-12 / 1e-5 relative of the non-FMA result, NOT bit-identical; one GPU) */
 int plbm_set_variant(plbm_handle grid, int variant);
 /* which kernel perform_lbm_step(nsteps >= 3) advances this grid with: 0 = one step per launch (k_lbm),
  * 1 = two steps per launch, raw columns by per-thread loads (k_lbm2), 2 = two steps per launch, raw columns by

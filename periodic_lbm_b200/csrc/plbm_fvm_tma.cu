@@ -15,6 +15,13 @@
 #include "plbm_internal.h"
 #include "plbm_fv.cuh"
 
+// plbm_fvm_tma_fma.cu compiles this file a second time with -fmad=true (see there): the same kernels with their
+// multiply-adds contracted, exported as launch_fv_tma_fma.  The kernels live in an anonymous namespace and device
+// code is not linked across translation units, so the two builds do not meet.
+#ifdef PLBM_FMA_BUILD
+#define launch_fv_tma launch_fv_tma_fma
+#endif
+
 namespace plbm {
 
 namespace {
@@ -301,6 +308,7 @@ int launch_one(const Grid& g, int which_src, const T* fin, T* fout, T dt, T of, 
 
 }  // namespace
 
+#ifndef PLBM_FMA_BUILD
 int make_tensor_maps(Grid& g)
 {
     g.tmap_ok = false;
@@ -323,6 +331,7 @@ int make_tensor_maps(Grid& g)
     g.tmap_ok = true;
     return PLBM_OK;
 }
+#endif  // !PLBM_FMA_BUILD
 
 template <typename T>
 int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode, int model, T dt, T of, T oh, T oc,

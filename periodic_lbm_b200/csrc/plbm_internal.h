@@ -127,6 +127,10 @@ int make_tensor_maps(Grid& g);
 template <typename T>
 int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode, int model, T dt, T omega_full, T omega_half,
                   T omega_face, const CollideParams<T>& cp, cudaStream_t s);
+// the same kernels compiled with FMA contraction (plbm_fvm_tma_fma.cu): within tolerance, not bit-identical; variant 3
+template <typename T>
+int launch_fv_tma_fma(const Grid& g, int which_src, const T* fin, T* fout, int mode, int model, T dt, T omega_full, T omega_half,
+                      T omega_face, const CollideParams<T>& cp, cudaStream_t s);
 template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s);
 
 // multi-GPU ring exchange (plbm_comm.cu)

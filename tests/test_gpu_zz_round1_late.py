@@ -117,3 +117,41 @@ def test_pair_kernel_selection(plbm):
         g.set_variant(variant)
         assert g.pair_kernel() == want, (shape, prec, variant, g.pair_kernel())
         plbm.dealloc_grid(g)
+
+
+@pytest.mark.skipif(os.environ.get("PLBM_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="FMA-contracted tile kernels (csrc/plbm_fvm_tma_fma.cu, variant 3): set PLBM_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("prec,rtol", [("f64", 1e-12), ("f32", 1e-5)])
+@pytest.mark.parametrize("scheme", ["dugks", "fvm", "fdm_bardow"])
+def test_fma_contracted_tile_kernels_stay_within_the_stated_tolerance(plbm, scheme, prec, rtol):
+    """variant 3 = the TMA-pipelined tile kernels compiled with -fmad=true: NOT bit-identical, but within
+    BASELINE.json's tolerance (1e-12 relative fp64, 1e-5 fp32) of the oracle after N steps, PDFs and rho/u."""
+    nx = ny = 130
+    nsteps = 10
+    og = OracleGrid(nx, ny, prec)
+    og.set_properties(0.02, 0.3, 0.25)
+    f0 = random_state(og.o, nx, ny)
+    og.lattice(og.iold)[...] = f0
+    og.lattice(og.inew)[...] = 0
+    g = plbm.alloc_grid(nx, ny, precision=prec)
+    plbm.set_properties(g, 0.02, 0.3, 0.25)
+    g.upload_f(g.iold, np.nan_to_num(f0, nan=0.0))
+    g.upload_f(g.inew, np.zeros_like(f0))
+    g.set_variant(3)
+    if scheme == "dugks":
+        og.run(Oracle.SCHEME_DUGKS, Oracle.BGK, nsteps)
+        plbm.perform_dugks_step(g, nsteps)
+    else:
+        g.collision = plbm.collide_bgk
+        g.streaming = plbm.stream_fvm_bardow if scheme == "fvm" else plbm.stream_fdm_bardow
+        og.run(Oracle.SCHEME_FVM_BARDOW if scheme == "fvm" else Oracle.SCHEME_FDM_BARDOW, Oracle.BGK, nsteps)
+        plbm.perform_step(g, nsteps)
+    got = g.download_f(g.iold)[:, :, :ny].astype(np.float64)
+    want = og.lattice(og.iold)[:, :, :ny].astype(np.float64)
+    assert np.abs(got - want).max() <= rtol * np.abs(want).max()
+    plbm.update_macros(g, lagged=False)
+    r, u, v = og.update_macros(lagged=False)
+    assert np.abs(g.rho - r).max() <= rtol * np.abs(r).max()
+    assert np.abs(g.ux - u).max() <= rtol * max(np.abs(u).max(), np.abs(v).max())
+    assert np.abs(g.uy - v).max() <= rtol * max(np.abs(u).max(), np.abs(v).max())
+    plbm.dealloc_grid(g)

@@ -18,6 +18,10 @@ for sl in 32 128 256; do
 done
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:k_lbmn_bulk -c 1 -f -o $O/${R}_k_lbmn_bulk3_bgk_f64_8192 \
     python tools/pair_ab.py --cases 8192x8192:f64:bgk --variants 10 --once > /dev/null 2>&1; step ncu-full-lbmn3 $?
+timeout 120 env PLBM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_zz_round1_late.py -q -m gpu > $O/${R}_pytest_late.txt 2>&1; step late-tests $?
+for c in dugks,f64,bgk,0 dugks,f64,bgk,3 dugks,f32,bgk,0 dugks,f32,bgk,3 fvm,f64,bgk,0 fvm,f64,bgk,3; do
+    timeout 90 python tools/kbench.py --n 2048 --steps 50 --case $c >> $O/${R}_kbench_fma.jsonl 2>&1; step kbench-$c $?
+done
 timeout 400 python -m pytest tests -m gpu -q -x > $O/${R}_pytest_gpu.txt 2>&1; step pytest-gpu $?
 timeout 60 python __graft_entry__.py smoke > $O/${R}_smoke.txt 2>&1; step smoke $?
 cat $S
