@@ -179,7 +179,9 @@ long long plbm_launch_count(void);
  *                      5 = like 0 but never the cluster kernel (tests of the two-step kernel on small grids);
  *                      6 / 7 = like 5 with the two-step kernel's raw columns fetched by per-thread loads (k_lbm2) /
  *                      by bulk async copies (k_lbm2_bulk); 8 = 7 issued as the three line ranges of the slab schedule;
- *                      9 / 10 = EXPERIMENTAL depth-generic kernel k_lbmn_bulk (bgk/trt/rr, one GPU): pairs / triples
+ *                      9 / 10 = EXPERIMENTAL depth-generic kernel k_lbmn_bulk (bgk/trt/rr, one GPU): pairs / triples;
+ *                      11 = EXPERIMENTAL the two-step kernels compiled with FMA contraction (one GPU; within 1e-12 /
+ *                      1e-5 relative of the non-FMA result, NOT bit-identical)
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
  *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused
  *   both                   : 3 = EXPERIMENTAL the TMA-pipelined kernel compiled with FMA contraction (fewer fp64

@@ -190,6 +190,8 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
                 rc = launch_lbm_pair<T>(g, src, dst, 0, 2, nullptr, nullptr, model, cp, g.stream);
                 if (!rc) rc = launch_lbm_pair<T>(g, src, dst, g.nx - 2, g.nx, nullptr, nullptr, model, cp, g.stream);
                 if (!rc) rc = launch_lbm_pair<T>(g, src, dst, 2, g.nx - 2, nullptr, nullptr, model, cp, g.stream);
+            } else if (g.variant == 11) {
+                rc = launch_lbm_pair_fma<T>(g, src, dst, 0, g.nx, nullptr, nullptr, model, cp, g.stream);  // opt-in, FMA-contracted
             } else {
                 rc = launch_lbm_pair<T>(g, src, dst, 0, g.nx, nullptr, nullptr, model, cp, g.stream);
             }

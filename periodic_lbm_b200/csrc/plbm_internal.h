@@ -112,11 +112,15 @@ bool lbm_pair_applicable(const Grid& g);
 // variants of perform_lbm_step that advance two steps per launch: 0 default, 5 never the cluster kernel,
 // 6 per-thread loads forced, 7 bulk async copies forced, 8 = 7 issued as the slab schedule's three x ranges
 // (9 / 10: the experimental depth-generic kernel of plbm_lbmn.cu on one GPU, pairs / triples; like 5 otherwise)
-inline bool lbm_pair_variant(int variant) { return variant == 0 || (variant >= 5 && variant <= 10); }
+// (11: the default two-step kernels compiled with FMA contraction, plbm_lbm2_fma.cu, one GPU; like 5 otherwise)
+inline bool lbm_pair_variant(int variant) { return variant == 0 || (variant >= 5 && variant <= 11); }
 int lbm_pair_flavour(const Grid& g);  // 0 one step per launch, 1 k_lbm2, 2 k_lbm2_bulk
 template <typename T>
 int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
                     const CollideParams<T>& cp, cudaStream_t s);
+template <typename T>
+int launch_lbm_pair_fma(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
+                        const CollideParams<T>& cp, cudaStream_t s);  // plbm_lbm2_fma.cu: within tolerance, not bit-identical
 // EXPERIMENTAL: `nstep` (2 or 3) fused steps per pass over HBM, depth-generic form of k_lbm2_bulk (plbm_lbmn.cu)
 bool lbm_multi_applicable(const Grid& g, int model, int nstep);
 template <typename T>

@@ -46,6 +46,13 @@
 
 #include "plbm_internal.h"
 
+// plbm_lbm2_fma.cu compiles this file a second time with -fmad=true: the same kernels with their multiply-adds
+// contracted, exported as launch_lbm_pair_fma (opt-in variant 11, see that file).  The kernels live in an anonymous
+// namespace and device code is not linked across translation units, so the two builds do not meet.
+#ifdef PLBM_FMA_BUILD
+#define launch_lbm_pair launch_lbm_pair_fma
+#endif
+
 namespace plbm {
 
 namespace {
@@ -564,6 +571,7 @@ int dispatch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, c
 
 }  // namespace
 
+#ifndef PLBM_FMA_BUILD
 bool lbm_pair_applicable(const Grid& g)
 {
     const int v = 16 / (int)g.esize();
@@ -588,6 +596,8 @@ int lbm_pair_flavour(const Grid& g)
     const long long strips = (g.ny + 126 * v - 1) / (126 * v), segs = (g.nx + 63) / 64;
     return strips * segs >= 2LL * 3 * g.sm_count ? 2 : 1;
 }
+
+#endif  // !PLBM_FMA_BUILD
 
 // Two fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' two
 // nearest lines ([2][9][ld]) under a slab decomposition, nullptr = periodic self-wrap.  The caller

@@ -155,3 +155,33 @@ def test_fma_contracted_tile_kernels_stay_within_the_stated_tolerance(plbm, sche
     assert np.abs(g.ux - u).max() <= rtol * max(np.abs(u).max(), np.abs(v).max())
     assert np.abs(g.uy - v).max() <= rtol * max(np.abs(u).max(), np.abs(v).max())
     plbm.dealloc_grid(g)
+
+
+@pytest.mark.skipif(os.environ.get("PLBM_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="FMA-contracted two-step LBM kernels (csrc/plbm_lbm2_fma.cu, variant 11): set PLBM_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("prec,rtol", [("f64", 1e-12), ("f32", 1e-5)])
+@pytest.mark.parametrize("nx,ny", [(40, 516), (16, 24)])
+def test_fma_contracted_two_step_kernels_stay_within_the_stated_tolerance(plbm, nx, ny, prec, rtol):
+    """variant 11 = k_lbm2_bulk / k_lbm2 compiled with -fmad=true: within BASELINE.json's tolerance of the oracle
+    after N steps (PDFs and rho/u), not bit-identical."""
+    nsteps = 21
+    for coll, ocoll in ((plbm.collide_bgk, Oracle.BGK), (plbm.collide_trt, Oracle.TRT), (plbm.collide_rr, Oracle.RR)):
+        og = OracleGrid(nx, ny, prec)
+        og.set_properties(0.02, 1.0, 0.25)
+        f0 = random_state(og.o, nx, ny)
+        og.lattice(og.iold)[...] = f0
+        og.lattice(og.inew)[...] = 0
+        og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
+        g = make(plbm, nx, ny, prec, np.nan_to_num(f0, nan=0.0), 0)
+        g.set_variant(11)
+        g.collision = coll
+        plbm.perform_lbm_step(g, nsteps)
+        assert (g.iold, g.inew) == (og.iold, og.inew)
+        got = g.download_f(g.iold)[:, :, :ny].astype(np.float64)
+        want = og.lattice(og.iold)[:, :, :ny].astype(np.float64)
+        assert np.abs(got - want).max() <= rtol * np.abs(want).max()
+        plbm.update_macros(g, lagged=False)
+        r, u, v = og.update_macros(lagged=False)
+        assert np.abs(g.rho - r).max() <= rtol * np.abs(r).max()
+        assert np.abs(g.ux - u).max() <= rtol * max(np.abs(u).max(), np.abs(v).max())
+        plbm.dealloc_grid(g)

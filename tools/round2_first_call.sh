@@ -13,6 +13,7 @@ step() { echo "$1 rc=$2 elapsed=$(( $(date +%s) - T0 ))s" >> $S; }
 timeout 200 env PLBM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_parity.py -k "multi_step_kernel_experimental" -x -q -m gpu > $O/${R}_pytest_experimental.txt 2>&1; step experimental-parity $?
 timeout 200 python tools/pair_ab.py --cases 8192x8192:f64:bgk,8192x8192:f64:trt,8192x8192:f64:rr,8192x8192:f32:bgk,8192x8192:f32:rr,4096x32768:f64:bgk --variants 7,9,10 > $O/${R}_pair_ab.jsonl 2>&1; step ab $?
 timeout 100 env PLBM_MULTI_NT=256 python tools/pair_ab.py --cases 8192x8192:f64:bgk,8192x8192:f32:bgk,4096x32768:f64:bgk --variants 10 > $O/${R}_pair_ab_nt256.jsonl 2>&1; step ab-nt256 $?
+timeout 100 python tools/pair_ab.py --cases 8192x8192:f64:rr,8192x8192:f32:rr,8192x8192:f64:bgk --variants 0,11 > $O/${R}_pair_ab_fma.jsonl 2>&1; step ab-fma $?
 for sl in 32 128 256; do
     timeout 60 env PLBM_MULTI_SEGLEN=$sl python tools/pair_ab.py --cases 8192x8192:f64:bgk --variants 10 >> $O/${R}_pair_ab_seglen.jsonl 2>&1; step ab-seglen-$sl $?
 done
