@@ -97,7 +97,7 @@ def test_changes_between_deferred_steps_take_effect_in_order(plbm):
         plbm.perform_lbm_step(g, 1)
         plbm.perform_lbm_step(g, 40)        # >= the budget: runs at once, after what was pending
         plbm.perform_lbm_step(g, 1)
-        st = state(plbm, g)                 # update_macros is an observer: it sees all 57 steps
+        st = state(plbm, g)                 # update_macros is an observer: it sees all 56 steps
         d0 = g.diagnostics()
         res.append((st, d0["sum_rho"], d0["kinetic_energy"]))
         plbm.dealloc_grid(g)
