@@ -1,0 +1,192 @@
+"""A SECOND, independent restatement of the LBM path of the reference, in whole-array numpy (test infrastructure).
+
+The C oracle (oracle/plbm_oracle.c) is one reading of the Fortran; the reference ships no golden data for
+lbm_stream, collide_trt and collide_rr ("parity unpinned by the reference").  This module is a second
+reading, written separately from the Fortran text, statement by statement and in the Fortran's evaluation order
+(left to right within a precedence level, parentheses kept, every literal rounded to the working precision like
+`_wp`).  numpy's elementwise add / subtract / multiply / divide are correctly rounded IEEE operations and never
+fused, so two faithful readings must agree BIT FOR BIT -- tests/test_oracle_second_restatement.py checks exactly
+that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of the oracle's layout are ignored).
+
+  equilibrium            src/fvm_bardow.F90:99-126
+  update_macros_kernel   src/fvm_bardow.F90:358-386
+  lbm_stream_kernel      src/periodic_lbm.f90:45-127
+  bgk_kernel             src/collision_bgk.F90:35-82
+  trt_naive, lambda_d    src/collision_trt.F90:13-34, 64-160
+  rr_kernel_naive        src/collision_regularized.F90:11-14, 40-202
+"""
+import numpy as np
+
+CX = (0, 1, 0, -1, 0, 1, -1, -1, 1)  # src/fvm_bardow.F90:87-88
+CY = (0, 0, 1, 0, -1, 1, 1, -1, -1)
+
+
+def lbm_stream(f):
+    """fdst(y,x,q) = fsrc(y - cy_q, x - cx_q, q) with periodic neighbours (xm1, xp1, ym1, yp1 of the Fortran)."""
+    out = np.empty_like(f)
+    for q in range(9):
+        out[q] = np.roll(f[q], shift=(CX[q], CY[q]), axis=(0, 1))
+    return out
+
+
+def equilibrium(T, rho, ux, uy):
+    w0, ws, wd = T(4) / T(9), T(1) / T(9), T(1) / T(36)
+    uxx = ux * ux
+    uyy = uy * uy
+    indp = T(1) - T(1.5) * (uxx + uyy)
+    feq = [None] * 9
+    feq[0] = w0 * rho * indp
+    feq[1] = ws * rho * (indp + T(3) * ux + T(4.5) * uxx)
+    feq[2] = ws * rho * (indp + T(3) * uy + T(4.5) * uyy)
+    feq[3] = ws * rho * (indp - T(3) * ux + T(4.5) * uxx)
+    feq[4] = ws * rho * (indp - T(3) * uy + T(4.5) * uyy)
+    uxpy = ux + uy
+    feq[5] = wd * rho * (indp + T(3) * uxpy + T(4.5) * uxpy * uxpy)
+    feq[7] = wd * rho * (indp - T(3) * uxpy + T(4.5) * uxpy * uxpy)
+    uxmy = ux - uy
+    feq[6] = wd * rho * (indp - T(3) * uxmy + T(4.5) * uxmy * uxmy)
+    feq[8] = wd * rho * (indp + T(3) * uxmy + T(4.5) * uxmy * uxmy)
+    return feq
+
+
+def update_macros(f):
+    T = f.dtype.type
+    fs = f
+    rho = fs[0] + (((fs[5] + fs[7]) + (fs[6] + fs[8])) + ((fs[1] + fs[3]) + (fs[2] + fs[4])))
+    invrho = T(1) / rho
+    ux = invrho * (((fs[5] - fs[7]) + (fs[8] - fs[6])) + (fs[1] - fs[3]))
+    uy = invrho * (((fs[5] - fs[7]) + (fs[6] - fs[8])) + (fs[2] - fs[4]))
+    return rho, ux, uy
+
+
+def collide_bgk(f, omega):
+    T = f.dtype.type
+    omega = T(omega)
+    omegabar = T(1) - omega
+    fs = f
+    rho = (((fs[5] + fs[7]) + (fs[6] + fs[8])) + ((fs[1] + fs[3]) + (fs[2] + fs[4]))) + fs[0]
+    invrho = T(1) / rho
+    ux = invrho * (((fs[5] - fs[7]) + (fs[8] - fs[6])) + (fs[1] - fs[3]))
+    uy = invrho * (((fs[5] - fs[7]) + (fs[6] - fs[8])) + (fs[2] - fs[4]))
+    feq = equilibrium(T, rho, ux, uy)
+    return np.stack([omegabar * fs[q] + omega * feq[q] for q in range(9)])
+
+
+def lambda_d(T, omega, x):
+    omega, x = T(omega), T(x)
+    return (T(4) - T(2) * omega) / (T(4) * x * omega + T(2) - omega)
+
+
+def collide_trt(f, omega, magic):
+    T = f.dtype.type
+    t0 = T(4) / T(9)
+    t1x2 = (T(1) / T(9)) * T(2)
+    t2x2 = (T(1) / T(36)) * T(2)
+    inv2csq2 = T(1) / (T(2) * (T(1) / T(3)) * (T(1) / T(3)))
+    fac1 = t1x2 * inv2csq2
+    fac2 = t2x2 * inv2csq2
+    lam_e = T(omega)
+    lam_d = lambda_d(T, omega, magic)
+    les = T(0.5) * lam_e
+    lds = T(0.5) * lam_d
+    vC, vE, vN, vW, vS, vNE, vNW, vSW, vSE = (f[q] for q in range(9))
+    rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC
+    velX = ((vNE - vSW) + (vSE - vNW)) + (vE - vW)
+    velY = ((vNE - vSW) + (vNW - vSE)) + (vN - vS)
+    velX2 = velX * velX
+    velY2 = velY * velY
+    feq_common = rho - T(1.5) * (velX2 + velY2)
+    out = [None] * 9
+    out[0] = vC * (T(1) - lam_e) + lam_e * t0 * feq_common
+    velXPY = velX + velY
+    sym = les * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common)
+    asym = lds * (vNE - vSW - T(3) * t2x2 * velXPY)
+    out[5] = vNE - sym - asym
+    out[7] = vSW - sym + asym
+    velXMY = velX - velY
+    sym = les * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common)
+    asym = lds * (vSE - vNW - T(3) * t2x2 * velXMY)
+    out[8] = vSE - sym - asym
+    out[6] = vNW - sym + asym
+    sym = les * (vN + vS - fac1 * velY2 - t1x2 * feq_common)
+    asym = lds * (vN - vS - T(3) * t1x2 * velY)
+    out[2] = vN - sym - asym
+    out[4] = vS - sym + asym
+    sym = les * (vE + vW - fac1 * velX2 - t1x2 * feq_common)
+    asym = lds * (vE - vW - T(3) * t1x2 * velX)
+    out[1] = vE - sym - asym
+    out[3] = vW - sym + asym
+    return np.stack(out)
+
+
+def collide_rr(f, omega):
+    T = f.dtype.type
+    w0, ws, wd, csqr = T(4) / T(9), T(1) / T(9), T(1) / T(36), T(1) / T(3)
+    omega = T(omega)
+    omega_w0 = w0 * (T(1) - omega)
+    omega_ws = ws * (T(1) - omega)
+    omega_wd = wd * (T(1) - omega)
+    vC, vE, vN, vW, vS, vNE, vNW, vSW, vSE = (f[q] for q in range(9))
+    rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC
+    invrho = T(1) / rho
+    ux = invrho * (((vNE - vSW) + (vSE - vNW)) + (vE - vW))
+    uy = invrho * (((vNE - vSW) + (vNW - vSE)) + (vN - vS))
+    uxx = ux * ux
+    uyy = uy * uy
+    uxxy = uxx * uy
+    uyyx = uyy * ux
+    uxxyy = uxx * uyy
+    indp0 = T(1) - T(1.5) * (uxx + uyy)
+    indps = indp0 - T(4.5) * uxxyy
+    indpd = indp0 + T(9) * uxxyy
+    indp0 = indp0 + T(2.25) * uxxyy
+    feq = [None] * 9
+    feq[0] = w0 * rho * indp0
+    feq[1] = ws * rho * (indps + T(3) * ux + T(4.5) * (uxx - uyyx))
+    feq[3] = ws * rho * (indps - T(3) * ux + T(4.5) * (uxx + uyyx))
+    feq[2] = ws * rho * (indps + T(3) * uy + T(4.5) * (uyy - uxxy))
+    feq[4] = ws * rho * (indps - T(3) * uy + T(4.5) * (uyy + uxxy))
+    vC = vC - feq[0]
+    vE = vE - feq[1]
+    vN = vN - feq[2]
+    vW = vW - feq[3]
+    vS = vS - feq[4]
+    axx = csqr * (T(2) * (vE + vW) - (vN + vS) - vC)
+    ayy = csqr * (T(2) * (vN + vS) - (vE + vW) - vC)
+    u3p = uxxy + uyyx
+    uxpy = ux + uy
+    indp57 = indpd + T(4.5) * uxpy * uxpy
+    feq[5] = wd * rho * (indp57 + T(3) * uxpy + T(9) * u3p)
+    feq[7] = wd * rho * (indp57 - T(3) * uxpy - T(9) * u3p)
+    u3m = uxxy - uyyx
+    uxmy = ux - uy
+    indp68 = indpd + T(4.5) * uxmy * uxmy
+    feq[6] = wd * rho * (indp68 - T(3) * uxmy + T(9) * u3m)
+    feq[8] = wd * rho * (indp68 + T(3) * uxmy - T(9) * u3m)
+    vNE = vNE - feq[5]
+    vNW = vNW - feq[6]
+    vSW = vSW - feq[7]
+    vSE = vSE - feq[8]
+    tmp = T(2) * csqr * (vNE + vNW + vSW + vSE)
+    axx = axx + tmp
+    ayy = ayy + tmp
+    axy = (vNE + vSW) - (vNW + vSE)
+    axxy = T(2) * ux * axy + uy * axx
+    ayyx = T(2) * uy * axy + ux * ayy
+    axxyy = T(2) * (ux * ayyx + uy * axxy) - uxx * ayy - uyy * axx - T(4) * ux * uy * axy
+    indp0 = T(-1.5) * (axx + ayy)
+    indps = indp0 - T(4.5) * axxyy
+    indpd = T(9) * axxyy - T(2) * indp0
+    indp0 = indp0 + T(2.25) * axxyy
+    vC = indp0
+    vE = indps + T(4.5) * (axx - ayyx)
+    vW = indps + T(4.5) * (axx + ayyx)
+    vN = indps + T(4.5) * (ayy - axxy)
+    vS = indps + T(4.5) * (ayy + axxy)
+    vNE = indpd + T(9) * (axxy + ayyx + axy)
+    vSW = indpd - T(9) * (axxy + ayyx - axy)
+    vNW = indpd + T(9) * (axxy - ayyx - axy)
+    vSE = indpd - T(9) * (axxy - ayyx + axy)
+    out = [feq[0] + omega_w0 * vC, feq[1] + omega_ws * vE, feq[2] + omega_ws * vN, feq[3] + omega_ws * vW, feq[4] + omega_ws * vS,
+           feq[5] + omega_wd * vNE, feq[6] + omega_wd * vNW, feq[7] + omega_wd * vSW, feq[8] + omega_wd * vSE]
+    return np.stack(out)
