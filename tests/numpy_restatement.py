@@ -14,6 +14,7 @@ that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of 
   bgk_kernel             src/collision_bgk.F90:35-82
   trt_naive, lambda_d    src/collision_trt.F90:13-34, 64-160
   rr_kernel_naive        src/collision_regularized.F90:11-14, 40-202
+  vorticity_2nd / _4th   src/vorticity.f90:13-43, 46-87   (fields are u[x, y])
 """
 import numpy as np
 
@@ -190,3 +191,19 @@ def collide_rr(f, omega):
     out = [feq[0] + omega_w0 * vC, feq[1] + omega_ws * vE, feq[2] + omega_ws * vN, feq[3] + omega_ws * vW, feq[4] + omega_ws * vS,
            feq[5] + omega_wd * vNE, feq[6] + omega_wd * vNW, feq[7] + omega_wd * vSW, feq[8] + omega_wd * vSE]
     return np.stack(out)
+
+
+def vorticity_2nd(ux, uy):
+    T = ux.dtype.type
+    duydx = T(0.5) * (np.roll(uy, -1, axis=0) - np.roll(uy, 1, axis=0))  # uy(y,xp1) - uy(y,xm1)
+    duxdy = T(0.5) * (np.roll(ux, -1, axis=1) - np.roll(ux, 1, axis=1))  # ux(yp1,x) - ux(ym1,x)
+    return duydx - duxdy
+
+
+def vorticity_4th(ux, uy):
+    """as shipped: t1 = 1/12 weighs the +-1 neighbours and t2 = 2/3 the (m2 - p2) pair"""
+    T = ux.dtype.type
+    t1, t2 = T(1) / T(12), T(2) / T(3)
+    duydx = t1 * (np.roll(uy, -1, axis=0) - np.roll(uy, 1, axis=0)) + t2 * (np.roll(uy, 2, axis=0) - np.roll(uy, -2, axis=0))
+    duxdy = t1 * (np.roll(ux, -1, axis=1) - np.roll(ux, 1, axis=1)) + t2 * (np.roll(ux, 2, axis=1) - np.roll(ux, -2, axis=1))
+    return duydx - duxdy

@@ -76,3 +76,14 @@ def test_fifty_steps(prec, name):
         a, b = b, a
     assert np.array_equal(a[:, :, :ny], n)
     assert np.isfinite(n).all()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("nx,ny", SHAPES)
+def test_vorticity(prec, nx, ny):
+    o = Oracle(prec)
+    rng = np.random.default_rng(7)
+    ux = rng.standard_normal((nx, ny)).astype(o.dtype)
+    uy = rng.standard_normal((nx, ny)).astype(o.dtype)
+    assert np.array_equal(o.vorticity(ux, uy, order=2), nr.vorticity_2nd(ux, uy))
+    assert np.array_equal(o.vorticity(ux, uy, order=4), nr.vorticity_4th(ux, uy))
