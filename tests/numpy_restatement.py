@@ -15,6 +15,7 @@ that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of 
   trt_naive, lambda_d    src/collision_trt.F90:13-34, 64-160
   rr_kernel_naive        src/collision_regularized.F90:11-14, 40-202
   vorticity_2nd / _4th   src/vorticity.f90:13-43, 46-87   (fields are u[x, y])
+  sim/ seam (slbm)       sim/sim.F90:119-131, 148-199, 352-383, 404-505, 568-624   (DDF-shifted populations f[k, j, i])
 """
 import numpy as np
 
@@ -207,3 +208,60 @@ def vorticity_4th(ux, uy):
     duydx = t1 * (np.roll(uy, -1, axis=0) - np.roll(uy, 1, axis=0)) + t2 * (np.roll(uy, 2, axis=0) - np.roll(uy, -2, axis=0))
     duxdy = t1 * (np.roll(ux, -1, axis=1) - np.roll(ux, 1, axis=1)) + t2 * (np.roll(ux, 2, axis=1) - np.roll(ux, -2, axis=1))
     return duydx - duxdy
+
+
+# ---- the sim/ plugin seam (sim/sim_slbm.F90 over sim/sim.F90): populations are stored shifted by their weight -----
+def sim_equilibrium(rho, ux, uy):
+    """equilibrium() with ddf_shift = .true. (sim/sim.F90:352-383)"""
+    T = rho.dtype.type
+    w0, ws, wd = T(4) / T(9), T(1) / T(9), T(1) / T(36)
+    w = (w0, ws, ws, ws, ws, wd, wd, wd, wd)
+    rho0 = T(1)
+    uxx = ux * ux
+    uyy = uy * uy
+    uxpy = ux + uy
+    uxmy = ux - uy
+    indp = T(-1.5) * (uxx + uyy)
+    feq = [None] * 9
+    feq[0] = w0 * rho * indp
+    feq[1] = ws * rho * (indp + T(3) * ux + T(4.5) * uxx)
+    feq[2] = ws * rho * (indp + T(3) * uy + T(4.5) * uyy)
+    feq[3] = ws * rho * (indp - T(3) * ux + T(4.5) * uxx)
+    feq[4] = ws * rho * (indp - T(3) * uy + T(4.5) * uyy)
+    feq[5] = wd * rho * (indp + T(3) * uxpy + T(4.5) * uxpy * uxpy)
+    feq[7] = wd * rho * (indp - T(3) * uxpy + T(4.5) * uxpy * uxpy)
+    feq[6] = wd * rho * (indp - T(3) * uxmy + T(4.5) * uxmy * uxmy)
+    feq[8] = wd * rho * (indp + T(3) * uxmy + T(4.5) * uxmy * uxmy)
+    return [feq[k] + w[k] * (rho - rho0) for k in range(9)]
+
+
+def sim_eqinit(p, u, v):
+    """lbm_eqinit_fields (sim/sim.F90:181-199): rho = rho0 + p / csqr, f = equilibrium(rho, u, v); fields [j, i]"""
+    T = p.dtype.type
+    csqr = T(1) / T(3)
+    rho = T(1) + p / csqr
+    return np.stack(sim_equilibrium(rho, u, v))
+
+
+def sim_macros(f):
+    """lbm_macros (sim/sim.F90:148-179)"""
+    T = f.dtype.type
+    rho = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0]
+    rho = rho + T(1)
+    u = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) / rho
+    v = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) / rho
+    return rho, u, v
+
+
+def sim_step(f, omega):
+    """lbm_collide_and_stream_fused with push = .true. followed by lbm_periodic_bc_push (sim/sim.F90:404-505,
+    568-624): collide, scatter to (i + cx, j + cy), fold the halo ring back = a periodic shift of the interior."""
+    T = f.dtype.type
+    omega = T(omega)
+    rho, ux, uy = sim_macros(f)
+    feq = sim_equilibrium(rho, ux, uy)
+    out = np.empty_like(f)
+    for k in range(9):
+        post = omega * (feq[k] - f[k]) + f[k]
+        out[k] = np.roll(post, shift=(CY[k], CX[k]), axis=(0, 1))  # axes (j, i)
+    return out

@@ -87,3 +87,29 @@ def test_vorticity(prec, nx, ny):
     uy = rng.standard_normal((nx, ny)).astype(o.dtype)
     assert np.array_equal(o.vorticity(ux, uy, order=2), nr.vorticity_2nd(ux, uy))
     assert np.array_equal(o.vorticity(ux, uy, order=4), nr.vorticity_4th(ux, uy))
+
+
+def test_sim_plugin_seam():
+    """the DDF-shifted path behind c_slbm_* (sim/sim.F90): init, 25 collide + push-stream + halo-fold steps, macros"""
+    nx, ny, steps, omega = 48, 40, 25, 1.7
+    o = Oracle("f64")
+    rng = np.random.default_rng(11)
+    p = 1e-3 * rng.standard_normal((ny, nx))
+    u = 0.05 * rng.standard_normal((2, ny, nx))
+    f1 = np.zeros((9, ny + 2, nx + 2))
+    f2 = np.zeros_like(f1)
+    P = lambda a: a.ctypes.data  # noqa: E731
+    o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
+    n = nr.sim_eqinit(p, u[0], u[1])
+    assert np.array_equal(f1[:, 1:ny + 1, 1:nx + 1], n)
+    f2[...] = f1
+    for _ in range(steps):
+        o._sim_step(nx, ny, P(f1), P(f2), omega)
+        o._sim_bc(nx, ny, P(f2))
+        f1, f2 = f2, f1
+        n = nr.sim_step(n, omega)
+    assert np.array_equal(f1[:, 1:ny + 1, 1:nx + 1], n)
+    rho_w, u_w, v_w = np.zeros((ny, nx)), np.zeros((ny, nx)), np.zeros((ny, nx))
+    o._sim_macros(nx, ny, P(f1), P(rho_w), P(u_w), P(v_w))
+    r, a, b = nr.sim_macros(n)
+    assert np.array_equal(rho_w, r) and np.array_equal(u_w, a) and np.array_equal(v_w, b)
