@@ -15,6 +15,9 @@ that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of 
   trt_naive, lambda_d    src/collision_trt.F90:13-34, 64-160
   rr_kernel_naive        src/collision_regularized.F90:11-14, 40-202
   vorticity_2nd / _4th   src/vorticity.f90:13-43, 46-87   (fields are u[x, y])
+  fvm_bardow_kernel      src/fvm_bardow.F90:410-507   (square grids: the shipped loop bounds are swapped)
+  periodic_dugks         src/periodic_dugks.F90:25-77 (step, dugks_collide), 80-169 (kernel_bgk), 172-304 (kernel_stream),
+                         310-434 (update_ew / update_ns); built with -DDUGKS
   sim/ seam (slbm)       sim/sim.F90:119-131, 148-199, 352-383, 404-505, 568-624   (DDF-shifted populations f[k, j, i])
 """
 import numpy as np
@@ -265,3 +268,104 @@ def sim_step(f, omega):
         post = omega * (feq[k] - f[k]) + f[k]
         out[k] = np.roll(post, shift=(CY[k], CX[k]), axis=(0, 1))  # axes (j, i)
     return out
+
+
+def stream_fvm_bardow(f, dt):
+    """fvm_bardow_kernel: bilinear face values from the 3 x 3 neighbourhood, conservative update; f[q, x, y]"""
+    T = f.dtype.type
+    dt = T(dt)
+    p2, p8 = T(0.5), T(0.125)
+    out = np.empty_like(f)
+    out[0] = f[0]
+    sh = lambda a, dx, dy: np.roll(a, shift=(-dx, -dy), axis=(0, 1))  # noqa: E731  value at (x + dx, y + dy)
+    for q in range(1, 9):
+        cxq = dt * T(CX[q])
+        cyq = dt * T(CY[q])
+        fc = f[q]
+        fe, fn, fw, fs = sh(fc, 1, 0), sh(fc, 0, 1), sh(fc, -1, 0), sh(fc, 0, -1)
+        fne, fnw, fsw, fse = sh(fc, 1, 1), sh(fc, -1, 1), sh(fc, -1, -1), sh(fc, 1, -1)
+        cfw = p2 * (fc + fw) - p2 * cxq * (fc - fw) - p8 * cyq * (fnw + fn - fsw - fs)
+        cfn = p2 * (fc + fn) - p2 * cyq * (fn - fc) - p8 * cxq * (fne + fe - fnw - fw)
+        cfe = p2 * (fc + fe) - p2 * cxq * (fe - fc) - p8 * cyq * (fne + fn - fse - fs)
+        cfs = p2 * (fc + fs) - p2 * cyq * (fc - fs) - p8 * cxq * (fse + fe - fsw - fw)
+        out[q] = fc - cxq * (cfe - cfw) - cyq * (cfn - cfs)
+    return out
+
+
+# ---- DUGKS (src/periodic_dugks.F90, -DDUGKS) ----------------------------------------------------------------------
+def _dugks_moments(f):
+    T = f[0].dtype.type
+    rho = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0]
+    invrho = T(1) / rho
+    ux = invrho * (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3]))
+    uy = invrho * (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4]))
+    indp = T(1) / T(3) - T(0.5) * (ux * ux + uy * uy)
+    return rho, ux, uy, indp
+
+
+def _dugks_relax(f, omega, which):
+    """kernel_bgk (which = 'all'), update_ew ('ew': populations with cx != 0), update_ns ('ns': cy != 0); f is a list of 9"""
+    T = f[0].dtype.type
+    omega = T(omega)
+    w0, ws, wd = T(4) / T(9), T(1) / T(9), T(1) / T(36)
+    omegabar = T(1) - omega
+    omega_w0 = T(3) * omega * w0
+    omega_ws = T(3) * omega * ws
+    omega_wd = T(3) * omega * wd
+    rho, ux, uy, indp = _dugks_moments(f)
+    g = list(f)
+    if which == "all":
+        g[0] = omegabar * f[0] + omega_w0 * rho * indp
+    if which in ("all", "ew"):
+        t13 = indp + T(1.5) * ux * ux
+        g[1] = omegabar * f[1] + omega_ws * rho * (t13 + ux)
+        g[3] = omegabar * f[3] + omega_ws * rho * (t13 - ux)
+    if which in ("all", "ns"):
+        t24 = indp + T(1.5) * uy * uy
+        g[2] = omegabar * f[2] + omega_ws * rho * (t24 + uy)
+        g[4] = omegabar * f[4] + omega_ws * rho * (t24 - uy)
+    velxpy = ux + uy
+    t57 = indp + T(1.5) * velxpy * velxpy
+    g[5] = omegabar * f[5] + omega_wd * rho * (t57 + velxpy)
+    g[7] = omegabar * f[7] + omega_wd * rho * (t57 - velxpy)
+    velxmy = ux - uy
+    t68 = indp + T(1.5) * velxmy * velxmy
+    g[6] = omegabar * f[6] + omega_wd * rho * (t68 - velxmy)
+    g[8] = omegabar * f[8] + omega_wd * rho * (t68 + velxmy)
+    return g
+
+
+def dugks_step(ftilde, grid_omega, tau, dt):
+    """perform_dugks_step: dugks_collide, dugks_stream (the swap is the caller's).  Returns (ftilde_new, fbar_plus):
+    what the reference leaves in lattice `inew` / `iold` BEFORE the swap, i.e. `iold` / `inew` after it."""
+    T = ftilde.dtype.type
+    tau, dt = T(tau), T(dt)
+    tau_d = tau / dt
+    omega = T(1) / (tau_d + T(0.5))
+    fnew = _dugks_relax([ftilde[q] for q in range(9)], grid_omega, "all")     # ftilde^+ (full step, grid%omega)
+    omega = T(0.75) * omega
+    fold = _dugks_relax([ftilde[q] for q in range(9)], omega, "all")          # fbar^+ (half step)
+    omega_f = T(1) / (T(4) * tau_d + T(1))
+    p2, p8 = T(0.5), T(0.125)
+    sh = lambda a, dx, dy: np.roll(a, shift=(-dx, -dy), axis=(0, 1))  # noqa: E731  value at (x + dx, y + dy)
+    cfw, cfn, cfe, cfs = [None] * 9, [None] * 9, [None] * 9, [None] * 9
+    for q in range(9):
+        cxq = dt * T(CX[q])
+        cyq = dt * T(CY[q])
+        fc = fold[q]
+        fe, fn, fw, fs = sh(fc, 1, 0), sh(fc, 0, 1), sh(fc, -1, 0), sh(fc, 0, -1)
+        fne, fnw, fsw, fse = sh(fc, 1, 1), sh(fc, -1, 1), sh(fc, -1, -1), sh(fc, 1, -1)
+        cfw[q] = p2 * (fc + fw) - p2 * cxq * (fc - fw) - p8 * cyq * (fnw + fn - fsw - fs)
+        cfn[q] = p2 * (fc + fn) - p2 * cyq * (fn - fc) - p8 * cxq * (fne + fe - fnw - fw)
+        cfe[q] = p2 * (fc + fe) - p2 * cxq * (fe - fc) - p8 * cyq * (fne + fn - fse - fs)
+        cfs[q] = p2 * (fc + fs) - p2 * cyq * (fc - fs) - p8 * cxq * (fse + fe - fsw - fw)
+    cfw = _dugks_relax(cfw, omega_f, "ew")
+    cfe = _dugks_relax(cfe, omega_f, "ew")
+    cfn = _dugks_relax(cfn, omega_f, "ns")
+    cfs = _dugks_relax(cfs, omega_f, "ns")
+    out = [fnew[0]]
+    for q in range(1, 9):
+        cxq = dt * T(CX[q])
+        cyq = dt * T(CY[q])
+        out.append(fnew[q] - cxq * (cfe[q] - cfw[q]) - cyq * (cfn[q] - cfs[q]))
+    return np.stack(out), np.stack(fold)

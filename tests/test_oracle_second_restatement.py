@@ -113,3 +113,41 @@ def test_sim_plugin_seam():
     o._sim_macros(nx, ny, P(f1), P(rho_w), P(u_w), P(v_w))
     r, a, b = nr.sim_macros(n)
     assert np.array_equal(rho_w, r) and np.array_equal(u_w, a) and np.array_equal(v_w, b)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [64, 5, 37])
+def test_bardow_fvm_with_bgk(prec, n):
+    """perform_step with stream_fvm_bardow + collide_bgk (what app/main_vortex.f90 runs), 20 steps, dt = 0.3"""
+    o = Oracle(prec)
+    p = o.set_properties(0.02, 0.3, 0.25)
+    f = random_state(o, n, n)
+    a, b = f.copy(), o.alloc_f(n, n)
+    m = f[:, :, :n].copy()
+    for _ in range(20):
+        o.stream_fvm_bardow(a, b, n, p["dt"])
+        o.collide_bgk(b, n, p["omega"])
+        m = nr.collide_bgk(nr.stream_fvm_bardow(m, p["dt"]), p["omega"])
+        a, b = b, a
+    assert np.array_equal(a[:, :, :n], m)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n,ratio", [(64, 5.0), (5, 1.0), (37, 10.0)])
+def test_dugks(prec, n, ratio):
+    """perform_dugks_step (-DDUGKS) x 20 on an n x n grid with dt = ratio * tau: both lattices, bit for bit"""
+    o = Oracle(prec)
+    T = o.dtype
+    nu = T(0.004)
+    tau = T(3) * nu
+    p = o.set_properties(nu, T(ratio) * tau, 0.25)
+    f = random_state(o, n, n)
+    a, b = f.copy(), o.alloc_f(n, n)  # a = iold (ftilde), b = inew
+    m = f[:, :, :n].copy()
+    for _ in range(20):
+        o.dugks_collide(a, b, n, p["omega"], p["tau"], p["dt"], True)
+        o.dugks_stream(a, b, n, p["tau"], p["dt"], True)
+        a, b = b, a  # swap: iold = the new ftilde, inew = fbar+
+        m, fbar = nr.dugks_step(m, p["omega"], p["tau"], p["dt"])
+        assert np.array_equal(a[:, :, :n], m)
+        assert np.array_equal(b[:, :, :n], fbar)
