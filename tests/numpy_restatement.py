@@ -8,7 +8,8 @@ reading, written separately from the Fortran text, statement by statement and in
 fused, so two faithful readings must agree BIT FOR BIT -- tests/test_oracle_second_restatement.py checks exactly
 that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of the oracle's layout are ignored).
 
-  equilibrium            src/fvm_bardow.F90:99-126
+  set_properties         src/fvm_bardow.F90:242-269
+  equilibrium            src/fvm_bardow.F90:99-126   (set_pdf_to_equilibrium :272-305 applies it node by node)
   update_macros_kernel   src/fvm_bardow.F90:358-386
   lbm_stream_kernel      src/periodic_lbm.f90:45-127
   bgk_kernel             src/collision_bgk.F90:35-82
@@ -24,6 +25,16 @@ import numpy as np
 
 CX = (0, 1, 0, -1, 0, 1, -1, -1, 1)  # src/fvm_bardow.F90:87-88
 CY = (0, 0, 1, 0, -1, 1, 1, -1, -1)
+
+
+def set_properties(T, nu, dt, magic=None):
+    nu, dt = T(nu), T(dt)
+    csqr = T(1) / T(3)
+    invcsqr = T(1) / csqr
+    tau = invcsqr * nu
+    omega = dt / (tau + T(0.5) * dt)
+    trt_magic = T(magic) if magic is not None else (tau / dt) ** 2
+    return dict(tau=tau, omega=omega, trt_magic=trt_magic, csqr=csqr)
 
 
 def lbm_stream(f):

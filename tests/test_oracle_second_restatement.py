@@ -151,3 +151,20 @@ def test_dugks(prec, n, ratio):
         m, fbar = nr.dugks_step(m, p["omega"], p["tau"], p["dt"])
         assert np.array_equal(a[:, :, :n], m)
         assert np.array_equal(b[:, :, :n], fbar)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_properties_and_equilibrium_init(prec):
+    o = Oracle(prec)
+    T = o.dtype
+    for nu, dt, magic in [(0.02, 1.0, 0.25), (0.0036950, 0.05542, None), (1.8919, 1.0, 0.25), (0.47297, 1.0, None)]:
+        a, b = o.set_properties(nu, dt, magic), nr.set_properties(T, nu, dt, magic)
+        assert all(a[k] == b[k] and type(b[k]) is T for k in ("tau", "omega", "trt_magic", "csqr")), (a, b)
+    rng = np.random.default_rng(3)
+    nx, ny = 19, 23
+    rho = (0.9 + 0.2 * rng.random((nx, ny))).astype(T)
+    ux = (0.1 * (rng.random((nx, ny)) - 0.5)).astype(T)
+    uy = (0.1 * (rng.random((nx, ny)) - 0.5)).astype(T)
+    f = o.alloc_f(nx, ny)
+    o.set_pdf_to_equilibrium(rho, ux, uy, f)
+    assert np.array_equal(f[:, :, :ny], np.stack(nr.equilibrium(T, rho, ux, uy)))
