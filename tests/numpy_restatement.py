@@ -33,7 +33,7 @@ def set_properties(T, nu, dt, magic=None):
     invcsqr = T(1) / csqr
     tau = invcsqr * nu
     omega = dt / (tau + T(0.5) * dt)
-    trt_magic = T(magic) if magic is not None else (tau / dt) ** 2
+    trt_magic = T(magic) if magic is not None else (tau / dt) * (tau / dt)  # (tau/dt)**2: gfortran emits x*x
     return dict(tau=tau, omega=omega, trt_magic=trt_magic, csqr=csqr)
 
 
