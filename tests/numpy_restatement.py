@@ -17,6 +17,8 @@ that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of 
   rr_kernel_naive        src/collision_regularized.F90:11-14, 40-202
   vorticity_2nd / _4th   src/vorticity.f90:13-43, 46-87   (fields are u[x, y])
   fvm_bardow_kernel      src/fvm_bardow.F90:410-507   (square grids: the shipped loop bounds are swapped)
+  fdm_bardow_kernel      src/fvm_bardow.F90:526-682   (default build and -DFDM_WLS / _GAUSS_V1 / _GAUSS_V2 / -DFDM_ISO)
+  fdm_sofonea_kernel     src/fvm_bardow.F90:702-880
   periodic_dugks         src/periodic_dugks.F90:25-77 (step, dugks_collide), 80-169 (kernel_bgk), 172-304 (kernel_stream),
                          310-434 (update_ew / update_ns); built with -DDUGKS
   sim/ seam (slbm)       sim/sim.F90:119-131, 148-199, 352-383, 404-505, 568-624   (DDF-shifted populations f[k, j, i])
@@ -380,3 +382,84 @@ def dugks_step(ftilde, grid_omega, tau, dt):
         cyq = dt * T(CY[q])
         out.append(fnew[q] - cxq * (cfe[q] - cfw[q]) - cyq * (cfn[q] - cfs[q]))
     return np.stack(out), np.stack(fold)
+
+
+def _neighbours(fc):
+    sh = lambda a, dx, dy: np.roll(a, shift=(-dx, -dy), axis=(0, 1))  # noqa: E731  value at (x + dx, y + dy)
+    return (sh(fc, 1, 0), sh(fc, 0, 1), sh(fc, -1, 0), sh(fc, 0, -1), sh(fc, 1, 1), sh(fc, -1, 1), sh(fc, -1, -1), sh(fc, 1, -1))
+
+
+def stream_fdm_bardow(f, dt, stencil="default"):
+    """fdm_bardow_kernel: second-order Taylor (Lax-Wendroff) streaming; `stencil` = the cpp macro of the build"""
+    T = f.dtype.type
+    dt = T(dt)
+    p2 = T(0.5)
+    two_thirds, one_sixth = T(2) / T(3), T(1) / T(6)
+    five_sixths, one_twelth = T(10) / T(12), T(1) / T(12)
+    one_third = T(1) / T(3)
+    out = np.empty_like(f)
+    out[0] = f[0]
+    for q in range(1, 9):
+        cxq = dt * T(CX[q])
+        cyq = dt * T(CY[q])
+        cxxq = T(0.5) * cxq * cxq
+        cyyq = T(0.5) * cyq * cyq
+        cxyq = cxq * cyq
+        fc = f[q]
+        fe, fn, fw, fs, fne, fnw, fsw, fse = _neighbours(fc)
+        if stencil == "wls":
+            dfx = one_sixth * ((fne - fnw) + (fe - fw) + (fse - fsw))
+            dfy = one_sixth * ((fne - fse) + (fn - fs) + (fnw - fsw))
+            dfxx = one_third * (fne - T(2) * fn + fnw) + one_third * (fe - T(2) * fc + fw) + one_third * (fse - T(2) * fs + fsw)
+            dfyy = one_third * (fne - T(2) * fe + fse) + one_third * (fn - T(2) * fc + fs) + one_third * (fnw - T(2) * fw + fsw)
+            dfxy = T(0.25) * (fne - fnw + fsw - fse)
+        elif stencil in ("wls_gauss_v1", "wls_gauss_v2"):
+            if stencil == "wls_gauss_v1":
+                p1s, p1d = T(0.2880584423829145035434), T(0.1059707788085427065949)
+                p2c, p2d1 = T(-1.152233769531658458263), T(0.5761168847658292291314)
+                p2d2, p2d = T(-0.4238831152341712149578), T(0.2119415576170855242122)
+            else:
+                p1s, p1d = T(0.3934930210807994210853), T(0.05325348945960039354075)
+                p2c, p2d1 = T(-1.573972084323197018207), T(0.7869860421615988421706)
+                p2d2, p2d = T(-0.2130139578384016019186), T(0.1065069789192007732037)
+            dfx = p1s * (fe - fw) + p1d * (fne - fnw) + p1d * (fse - fsw)
+            dfy = p1s * (fn - fs) + p1d * (fne - fse) + p1d * (fnw - fsw)
+            dfxx = p2c * fc + p2d1 * (fe + fw) + p2d2 * (fn + fs) + p2d * (fne + fnw + fsw + fse)
+            dfyy = p2c * fc + p2d2 * (fe + fw) + p2d1 * (fn + fs) + p2d * (fne + fnw + fsw + fse)
+            dfxy = T(0.25) * (fne - fnw + fsw - fse)
+        elif stencil == "iso":
+            dfx = p2 * (one_sixth * (fne - fnw) + two_thirds * (fe - fw) + one_sixth * (fse - fsw))
+            dfy = p2 * (one_sixth * (fne - fse) + two_thirds * (fn - fs) + one_sixth * (fnw - fsw))
+            dfxx = one_twelth * (fne - T(2) * fn + fnw) + five_sixths * (fe - T(2) * fc + fw) + one_twelth * (fse - T(2) * fs + fsw)
+            dfyy = one_twelth * (fne - T(2) * fe + fse) + five_sixths * (fn - T(2) * fc + fs) + one_twelth * (fnw - T(2) * fw + fsw)
+            dfxy = T(0.25) * (fne - fse - fnw + fsw)
+        else:
+            dfx = p2 * (fe - fw)
+            dfy = p2 * (fn - fs)
+            dfxx = fe - T(2) * fc + fw
+            dfyy = fn - T(2) * fc + fs
+            dfxy = T(0.25) * (fne - fse - fnw + fsw)
+        out[q] = fc - cxq * dfx - cyq * dfy + (cxxq * dfxx + cxyq * dfxy + cyyq * dfyy)
+    return out
+
+
+def stream_fdm_sofonea(f, dt):
+    """fdm_sofonea_kernel: one-dimensional Lax-Wendroff along each lattice direction (square grids)"""
+    T = f.dtype.type
+    dt = T(dt)
+    p2 = T(0.5) / np.sqrt(T(2))
+    sh = lambda a, dx, dy: np.roll(a, shift=(-dx, -dy), axis=(0, 1))  # noqa: E731
+    out = np.empty_like(f)
+    out[0] = f[0]
+    for q in range(1, 9):
+        fc = f[q]
+        fu = sh(fc, CX[q], CY[q])
+        fd = sh(fc, -CX[q], -CY[q])
+        if q <= 4:
+            du1 = T(0.5) * (fu - fd)
+            du2 = fu - T(2) * fc + fd
+        else:
+            du1 = p2 * (fu - fd)
+            du2 = T(0.5) * (fu - T(2) * fc + fd)
+        out[q] = fc + dt * (T(0.5) * dt * du2 - du1)
+    return out

@@ -168,3 +168,26 @@ def test_properties_and_equilibrium_init(prec):
     f = o.alloc_f(nx, ny)
     o.set_pdf_to_equilibrium(rho, ux, uy, f)
     assert np.array_equal(f[:, :, :ny], np.stack(nr.equilibrium(T, rho, ux, uy)))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("stencil", ["default", "wls", "wls_gauss_v1", "wls_gauss_v2", "iso", "sofonea"])
+def test_fdm_streaming_schemes(prec, stencil):
+    """stream_fdm_bardow (every cpp build) and stream_fdm_sofonea fused with collide_trt, 10 steps, dt = 0.3"""
+    n = 29
+    o = Oracle(prec)
+    p = o.set_properties(0.02, 0.3, 0.25)
+    f = random_state(o, n, n)
+    a, b = f.copy(), o.alloc_f(n, n)
+    m = f[:, :, :n].copy()
+    for _ in range(10):
+        if stencil == "sofonea":
+            o.stream_fdm_sofonea(a, b, n, p["dt"])
+            m = nr.stream_fdm_sofonea(m, p["dt"])
+        else:
+            o.stream_fdm_bardow(a, b, n, p["dt"], Oracle.FDM_STENCILS[stencil])
+            m = nr.stream_fdm_bardow(m, p["dt"], stencil)
+        o.collide_trt(b, n, p["omega"], p["trt_magic"])
+        m = nr.collide_trt(m, p["omega"], p["trt_magic"])
+        a, b = b, a
+    assert np.array_equal(a[:, :, :n], m), np.abs(a[:, :, :n] - m).max()
