@@ -15,6 +15,9 @@ that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of 
   bgk_kernel             src/collision_bgk.F90:35-82
   trt_naive, lambda_d    src/collision_trt.F90:13-34, 64-160
   rr_kernel_naive        src/collision_regularized.F90:11-14, 40-202
+  bgk_kernel_cache       src/collision_bgk.F90:84-176 (-DSPLIT; same text as periodic_dugks' kernel_bgk)
+  trt_split              src/collision_trt.F90:162-290 (-DSPLIT)
+  bgk_improved_kernel    src/collision_bgk_improved.f90:21-107
   vorticity_2nd / _4th   src/vorticity.f90:13-43, 46-87   (fields are u[x, y])
   fvm_bardow_kernel      src/fvm_bardow.F90:410-507   (square grids: the shipped loop bounds are swapped)
   fdm_bardow_kernel      src/fvm_bardow.F90:526-682   (default build and -DFDM_WLS / _GAUSS_V1 / _GAUSS_V2 / -DFDM_ISO)
@@ -463,3 +466,85 @@ def stream_fdm_sofonea(f, dt):
             du2 = T(0.5) * (fu - T(2) * fc + fd)
         out[q] = fc + dt * (T(0.5) * dt * du2 - du1)
     return out
+
+
+def collide_bgk_split(f, omega):
+    """bgk_kernel_cache (-DSPLIT): the re-associated BGK form, identical in text to periodic_dugks' kernel_bgk"""
+    return np.stack(_dugks_relax([f[q] for q in range(9)], omega, "all"))
+
+
+def collide_trt_split(f, omega, magic):
+    """trt_split (-DSPLIT): like trt_naive but fac1 * vel * vel is evaluated left to right (no vel2 temporaries)"""
+    T = f.dtype.type
+    t0 = T(4) / T(9)
+    t1x2 = (T(1) / T(9)) * T(2)
+    t2x2 = (T(1) / T(36)) * T(2)
+    inv2csq2 = T(1) / (T(2) * (T(1) / T(3)) * (T(1) / T(3)))
+    fac1 = t1x2 * inv2csq2
+    fac2 = t2x2 * inv2csq2
+    lam_e = T(omega)
+    lam_d = lambda_d(T, omega, magic)
+    les = T(0.5) * lam_e
+    lds = T(0.5) * lam_d
+    vC, vE, vN, vW, vS, vNE, vNW, vSW, vSE = (f[q] for q in range(9))
+    rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC
+    velX = ((vNE - vSW) + (vSE - vNW)) + (vE - vW)
+    velY = ((vNE - vSW) + (vNW - vSE)) + (vN - vS)
+    feq_common = rho - T(1.5) * (velX * velX + velY * velY)
+    out = [None] * 9
+    out[0] = vC * (T(1) - lam_e) + lam_e * t0 * feq_common
+    velXPY = velX + velY
+    sym = les * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common)
+    asym = lds * (vNE - vSW - T(3) * t2x2 * velXPY)
+    out[5] = vNE - sym - asym
+    out[7] = vSW - sym + asym
+    velXMY = velX - velY
+    sym = les * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common)
+    asym = lds * (vSE - vNW - T(3) * t2x2 * velXMY)
+    out[8] = vSE - sym - asym
+    out[6] = vNW - sym + asym
+    sym = les * (vN + vS - fac1 * velY * velY - t1x2 * feq_common)
+    asym = lds * (vN - vS - T(3) * t1x2 * velY)
+    out[2] = vN - sym - asym
+    out[4] = vS - sym + asym
+    sym = les * (vE + vW - fac1 * velX * velX - t1x2 * feq_common)
+    asym = lds * (vE - vW - T(3) * t1x2 * velX)
+    out[1] = vE - sym - asym
+    out[3] = vW - sym + asym
+    return np.stack(out)
+
+
+def collide_bgk_improved(f, omega):
+    T = f.dtype.type
+    omega = T(omega)
+    one_third, two_thirds = T(1) / T(3), T(2) / T(3)
+    fac = T(4.5) - T(2.25) * omega
+    omegabar = T(1) - omega
+    vC, vE, vN, vW, vS, vNE, vNW, vSW, vSE = (f[q] for q in range(9))
+    rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC
+    invrho = T(1) / rho
+    sumX1 = vE + vNE + vSE
+    sumXN = vW + vNW + vSW
+    sumY1 = vN + vNE + vNW
+    sumYN = vS + vSE + vSW
+    m10 = invrho * (sumX1 - sumXN)
+    m01 = invrho * (sumY1 - sumYN)
+    u2 = m10 * m10
+    v2 = m01 * m01
+    m20 = invrho * (sumX1 + sumXN)
+    m02 = invrho * (sumY1 + sumYN)
+    Gx = fac * u2 * (m20 - one_third - u2)
+    Gy = fac * v2 * (m02 - one_third - v2)
+    X0 = -two_thirds + u2 + Gx
+    X1 = -(X0 + T(1) + m10) * T(0.5)
+    XN = X1 + m10
+    Y0 = -two_thirds + v2 + Gy
+    Y1 = -(Y0 + T(1) + m01) * T(0.5)
+    YN = Y1 + m01
+    rho_omega = rho * omega
+    X0 = X0 * rho_omega
+    X1 = X1 * rho_omega
+    XN = XN * rho_omega
+    out = [omegabar * vC + X0 * Y0, omegabar * vE + X1 * Y0, omegabar * vN + X0 * Y1, omegabar * vW + XN * Y0, omegabar * vS + X0 * YN,
+           omegabar * vNE + X1 * Y1, omegabar * vNW + XN * Y1, omegabar * vSW + XN * YN, omegabar * vSE + X1 * YN]
+    return np.stack(out)

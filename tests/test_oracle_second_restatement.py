@@ -191,3 +191,21 @@ def test_fdm_streaming_schemes(prec, stencil):
         m = nr.collide_trt(m, p["omega"], p["trt_magic"])
         a, b = b, a
     assert np.array_equal(a[:, :, :n], m), np.abs(a[:, :, :n] - m).max()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("omega", [0.6, 1.0, 1.95662121778720])
+def test_split_and_improved_collisions(prec, omega):
+    """the -DSPLIT builds (bgk_kernel_cache, trt_split) and collide_bgk_improved"""
+    nx, ny = 23, 37
+    o, p, f = start(prec, nx, ny)
+    T = o.dtype
+    a = f.copy()
+    o.kernel_bgk(a, ny, T(omega))
+    assert np.array_equal(a[:, :, :ny], nr.collide_bgk_split(f[:, :, :ny], omega))
+    a = f.copy()
+    o.collide_trt_split(a, ny, T(omega), T(0.25))
+    assert np.array_equal(a[:, :, :ny], nr.collide_trt_split(f[:, :, :ny], omega, 0.25))
+    a = f.copy()
+    o.collide_bgk_improved(a, ny, T(omega))
+    assert np.array_equal(a[:, :, :ny], nr.collide_bgk_improved(f[:, :, :ny], omega))
