@@ -24,6 +24,7 @@ that, in fp64 and fp32.  Arrays are f[q, x, y] with y < ny (the padding rows of 
   fdm_sofonea_kernel     src/fvm_bardow.F90:702-880
   periodic_dugks         src/periodic_dugks.F90:25-77 (step, dugks_collide), 80-169 (kernel_bgk), 172-304 (kernel_stream),
                          310-434 (update_ew / update_ns); built with -DDUGKS
+  sim/ lw plugin         sim/sim_lw.F90:24-85 (lw_stream), 87-164 (lw_collision), 166-182 (lw_bc = periodic images)
   sim/ seam (slbm)       sim/sim.F90:119-131, 148-199, 352-383, 404-505, 568-624   (DDF-shifted populations f[k, j, i])
 """
 import numpy as np
@@ -548,3 +549,37 @@ def collide_bgk_improved(f, omega):
     out = [omegabar * vC + X0 * Y0, omegabar * vE + X1 * Y0, omegabar * vN + X0 * Y1, omegabar * vW + XN * Y0, omegabar * vS + X0 * YN,
            omegabar * vNE + X1 * Y1, omegabar * vNW + XN * Y1, omegabar * vSW + XN * YN, omegabar * vSE + X1 * YN]
     return np.stack(out)
+
+
+# ---- the 2nd-order Lax-Wendroff plugin of sim/ (sim/sim_lw.F90), populations DDF-shifted, fields f[k, j, i] --------------
+def lw_stream(f, dt):
+    T = f.dtype.type
+    dt = T(dt)
+    at = lambda a, di, dj: np.roll(a, shift=(-dj, -di), axis=(0, 1))  # noqa: E731  value at (i + di, j + dj)
+    out = np.empty_like(f)
+    out[0] = f[0]
+    for k in range(1, 9):
+        vx = dt * T(CX[k])
+        vy = dt * T(CY[k])
+        vxx = T(0.5) * vx * vx
+        vyy = T(0.5) * vy * vy
+        vxy = vx * vy
+        c = f[k]
+        dfx = T(0.5) * (at(c, 1, 0) - at(c, -1, 0))
+        dfy = T(0.5) * (at(c, 0, 1) - at(c, 0, -1))
+        dfxx = at(c, 1, 0) - T(2) * c + at(c, -1, 0)
+        dfyy = at(c, 0, 1) - T(2) * c + at(c, 0, -1)
+        dfxy = T(0.25) * (at(c, 1, 1) - at(c, -1, 1) + at(c, -1, -1) - at(c, 1, -1))
+        out[k] = c - vx * dfx - vy * dfy + (vxx * dfxx + vxy * dfxy + vyy * dfyy)
+    return out
+
+
+def lw_collision(f, omega):
+    T = f.dtype.type
+    omega = T(omega)
+    rho = f[0] + (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + T(1)
+    irho = T(1) / rho
+    ux = (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3])) * irho
+    uy = (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4])) * irho
+    feq = sim_equilibrium(rho, ux, uy)
+    return np.stack([f[k] + omega * (feq[k] - f[k]) for k in range(9)])

@@ -209,3 +209,26 @@ def test_split_and_improved_collisions(prec, omega):
     a = f.copy()
     o.collide_bgk_improved(a, ny, T(omega))
     assert np.array_equal(a[:, :, :ny], nr.collide_bgk_improved(f[:, :, :ny], omega))
+
+
+@pytest.mark.parametrize("dt", [1.0, 0.4])
+def test_sim_lw_plugin(dt):
+    """the 2nd-order Lax-Wendroff plugin behind c_lw_* (sim/sim_lw.F90): stream, collide, periodic halo; 12 steps"""
+    nx, ny, steps, omega = 40, 56, 12, 1.4
+    o = Oracle("f64")
+    rng = np.random.default_rng(12)
+    p = 1e-3 * rng.standard_normal((ny, nx))
+    u = 0.05 * rng.standard_normal((2, ny, nx))
+    f1 = np.zeros((9, ny + 2, nx + 2))
+    f2 = np.zeros_like(f1)
+    P = lambda a: a.ctypes.data  # noqa: E731
+    o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
+    o._lw_bc(nx, ny, P(f1))
+    n = nr.sim_eqinit(p, u[0], u[1])
+    for _ in range(steps):
+        o._lw_stream(nx, ny, P(f1), P(f2), dt)
+        o._lw_collision(nx, ny, P(f2), omega)
+        o._lw_bc(nx, ny, P(f2))
+        f1, f2 = f2, f1
+        n = nr.lw_collision(nr.lw_stream(n, dt), omega)
+    assert np.array_equal(f1[:, 1:ny + 1, 1:nx + 1], n)
