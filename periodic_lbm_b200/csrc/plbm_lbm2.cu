@@ -420,6 +420,8 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
     }
 }
 
+int env_int(const char* name, int dflt);
+
 template <typename T, int MODEL>
 int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
 {
@@ -453,6 +455,14 @@ int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end
     a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
     int nseg = (ncols + 63) / 64;
+    // measurement knob (PLBM_PAIR_BULK_FILL=1, with PLBM_PAIR_BULK=2 to force this kernel on small grids): shorter
+    // segments, down to 8 columns, until one wave of 3 blocks per SM is filled
+    static const int fill = env_int("PLBM_PAIR_BULK_FILL", 0);
+    if (fill && a.nstrips * nseg < 3 * g.sm_count) {
+        nseg = (3 * g.sm_count + a.nstrips - 1) / a.nstrips;
+        if (nseg > (ncols + 7) / 8) nseg = (ncols + 7) / 8;
+        if (nseg < 1) nseg = 1;
+    }
     a.seglen = (ncols + nseg - 1) / nseg;
     nseg = (ncols + a.seglen - 1) / a.seglen;
     kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);

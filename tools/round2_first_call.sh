@@ -14,6 +14,12 @@ timeout 200 env PLBM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_parity.
 timeout 200 python tools/pair_ab.py --cases 8192x8192:f64:bgk,8192x8192:f64:trt,8192x8192:f64:rr,8192x8192:f32:bgk,8192x8192:f32:rr,4096x32768:f64:bgk --variants 7,9,10 > $O/${R}_pair_ab.jsonl 2>&1; step ab $?
 timeout 100 env PLBM_MULTI_NT=256 python tools/pair_ab.py --cases 8192x8192:f64:bgk,8192x8192:f32:bgk,4096x32768:f64:bgk --variants 10 > $O/${R}_pair_ab_nt256.jsonl 2>&1; step ab-nt256 $?
 timeout 100 python tools/pair_ab.py --cases 8192x8192:f64:rr,8192x8192:f32:rr,8192x8192:f64:bgk --variants 0,11 > $O/${R}_pair_ab_fma.jsonl 2>&1; step ab-fma $?
+# crossover between k_lbm2 and k_lbm2_bulk on mid-size grids (default: bulk from two waves of its blocks upwards)
+for c in 1024x1024:f64:trt 2048x2048:f64:bgk 4096x4096:f64:bgk 4096x4096:f32:bgk; do
+    timeout 60 python tools/pair_ab.py --cases $c --variants 6 --steps 201 >> $O/${R}_pair_ab_crossover.jsonl 2>&1
+    timeout 60 env PLBM_PAIR_BULK=2 python tools/pair_ab.py --cases $c --variants 0 --steps 201 >> $O/${R}_pair_ab_crossover.jsonl 2>&1
+    timeout 60 env PLBM_PAIR_BULK=2 PLBM_PAIR_BULK_FILL=1 python tools/pair_ab.py --cases $c --variants 0 --steps 201 >> $O/${R}_pair_ab_crossover.jsonl 2>&1
+done; step ab-crossover $?
 for sl in 32 128 256; do
     timeout 60 env PLBM_MULTI_SEGLEN=$sl python tools/pair_ab.py --cases 8192x8192:f64:bgk --variants 10 >> $O/${R}_pair_ab_seglen.jsonl 2>&1; step ab-seglen-$sl $?
 done
