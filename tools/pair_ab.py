@@ -27,6 +27,7 @@ def run(nx, ny, prec, coll, variant, steps, reps, once=False):
     p.set_pdf_to_equilibrium(g)
     g.set_variant(variant)
     g.collision, g.streaming = getattr(p, "collide_" + coll), p.lbm_stream
+    kernel = g.pair_kernel()  # what variants 0 / 5..8 use (9 / 10: k_lbmn_bulk, 11: the FMA build of this one)
     if once:
         p.perform_lbm_step(g, 4)  # one pair + two single steps; variant 10: one triple + one single step
         g.synchronize()
@@ -43,7 +44,8 @@ def run(nx, ny, prec, coll, variant, steps, reps, once=False):
     p.dealloc_grid(g)
     mlups = nx * ny / best * 1e-6
     gbs = mlups * 1e6 * (144 if prec == "f64" else 72) / 1e9
-    return dict(nx=nx, ny=ny, prec=prec, coll=coll, variant=variant, steps=steps, ms_per_step=round(best * 1e3, 4),
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("PLBM_")}
+    return dict(nx=nx, ny=ny, prec=prec, coll=coll, variant=variant, kernel=kernel, env=knobs, steps=steps, ms_per_step=round(best * 1e3, 4),
                 mlups=round(mlups, 1), algorithmic_gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / PEAK, 4))
 
 
