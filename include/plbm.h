@@ -88,6 +88,10 @@ int plbm_dealloc_grid(plbm_handle grid);
 int plbm_get_dims(plbm_handle grid, int* nx, int* ny, int* ld, int* nf, int* precision);
 /* grid%iold / grid%inew / grid%imid (1-based; imid = -1 when nf == 2) */
 int plbm_get_indices(plbm_handle grid, int* iold, int* inew, int* imid);
+/* Set the lattice roles directly (restoring a checkpoint: the rotations of perform_triple_step cannot be reached by
+ * plbm_swap alone).  (iold, inew) must be a permutation of {1,2} for nf = 2 (imid ignored), (iold, inew, imid) of {1,2,3}
+ * for nf = 3; the reference keeps these as plain public components, src/fvm_bardow.F90:57. */
+int plbm_set_indices(plbm_handle grid, int iold, int inew, int imid);
 
 /* ---- set_properties (src/fvm_bardow.F90:242-269) ------------------------------------ */
 /* tau = nu/cs^2, omega = dt/(tau+dt/2), trt_magic = magic or (tau/dt)^2 */

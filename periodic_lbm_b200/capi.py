@@ -29,6 +29,7 @@ SIGNATURES = {
     "plbm_dealloc_grid": (_I, [_H]),
     "plbm_get_dims": (_I, [_H] + [C.POINTER(_I)] * 5),
     "plbm_get_indices": (_I, [_H] + [C.POINTER(_I)] * 3),
+    "plbm_set_indices": (_I, [_H, _I, _I, _I]),
     "plbm_set_properties": (_I, [_H, _D, _D, _D, _I]),
     "plbm_get_properties": (_I, [_H, C.POINTER(_D)]),
     "plbm_set_omega": (_I, [_H, _D]),

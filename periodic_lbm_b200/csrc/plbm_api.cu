@@ -507,6 +507,27 @@ int plbm_get_indices(plbm_handle g, int* iold, int* inew, int* imid)
     return PLBM_OK;
 }
 
+int plbm_set_indices(plbm_handle g, int iold, int inew, int imid)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    // a permutation of the lattices the grid owns: (iold, inew) of {1, 2} for nf = 2 (imid ignored, stays -1),
+    // (iold, inew, imid) of {1, 2, 3} for nf = 3 -- the rotations perform_triple_step reaches and the others alike
+    const bool ok2 = g->nf == 2 && ((iold == 1 && inew == 2) || (iold == 2 && inew == 1));
+    const bool ok3 = g->nf == 3 && iold >= 1 && iold <= 3 && inew >= 1 && inew <= 3 && imid >= 1 && imid <= 3 && iold != inew && iold != imid &&
+                     inew != imid;
+    if (!ok2 && !ok3) {
+        set_error("set_indices: (iold, inew[, imid]) must be a permutation of the grid's lattice numbers");
+        return PLBM_ERR_ARG;
+    }
+    if ((rc = materialize_inew(*g))) return rc;  // the pending half-step collision belongs to the OLD inew
+    g->iold = iold;
+    g->inew = inew;
+    if (g->nf == 3) g->imid = imid;
+    comm_invalidate_halo(*g);
+    return PLBM_OK;
+}
+
 int plbm_set_properties(plbm_handle g, double nu, double dt, double magic, int has_magic)
 {
     if (!g) {
@@ -717,6 +738,9 @@ int plbm_dugks_stream(plbm_handle g, int dugks)
     int rc = check(g);
     if (rc) return rc;
     if ((rc = need_props(g))) return rc;
+    // after a fused perform_dugks_step lattice inew still holds ftilde^n: the reference has fbar^+ there, and an
+    // unfused dugks_stream reads and updates exactly that lattice
+    if ((rc = materialize_inew(*g))) return rc;
     if (g->prec == PLBM_F64) {
         double of, oh, oc;
         dugks_rates<double>(*g, dugks != 0, of, oh, oc);

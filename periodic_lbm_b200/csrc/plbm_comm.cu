@@ -39,7 +39,7 @@ struct NcclUniqueId {
 };
 typedef void* ncclComm_t;
 typedef int ncclResult_t;
-constexpr int kNcclInt8 = 0, kNcclInt32 = 2, kNcclMin = 3;
+constexpr int kNcclInt8 = 0, kNcclInt32 = 2, kNcclFloat64 = 8, kNcclMin = 3;
 
 struct NcclApi {
     void* lib = nullptr;
@@ -282,6 +282,38 @@ static int p2p_setup(Grid& g)
             c->halo_hi[p] = c->ipc_block + off_hi(c->slot_bytes, p);
         }
     }
+    return PLBM_OK;
+}
+
+// Ring-wide reduction of a few doubles (global diagnostics).  NCCL's max / min follow the IEEE maxNum rule and
+// would drop a NaN, so a NaN flag is reduced alongside and re-applied: a rank that diverged poisons the global value.
+int comm_allreduce(Grid& g, double* values, int n, int op)
+{
+    Comm* c = g.comm;
+    if (!c || n < 1 || n > 8) {
+        set_error("comm_allreduce: no ring or bad count");
+        return PLBM_ERR_ARG;
+    }
+    double stage[9];
+    double nan_flag = 0.0;
+    for (int i = 0; i < n; ++i) {
+        stage[i] = values[i];
+        if (values[i] != values[i]) {
+            nan_flag = 1.0;
+            stage[i] = 0.0;
+        }
+    }
+    double* dev = (double*)c->send9_hi;  // scratch device memory (>= 9 * ld reals)
+    PLBM_CUDA(cudaStreamSynchronize(g.stream));
+    PLBM_CUDA(cudaMemcpyAsync(dev, stage, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    PLBM_CUDA(cudaMemcpyAsync(dev + 8, &nan_flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PLBM_NCCL(g_nccl.GroupStart());
+    PLBM_NCCL(g_nccl.AllReduce(dev, dev, (size_t)n, kNcclFloat64, op, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.AllReduce(dev + 8, dev + 8, 1, kNcclFloat64, PLBM_REDUCE_MAX, c->comm, c->stream));
+    PLBM_NCCL(g_nccl.GroupEnd());
+    PLBM_CUDA(cudaMemcpyAsync(stage, dev, sizeof(double) * 9, cudaMemcpyDeviceToHost, c->stream));
+    PLBM_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) values[i] = stage[8] > 0.0 ? __builtin_nan("") : stage[i];
     return PLBM_OK;
 }
 

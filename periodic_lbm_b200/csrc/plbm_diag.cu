@@ -122,16 +122,21 @@ __device__ __forceinline__ double warp_sum(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// max / min that PROPAGATE NaN (fmax / fmin drop it): a diverged field must not report max |u| = 0.  Any NaN speed makes
+// the result NaN (gfortran's maxval / minval, app/main_taylor_green.f90:106, return NaN only for an all-NaN array and skip
+// NaNs otherwise; for a blow-up detector "any" is the useful reading, and sum(rho) / kinetic energy behave that way too).
+__host__ __device__ __forceinline__ double nan_max(double a, double b) { return a != a ? a : ((b > a || b != b) ? b : a); }
+__host__ __device__ __forceinline__ double nan_min(double a, double b) { return a != a ? a : ((b < a || b != b) ? b : a); }
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ double warp_min(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = nan_min(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -147,8 +152,8 @@ __global__ void __launch_bounds__(256) k_reduce(const T* __restrict__ rho, const
         const double u = (double)ux[i], v = (double)uy[i];
         if (MODE == 0) {
             const double sp = hypot(u, v);
-            a = fmax(a, sp);
-            b = fmin(b, sp);
+            a = nan_max(a, sp);
+            b = nan_min(b, sp);
             const double r = (double)rho[i];
             c += r;
             d += 0.5 * r * (u * u + v * v);
@@ -175,8 +180,8 @@ __global__ void __launch_bounds__(256) k_reduce(const T* __restrict__ rho, const
         Red4 r = sm[0];
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
             if (MODE == 0) {
-                r.a = fmax(r.a, sm[i].a);
-                r.b = fmin(r.b, sm[i].b);
+                r.a = nan_max(r.a, sm[i].a);
+                r.b = nan_min(r.b, sm[i].b);
                 r.c += sm[i].c;
                 r.d += sm[i].d;
             } else {
@@ -203,13 +208,25 @@ static int reduce_impl(Grid& g, const T* p0, const T* p1, Red4& out, cudaStream_
     out = h[0];
     for (int i = 1; i < nb; ++i) {
         if (MODE == 0) {
-            out.a = h[i].a > out.a ? h[i].a : out.a;
-            out.b = h[i].b < out.b ? h[i].b : out.b;
+            out.a = nan_max(out.a, h[i].a);
+            out.b = nan_min(out.b, h[i].b);
             out.c += h[i].c;
             out.d += h[i].d;
         } else {
             out.a += h[i].a;
             out.b += h[i].b;
+        }
+    }
+    // slab decomposition: the diagnostics are those of the GLOBAL grid (app/main_taylor_green.f90:106,155,195-198 reduce over
+    // the whole field) -- every rank of the ring calls this, and every rank gets the same numbers
+    if (g.comm) {
+        int rc;
+        if (MODE == 0) {
+            if ((rc = comm_allreduce(g, &out.a, 1, PLBM_REDUCE_MAX))) return rc;
+            if ((rc = comm_allreduce(g, &out.b, 1, PLBM_REDUCE_MIN))) return rc;
+            if ((rc = comm_allreduce(g, &out.c, 2, PLBM_REDUCE_SUM))) return rc;
+        } else {
+            if ((rc = comm_allreduce(g, &out.a, 2, PLBM_REDUCE_SUM))) return rc;
         }
     }
     return PLBM_OK;

@@ -144,6 +144,9 @@ int comm_finalize(Grid& g);
 int comm_transport_is_p2p(const Grid& g);
 bool comm_pairs_agreed(const Grid& g);  // every slab of the ring can run the two-step kernel
 void comm_invalidate_halo(Grid& g);  // the lattices were modified behind the ring's back
+// ring-wide reduction of n doubles in place (every rank calls it; NaN propagates through max / min as through sum)
+enum { PLBM_REDUCE_SUM = 0, PLBM_REDUCE_MAX = 2, PLBM_REDUCE_MIN = 3 };  // = ncclSum, ncclMax, ncclMin
+int comm_allreduce(Grid& g, double* values, int n, int op);
 template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams<T>& cp, int nsteps);
 // one FVM/DUGKS halo exchange: all nine populations of lines 0 and nx-1 of `f` -> g.fv_halo_lo/hi
 template <typename T> int comm_fv_exchange(Grid& g, const T* f);

@@ -113,14 +113,21 @@ int launch_cluster(const Grid& g, T* fa, T* fb, int ncta, int lpc, size_t smem, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (ncta > 8) {  // a 16-CTA cluster needs a GPC with 16 free SMs: ask first, let the caller retry with 8
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, k_lbm_cluster<T, MODEL>, &cfg) != cudaSuccess || nclusters < 1) {
-            cudaGetLastError();
-            return -1;
-        }
+    // Ask first, for every cluster size: a 16-CTA cluster needs a GPC with 16 free SMs, and on a partitioned device (MIG,
+    // green contexts, SM-limited GPCs) even 8 or fewer may not be schedulable.  "Not applicable" (-1) lets the caller try a
+    // smaller cluster and finally fall back to the per-step kernels instead of failing perform_lbm_step.
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, k_lbm_cluster<T, MODEL>, &cfg) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        return -1;
     }
-    PLBM_CUDA(cudaLaunchKernelEx(&cfg, k_lbm_cluster<T, MODEL>, fa, fb, g.nx, g.ny, g.ld, lpc, nsteps, cp));
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_lbm_cluster<T, MODEL>, fa, fb, g.nx, g.ny, g.ld, lpc, nsteps, cp);
+    if (e == cudaErrorInvalidConfiguration || e == cudaErrorLaunchOutOfResources || e == cudaErrorInvalidValue ||
+        e == cudaErrorNotSupported) {
+        cudaGetLastError();  // a launch-configuration failure launched nothing and is not sticky: clear it
+        return -1;
+    }
+    PLBM_CUDA(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return PLBM_OK;
 }
@@ -136,7 +143,7 @@ int try_lbm_cluster_steps(const Grid& g, T* f_iold, T* f_inew, int model, const 
     *done = false;
     if (g.nx < 2 || g.ny < 2) return PLBM_OK;
     int rc = -1;
-    for (int max_ctas = MAX_CTAS; max_ctas >= 8 && rc == -1; max_ctas /= 2) {
+    for (int max_ctas = MAX_CTAS; max_ctas >= 2 && rc == -1; max_ctas /= 2) {
         int ncta = g.nx < max_ctas ? g.nx : max_ctas;
         const int lpc = (g.nx + ncta - 1) / ncta;
         ncta = (g.nx + lpc - 1) / lpc;  // every CTA owns at least one line

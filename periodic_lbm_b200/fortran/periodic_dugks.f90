@@ -2,7 +2,7 @@
 !! grid%dugks selects the -DDUGKS branch (default) or the macro-less default build of the reference.
 module periodic_dugks
    use, intrinsic :: iso_c_binding
-   use fvm_bardow, only: lattice_grid, sync_indices
+   use plbm_lattice, only: lattice_grid, dugks_stream, dugks_collide, plbm_sync_indices, plbm_push_omega
    use plbm_c
    implicit none
    private
@@ -11,10 +11,12 @@ module periodic_dugks
    public :: dugks_collide
 contains
 
+   !> src/periodic_dugks.F90:25-38: collision(); streaming(); swap -- one fused launch when both
+   !! pointers are unset or name this module's own passes
    subroutine perform_dugks_step(grid)
       type(lattice_grid), intent(inout) :: grid
       logical :: fused
-      call plbm_check(plbm_set_omega(grid%dev, real(grid%omega,c_double)), "set_omega")
+      call plbm_push_omega(grid)
       fused = .true.
       if (associated(grid%collision)) fused = fused .and. associated(grid%collision, dugks_collide)
       if (associated(grid%streaming)) fused = fused .and. associated(grid%streaming, dugks_stream)
@@ -25,17 +27,7 @@ contains
          call grid%streaming()
          call plbm_check(plbm_swap(grid%dev), "swap")
       end if
-      call sync_indices(grid)
-   end subroutine
-
-   subroutine dugks_collide(grid)
-      class(lattice_grid), intent(inout) :: grid
-      call plbm_check(plbm_dugks_collide(grid%dev, merge(1_c_int, 0_c_int, grid%dugks)), "dugks_collide")
-   end subroutine
-
-   subroutine dugks_stream(grid)
-      class(lattice_grid), intent(inout) :: grid
-      call plbm_check(plbm_dugks_stream(grid%dev, merge(1_c_int, 0_c_int, grid%dugks)), "dugks_stream")
+      call plbm_sync_indices(grid)
    end subroutine
 
 end module periodic_dugks

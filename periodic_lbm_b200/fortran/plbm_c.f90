@@ -4,13 +4,15 @@
 !! (SURVEY.md F1), so these modules have not been compiled there.  Build line on a machine with
 !! gfortran:  gfortran -c -cpp precision.F90 plbm_c.f90 fvm_bardow.F90 periodic_lbm.F90 ...
 !!            gfortran app.f90 *.o -L<repo>/periodic_lbm_b200 -lplbm_b200
+!! (the full list, with the reference's own output / flow-case modules, is in INTEGRATION.md section 1)
 module plbm_c
    use, intrinsic :: iso_c_binding
    implicit none
    public
 
    integer(c_int), parameter :: PLBM_F64 = 0, PLBM_F32 = 1
-   integer(c_int), parameter :: PLBM_BGK = 0, PLBM_TRT = 1, PLBM_RR = 2, PLBM_BGK_SPLIT = 3
+   integer(c_int), parameter :: PLBM_BGK = 0, PLBM_TRT = 1, PLBM_RR = 2, PLBM_BGK_SPLIT = 3, &
+                                PLBM_TRT_SPLIT = 4, PLBM_BGK_IMPROVED = 5
    integer(c_int), parameter :: PLBM_STREAM_LBM = 0, PLBM_STREAM_FVM_BARDOW = 1, &
                                 PLBM_STREAM_FDM_BARDOW = 2, PLBM_STREAM_FDM_SOFONEA = 3
 
@@ -74,6 +76,12 @@ module plbm_c
          integer(c_int) :: stat
       end function
       function plbm_perform_step(grid, streaming, collision, nsteps) bind(c, name="plbm_perform_step") result(stat)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: grid
+         integer(c_int), value :: streaming, collision, nsteps
+         integer(c_int) :: stat
+      end function
+      function plbm_perform_triple_step(grid, streaming, collision, nsteps) bind(c, name="plbm_perform_triple_step") result(stat)
          import :: c_ptr, c_int
          type(c_ptr), value :: grid
          integer(c_int), value :: streaming, collision, nsteps

@@ -139,6 +139,15 @@ class LatticeGrid:
         check(lib.plbm_diagnostics(self._h, out), "diagnostics")
         return dict(max_speed=out[0], min_speed=out[1], sum_rho=out[2], kinetic_energy=out[3])
 
+    def l2_sums(self, uxa, uya):
+        """(sum |u - ua|^2, sum |ua|^2) of the device ux,uy vs host analytic fields; under a slab decomposition the
+        sums run over the GLOBAL grid (each rank passes its own lines of the analytic fields)."""
+        uxa = np.ascontiguousarray(uxa, dtype=self.dtype)
+        uya = np.ascontiguousarray(uya, dtype=self.dtype)
+        out = (C.c_double * 2)()
+        check(lib.plbm_l2_sums(self._h, _ptr(uxa), _ptr(uya), out), "l2_sums")
+        return float(out[0]), float(out[1])
+
     def l2_error(self, uxa, uya):
         """calc_L2_norm (app/main_taylor_green.f90:174-212) of the device ux,uy vs host analytic fields."""
         uxa = np.ascontiguousarray(uxa, dtype=self.dtype)

@@ -117,16 +117,12 @@ def load_checkpoint(path: str, device=None) -> LatticeGrid:
     nu, dt, tau, omega, magic, _ = z["props"]
     set_properties(g, nu, dt, magic)
     g.omega = omega
-    # a fresh grid starts with inew=1, iold=2 (alloc_grid); put each saved lattice where the saved
-    # indices expect it after the same number of swaps modulo the cycle
-    saved = {"iold": int(z["iold"]), "inew": int(z["inew"]), "imid": int(z["imid"])}
+    # lattices are stored by NUMBER: restore the saved roles first (a fresh grid starts with inew=1, iold=2, imid=3;
+    # after perform_triple_step the roles rotate through all three lattices, which plbm_swap alone cannot reach)
     from .capi import check, lib
-    guard = 0
-    while (g.iold, g.inew) != (saved["iold"], saved["inew"]) and guard < 3:
-        check(lib.plbm_swap(g._h), "swap")
-        guard += 1
-    if g.nf == 2 and (g.iold, g.inew) != (saved["iold"], saved["inew"]):
-        raise RuntimeError("load_checkpoint: cannot restore lattice indices")
+    check(lib.plbm_set_indices(g._h, int(z["iold"]), int(z["inew"]), int(z["imid"])), "set_indices")
+    if (g.iold, g.inew, g.imid) != (int(z["iold"]), int(z["inew"]), int(z["imid"])):
+        raise RuntimeError("load_checkpoint: lattice indices were not restored")
     for k in range(1, g.nf + 1):
         g.upload_f(k, z[f"f{k}"])
     return g

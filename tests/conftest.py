@@ -14,9 +14,11 @@ def pytest_configure(config):
 
 
 def _ensure_built():
+    """Never test a stale libplbm_b200.so: rebuild (incremental `make`) whenever the sources differ from the ones the
+    library was built from (content hash, __graft_entry__.source_stamp -- file times do not survive the copy to the GPU box)."""
     import __graft_entry__ as ge
 
-    if not os.path.exists(os.path.join(ROOT, "periodic_lbm_b200", "libplbm_b200.so")):
+    if not ge.is_current():
         ge.build()
     from oracle import oracle as orc
 

@@ -10,8 +10,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p2p"):
+def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p2p", env=None, expect_kernel=None):
     os.environ["PLBM_HALO"] = halo
+    os.environ.update(env or {})
     import periodic_lbm_b200 as p
     from periodic_lbm_b200.capi import check, lib
     from conftest import random_state
@@ -45,14 +46,88 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p
         p.perform_step(g, steps)
     else:
         g.streaming = p.lbm_stream
+        if expect_kernel is not None:
+            assert g.pair_kernel() == expect_kernel, (g.pair_kernel(), expect_kernel)
         # two calls: exercises the "halo already in flight" path between calls
         p.perform_lbm_step(g, steps // 2)
         p.perform_lbm_step(g, steps - steps // 2)
     got = g.download_f(g.iold)
     p.update_macros(g, lagged=False)
-    outq.put((rank, sl.x_offset, got, transport))
+    # global diagnostics: every rank gets the numbers of the WHOLE grid
+    diag = g.diagnostics()
+    uxa, uya = _analytic_fields(nxg, ny, g.dtype)
+    l2 = g.l2_sums(np.ascontiguousarray(uxa[sl.x_offset:sl.x_end]), np.ascontiguousarray(uya[sl.x_offset:sl.x_end]))
+    outq.put((rank, sl.x_offset, got, transport, diag, l2))
     check(lib.plbm_comm_finalize(g._h), "comm_finalize")
     p.dealloc_grid(g)
+
+
+def _analytic_fields(nxg, ny, dtype):
+    """any smooth reference field for the L2 sums (what calc_L2_norm compares against, app/main_taylor_green.f90:174-212)"""
+    x = (np.arange(nxg)[:, None] + 0.5) * (2 * np.pi / nxg)
+    y = (np.arange(ny)[None, :] + 0.5) * (2 * np.pi / ny)
+    return (0.02 * np.cos(x) * np.sin(y)).astype(dtype), (-0.02 * np.sin(x) * np.cos(y)).astype(dtype)
+
+
+def _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, halo, env=None, expect_kernel=None):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    idq, outq = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo, env, expect_kernel))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    parts = [outq.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    parts.sort(key=lambda t: t[1])
+    return parts
+
+
+def _single(plbm, nxg, ny, steps, coll_id, prec, seed):
+    from conftest import random_state
+    from oracle.oracle import Oracle
+
+    o = Oracle(prec)
+    f0 = np.nan_to_num(random_state(o, nxg, ny, seed=seed), nan=0.0)
+    g = plbm.alloc_grid(nxg, ny, precision=prec)
+    plbm.set_properties(g, 0.02, 1.0, 0.25)
+    g.upload_f(g.iold, f0)
+    g.collision = {0: plbm.collide_bgk, 1: plbm.collide_trt, 2: plbm.collide_rr}[coll_id % 10]
+    g.streaming = plbm.lbm_stream
+    plbm.perform_lbm_step(g, steps)
+    single = g.download_f(g.iold)
+    plbm.update_macros(g, lagged=False)
+    diag = g.diagnostics()
+    uxa, uya = _analytic_fields(nxg, ny, g.dtype)
+    l2 = g.l2_sums(uxa, uya)
+    plbm.dealloc_grid(g)
+    return single, diag, l2
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("coll_id", [0, 2])
+def test_slabs_with_bulk_interior_bitwise_equal_single_gpu(plbm, world, prec, coll_id):
+    """The kernel mix the scaling bench measures: k_lbm2_bulk on the interior of every slab (raw columns by bulk async
+    copies), k_lbm2<HALO> on the two boundary lines per side, closing single step by k_lbm -- on a grid large enough
+    that the interior launch has several strips and x segments.  Also: the global diagnostics
+    every rank reports equal the single-GPU ones."""
+    if plbm.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    nxg, ny, steps, seed = 512, 2048, 9, 7
+    parts = _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, "p2p", env={"PLBM_PAIR_BULK": "2"}, expect_kernel="k_lbm2_bulk")
+    assert all(t[3] == 1 for t in parts)
+    multi = np.concatenate([t[2] for t in parts], axis=1)
+    single, diag, l2 = _single(plbm, nxg, ny, steps, coll_id, prec, seed)
+    assert np.array_equal(multi[:, :, :ny], single[:, :, :ny])
+    for t in parts:
+        d, l = t[4], t[5]
+        assert d["max_speed"] == diag["max_speed"] and d["min_speed"] == diag["min_speed"]
+        np.testing.assert_allclose([d["sum_rho"], d["kinetic_energy"]], [diag["sum_rho"], diag["kinetic_energy"]], rtol=1e-12)
+        np.testing.assert_allclose(l, l2, rtol=1e-12)
 
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])
@@ -65,21 +140,11 @@ def test_slabs_bitwise_equal_single_gpu(plbm, nxg, ny, steps, coll_id, prec, hal
     world = min(plbm.device_count(), 4 if nxg >= 8 else 2)  # (7, 32): slabs of 4 and 3 lines -> no fused pairs anywhere
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
-    import torch.multiprocessing as mp
     from conftest import random_state
     from oracle.oracle import Oracle
 
     seed = 99
-    ctx = mp.get_context("spawn")
-    idq, outq = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo)) for r in range(world)]
-    for pr in procs:
-        pr.start()
-    parts = [outq.get(timeout=300) for _ in range(world)]
-    for pr in procs:
-        pr.join(timeout=120)
-        assert pr.exitcode == 0
-    parts.sort(key=lambda t: t[1])
+    parts = _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, halo)
     assert all(t[3] == (1 if halo == "p2p" else 0) for t in parts), [t[3] for t in parts]  # transport actually used
     multi = np.concatenate([t[2] for t in parts], axis=1)
 

@@ -519,6 +519,84 @@ def test_output_npy_and_checkpoint_roundtrip(plbm, tmp_path):
     plbm.dealloc_grid(h)
 
 
+def test_checkpoint_roundtrip_nf3_after_triple_steps(plbm, tmp_path):
+    """perform_triple_step rotates (iold, inew, imid) through all three lattices; a checkpoint taken
+    after an odd number of such steps must come back with the same roles (plbm_set_indices), so that the resumed run is
+    bit-identical to the uninterrupted one and lagged update_macros reads the right lattice."""
+    nx, ny = 40, 48
+    for nsteps_before in (1, 2, 5):
+        og = OracleGrid(nx, ny, "f64")
+        f0 = np.nan_to_num(random_state(og.o, nx, ny), nan=0.0)
+        g = plbm.alloc_grid(nx, ny, nf=3, precision="f64")
+        plbm.set_properties(g, 0.02, 1.0, 0.25)
+        g.upload_f(g.iold, f0)
+        g.collision, g.streaming = plbm.collide_bgk, plbm.lbm_stream
+        plbm.perform_triple_step(g, nsteps_before)
+        saved = (g.iold, g.inew, g.imid)
+        assert sorted(saved) == [1, 2, 3]
+        plbm.save_checkpoint(g, str(tmp_path / f"ckpt3_{nsteps_before}"))
+        plbm.update_macros(g)
+        rho_lag = g.rho.copy()
+        plbm.perform_triple_step(g, 3)
+        want = [g.download_f(k) for k in (g.iold, g.inew, g.imid)]
+        h = plbm.load_checkpoint(str(tmp_path / f"ckpt3_{nsteps_before}"))
+        assert (h.iold, h.inew, h.imid) == saved
+        h.collision, h.streaming = plbm.collide_bgk, plbm.lbm_stream
+        plbm.update_macros(h)
+        assert np.array_equal(h.rho, rho_lag)
+        plbm.perform_triple_step(h, 3)
+        assert (h.iold, h.inew, h.imid) == (g.iold, g.inew, g.imid)
+        for w, k in zip(want, (h.iold, h.inew, h.imid)):
+            assert np.array_equal(h.download_f(k)[:, :, :ny], w[:, :, :ny])
+        plbm.dealloc_grid(g)
+        plbm.dealloc_grid(h)
+
+
+def test_set_indices_rejects_non_permutations(plbm):
+    from periodic_lbm_b200.capi import lib
+    g2, g3 = plbm.alloc_grid(8, 8, nf=2), plbm.alloc_grid(8, 8, nf=3)
+    assert lib.plbm_set_indices(g2._h, 1, 2, -1) == 0 and (g2.iold, g2.inew, g2.imid) == (1, 2, -1)
+    assert lib.plbm_set_indices(g2._h, 1, 1, -1) != 0 and lib.plbm_set_indices(g2._h, 3, 1, 2) != 0
+    assert lib.plbm_set_indices(g3._h, 3, 1, 2) == 0 and (g3.iold, g3.inew, g3.imid) == (3, 1, 2)
+    assert lib.plbm_set_indices(g3._h, 3, 3, 2) != 0 and lib.plbm_set_indices(g3._h, 0, 1, 2) != 0
+    assert (g3.iold, g3.inew, g3.imid) == (3, 1, 2)
+    plbm.dealloc_grid(g2)
+    plbm.dealloc_grid(g3)
+
+
+def test_diagnostics_propagate_nan(plbm):
+    """a diverged field must not report max|u| = 0 / min|u| = 1e300 (fmax / fmin drop NaN)."""
+    g = plbm.alloc_grid(24, 20)
+    plbm.set_properties(g, 0.02, 1.0, 0.25)
+    g.rho[:], g.ux[:], g.uy[:] = 1.0, 0.01, 0.02
+    g.ux[7, 3] = np.nan
+    plbm.set_pdf_to_equilibrium(g)
+    plbm.update_macros(g, lagged=False)
+    d = g.diagnostics()
+    assert np.isnan(d["max_speed"]) and np.isnan(d["min_speed"]) and np.isnan(d["sum_rho"]) and np.isnan(d["kinetic_energy"])
+    g.ux[7, 3] = 0.01
+    plbm.set_pdf_to_equilibrium(g)
+    plbm.update_macros(g, lagged=False)
+    d = g.diagnostics()
+    assert d["max_speed"] == pytest.approx(np.hypot(0.01, 0.02), rel=1e-12) and d["min_speed"] == pytest.approx(np.hypot(0.01, 0.02), rel=1e-12)
+    plbm.dealloc_grid(g)
+
+
+def test_unfused_dugks_stream_after_a_fused_step(plbm):
+    """after a fused perform_dugks_step lattice inew must behave as the reference's fbar+ for an unfused
+    dugks_stream too (it used to read ftilde^n and leave the pending half-step collision behind)."""
+    nx, ny = 36, 44
+    og, g = make_pair(plbm, nx, ny, "f64", dt=0.3)
+    p = og.props
+    plbm.perform_dugks_step(g, 2)
+    og.run(Oracle.SCHEME_DUGKS, Oracle.BGK, 2)
+    plbm.dugks_stream(g)          # unfused pass on the lattices as the fused steps left them
+    og.o.dugks_stream(og.lattice(og.iold), og.lattice(og.inew), ny, p["tau"], p["dt"], True)
+    for k in (1, 2):
+        assert np.array_equal(g.download_f(k)[:, :, :ny], og.lattice(k)[:, :, :ny])
+    plbm.dealloc_grid(g)
+
+
 def test_error_paths(plbm):
     with pytest.raises(plbm.PlbmError):
         plbm.alloc_grid(0, 8)
