@@ -4,22 +4,22 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 Metric (BASELINE.json): MLUPS = lattice updates / microsecond (app/main_taylor_green.f90:122) of the
-D2Q9 fp64 stream+collide step, whole job over all N GPUs, plus achieved HBM GB/s against the
-measured peak (144 B per lattice update: 9 reads + 9 writes of 8 bytes).
+D2Q9 stream+collide step, whole job over all N GPUs, plus achieved HBM GB/s against the
+measured peak (144 B per lattice update in fp64 / 72 B in fp32: 9 reads + 9 writes).
 
 Default workload = BASELINE.json configs[4], the configuration the metric is quoted on at
 1/2/4/8 GPUs: D2Q9 BGK fp64, slab decomposition along the slow index, WEAK scaling with a
 32768 (unit-stride) x 4096 (slow) slab per GPU -- at N = 8 this is the full 32768 x 32768 grid.
-One "step" = one fused stream+collide pass over the whole grid.
+One "step" = one fused stream+collide pass over the whole grid.  The other BASELINE configs are
+selectable with --workload (C1 64^2 BGK, C2 1024^2 TRT, C3 8192^2 RR fp64/fp32, C4 2048^2 DUGKS).
 
 For N > 1 the driver launches this file with torch.distributed.run, one rank per GPU; ranks
-exchange one halo line of three populations per direction per step (inside libplbm_b200.so: peer
-stores over NVLink through CUDA IPC mappings, or NCCL send/recv as fallback), overlapped with the
-interior update.
+exchange two halo lines per direction per launch (inside libplbm_b200.so: peer stores over NVLink
+through CUDA IPC mappings, or NCCL send/recv as fallback), overlapped with the interior update.
 
 `--impl reference` times the reference's own CPU algorithm (the line-faithful C/OpenMP restatement
 in oracle/, because the Fortran reference cannot be compiled in this image -- no gfortran) with all
-host threads on a bounded sample of the same workload.
+host threads on a bounded SAMPLE of the same workload (stated in cpu_baseline.sample).
 """
 from __future__ import annotations
 
@@ -29,7 +29,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,17 +36,33 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# name: ny (unit stride), nx per GPU (negative: global, split over the ranks), scheme, collision, precision
 WORKLOADS = {
-    # name: (ny_fast, nx_slow_per_gpu, collision, precision, description)
-    "c5_bgk_f64_slab": (32768, 4096, "bgk", "f64", "C5 D2Q9 BGK fp64 Taylor-Green, y-slab weak scaling, 32768 x 4096 lines per GPU"),
-    # strong scaling of the full C5 grid: nx_slow_per_gpu = 32768 / N (154.6 GB of PDFs on one GPU)
-    "c5_bgk_f64_strong": (32768, -32768, "bgk", "f64", "C5 D2Q9 BGK fp64 Taylor-Green 32768 x 32768, y-slab STRONG scaling"),
-    "c3_rr_f64_8192": (8192, 8192, "rr", "f64", "C3 D2Q9 recursive-regularized fp64 Taylor-Green 8192 x 8192 per GPU"),
-    "c3_rr_f32_8192": (8192, 8192, "rr", "f32", "C3 D2Q9 recursive-regularized fp32 Taylor-Green 8192 x 8192 per GPU"),
-    "c2_trt_f64_1024": (1024, 1024, "trt", "f64", "C2 D2Q9 TRT fp64 1024 x 1024 per GPU"),
-    "c1_bgk_f64_64": (64, 64, "bgk", "f64", "C1 D2Q9 BGK fp64 Taylor-Green 64 x 64 (L2-resident, launch-bound)"),
+    "c5_bgk_f64_slab": dict(ny=32768, nxl=4096, scheme="lbm", collision="bgk", precision="f64",
+                            desc="C5 D2Q9 BGK fp64 Taylor-Green, y-slab weak scaling, 32768 x 4096 lines per GPU"),
+    # strong scaling of the full C5 grid: nx per GPU = 32768 / N (154.6 GB of PDFs on one GPU)
+    "c5_bgk_f64_strong": dict(ny=32768, nxl=-32768, scheme="lbm", collision="bgk", precision="f64",
+                              desc="C5 D2Q9 BGK fp64 Taylor-Green 32768 x 32768, y-slab STRONG scaling"),
+    "c3_rr_f64_8192": dict(ny=8192, nxl=8192, scheme="lbm", collision="rr", precision="f64",
+                           desc="C3 D2Q9 recursive-regularized fp64 Taylor-Green 8192 x 8192 per GPU"),
+    "c3_rr_f32_8192": dict(ny=8192, nxl=8192, scheme="lbm", collision="rr", precision="f32",
+                           desc="C3 D2Q9 recursive-regularized fp32 Taylor-Green 8192 x 8192 per GPU"),
+    "c2_trt_f64_1024": dict(ny=1024, nxl=1024, scheme="lbm", collision="trt", precision="f64",
+                            desc="C2 D2Q9 TRT fp64 1024 x 1024 per GPU"),
+    "c1_bgk_f64_64": dict(ny=64, nxl=64, scheme="lbm", collision="bgk", precision="f64",
+                          desc="C1 D2Q9 BGK fp64 Taylor-Green 64 x 64 (L2-resident, launch-bound)"),
+    # C4: DUGKS (src/periodic_dugks.F90:25-38, built with -DDUGKS), dt = 5 tau
+    "c4_dugks_f64_2048": dict(ny=2048, nxl=2048, scheme="dugks", collision="bgk", precision="f64",
+                              desc="C4 DUGKS Taylor-Green fp64 2048 x 2048 per GPU (perform_dugks_step, -DDUGKS branch), dt = 5 tau"),
+    "c4_dugks_f32_2048": dict(ny=2048, nxl=2048, scheme="dugks", collision="bgk", precision="f32",
+                              desc="C4 DUGKS Taylor-Green fp32 2048 x 2048 per GPU (perform_dugks_step, -DDUGKS branch), dt = 5 tau"),
+    # what app/main_vortex.f90 runs: stream_fvm_bardow + collide_bgk through perform_step
+    "c4_fvm_bardow_f64_2048": dict(ny=2048, nxl=2048, scheme="fvm_bardow", collision="bgk", precision="f64",
+                                   desc="Bardow FVM + BGK fp64 2048 x 2048 per GPU (perform_step: stream_fvm_bardow + collide_bgk), dt = 5 tau"),
 }
 BYTES_PER_LUP = {"f64": 144, "f32": 72}
+# the reference author's own three-pass accounting for DUGKS (sim/standard_lbm.F90:331): 9 * 8 * 2 * 3 bytes per update
+REF_DUGKS_BYTES_PER_LUP = {"f64": 432, "f32": 216}
 CPU_SAMPLE_LINES = 512  # lines of the slab timed on the CPU (bounded sample)
 
 
@@ -59,15 +74,18 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_lup(workload, kernel="k_lbm2"):
-    """dram bytes (read+write) per lattice update of the dominant kernel, from the committed ncu
-    --set full capture summarised in profiles/ncu_summary.json (None when that kernel was not captured
-    on this workload).  Keys: `<workload>` for k_lbm2, `<workload>@<kernel>` for the others."""
+def ncu_traffic_per_lup(workload, kernel):
+    """dram bytes (read+write) per lattice update of the dominant kernel, from the committed ncu --set full capture
+    summarised in profiles/ncu_summary.json (None when that kernel was not captured on this workload).  Keys:
+    `<workload>@<kernel>`, or `<workload>` for k_lbm2.  DRAM bytes cannot be counted outside a profiler, so this is a
+    constant of the committed capture, not an in-run measurement; `roofline.traffic_source` says so."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as fh:
-            return float(json.load(fh)[workload if kernel == "k_lbm2" else f"{workload}@{kernel}"]["dram_bytes_per_lup"])
+            d = json.load(fh)
+        e = d.get(f"{workload}@{kernel}") or (d.get(workload) if kernel == "k_lbm2" else None)
+        return (float(e["dram_bytes_per_lup"]), e.get("source", "profiles/ncu_summary.json")) if e else (None, None)
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -120,13 +138,25 @@ class ClockSampler:
         return out
 
 
+def config_of(name, world):
+    """the `config` object both arms print (same keys and values, so the two lines are comparable)"""
+    w = WORKLOADS[name]
+    strong = w["nxl"] < 0
+    nxl = -w["nxl"] // world if strong else w["nxl"]
+    return {"workload": name, "description": w["desc"], "scheme": w["scheme"], "ny_fast": w["ny"], "nx_slow_per_gpu": nxl,
+            "nx_slow_global": nxl * world, "collision": w["collision"], "lattice": "D2Q9, two lattices, SoA f(ld,nx,0:8)"}
+
+
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_mlups(ny, collision, precision, seconds_budget, steps=None, warmup=1):
-    """Reference CPU path (stream sweep + collide sweep, OpenMP over x, same layout) on a bounded
-    sample: CPU_SAMPLE_LINES lines of the ny-wide slab.  Only place bench.py executes oracle/."""
+def cpu_reference_mlups(workload, seconds_budget, steps=None, warmup=1):
+    """Reference CPU path (separate stream and collide sweeps / DUGKS collide + stream passes, OpenMP over x, same layout)
+    on a bounded SAMPLE: at most CPU_SAMPLE_LINES lines of the ny-wide grid.  The only place bench.py executes oracle/."""
     from oracle.oracle import Oracle, OracleGrid, taylor_green_setup
 
-    nx = min(CPU_SAMPLE_LINES, ny)
+    w = WORKLOADS[workload]
+    ny, precision, collision, scheme = w["ny"], w["precision"], w["collision"], w["scheme"]
+    nx_full = abs(w["nxl"])
+    nx = min(CPU_SAMPLE_LINES, nx_full)
     og = OracleGrid(nx, ny, precision, omp=True)
     o = og.o
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it)
@@ -135,25 +165,28 @@ def cpu_reference_mlups(ny, collision, precision, seconds_budget, steps=None, wa
     except Exception:
         o.set_num_threads(os.cpu_count() or 1)
     cores = o.num_threads()
-    s = taylor_green_setup(o, ny, dt=1.0)
+    s = taylor_green_setup(o, ny, dt=1.0) if scheme == "lbm" else taylor_green_setup(o, ny, dt_over_tau=5.0)
     og.set_properties(s["nu"], s["dt"], magic=0.25)
     og.rho[:] = 1.0
     og.ux[:] = 0.01
     og.uy[:] = -0.02
     og.set_pdf_to_equilibrium()
     coll = {"bgk": Oracle.BGK, "trt": Oracle.TRT, "rr": Oracle.RR}[collision]
-    og.run(Oracle.SCHEME_LBM, coll, warmup)
-    t0 = time.perf_counter()
-    og.run(Oracle.SCHEME_LBM, coll, 1)
-    t1 = time.perf_counter() - t0
+    sch = {"lbm": Oracle.SCHEME_LBM, "dugks": Oracle.SCHEME_DUGKS, "fvm_bardow": Oracle.SCHEME_FVM_BARDOW}[scheme]
+    og.run(sch, coll, max(1, warmup))
     if steps is None:
+        t0 = time.perf_counter()
+        og.run(sch, coll, 1)
+        t1 = time.perf_counter() - t0
         steps = max(2, min(200, int(seconds_budget / max(t1, 1e-6))))
     t0 = time.perf_counter()
-    og.run(Oracle.SCHEME_LBM, coll, steps)
+    og.run(sch, coll, steps)
     dt = time.perf_counter() - t0
     mlups = nx * ny * steps / dt * 1e-6
-    sample = (f"{ny} x {nx} lines of the slab (1/{max(1, 4096 // nx)} of one GPU's share), {steps} steps, "
-              f"separate stream + collide sweeps like the reference, OpenMP {cores} threads")
+    passes = {"lbm": "separate stream + collide sweeps", "dugks": "copy + two collision passes + flux pass",
+              "fvm_bardow": "separate flux-streaming + collide sweeps"}[scheme]
+    sample = (f"SAMPLED: {ny} x {nx} lines (1/{max(1, nx_full // nx)} of one GPU's {ny} x {nx_full} share; uniform initial state), "
+              f"{steps} steps, {passes} like the reference, OpenMP {cores} threads")
     return mlups, cores, sample, dt / steps * 1e3, steps
 
 
@@ -161,18 +194,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ny, nxl, collision, precision, desc = WORKLOADS[args.workload]
-    nxl = abs(nxl)
-    steps = args.steps if args.steps else None
-    # keep the whole run within a few minutes: cap the number of timed steps
-    mlups, cores, sample, ms, steps = cpu_reference_mlups(ny, collision, precision, 20.0, steps=min(steps, 100) if steps else None,
-                                                          warmup=max(1, min(args.warmup, 3)))
+    w = WORKLOADS[args.workload]
+    K = min(args.steps, 1000) if args.steps > 0 else None
+    W = max(1, args.warmup)
+    mlups, cores, sample, ms, steps = cpu_reference_mlups(args.workload, 20.0, steps=K, warmup=W)
+    cfg = config_of(args.workload, max(1, args.gpus))
+    cfg["note"] = "CPU run on rank 0's host cores; does not use the GPUs, value does not scale with n_gpus"
     line = {
         "impl": "reference", "metric": "MLUPS", "value": round(mlups, 2), "unit": "MLUPS (1e6 lattice updates/s)",
-        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": round(ms, 3), "higher_is_better": True,
-        "scaling": "strong" if WORKLOADS[args.workload][1] < 0 else "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "ny_fast": ny, "nx_slow_per_gpu": nxl, "collision": collision,
-                   "note": "CPU run does not use the GPUs; value does not scale with n_gpus"},
+        "n_gpus": args.gpus, "steps": steps, "warmup": W, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "strong" if w["nxl"] < 0 else "weak", "vs_baseline": None, "dtype": w["precision"], "data": "synthetic",
+        "config": cfg, "sampled": True,
         "cpu_baseline": {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample,
                          "why_port": "reference is Fortran; no Fortran compiler in this image (SURVEY F1): timed the line-faithful C/OpenMP restatement (oracle/)"},
         "e2e": {"value": round(mlups, 2), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -201,33 +233,56 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    ny, nxl, collision, precision, desc = WORKLOADS[args.workload]
+    w = WORKLOADS[args.workload]
+    ny, nxl, scheme, collision, precision = w["ny"], w["nxl"], w["scheme"], w["collision"], w["precision"]
     strong = nxl < 0
     if strong:  # fixed global grid, split over the ranks
         nxl = -nxl // world
     nx_global = nxl * world
     dtype = np.float64 if precision == "f64" else np.float32
-    stream = torch.cuda.Stream()
-
-    g = p.alloc_grid(nxl, ny, nf=2, precision=precision, device=local)
-    g.set_stream(stream.cuda_stream)
-    g.collision = {"bgk": p.collide_bgk, "trt": p.collide_trt, "rr": p.collide_rr}[collision]
-    g.streaming = p.lbm_stream
-    # Taylor-Green on the GLOBAL grid: umax = 0.01/sqrt(3), Re = 100, dt = 1
     T = dtype
+    stream = torch.cuda.Stream()
+    tdt = torch.float64 if precision == "f64" else torch.float32
+
+    # Taylor-Green: umax = 0.01/sqrt(3), Re = 100; LBM: dt = 1; DUGKS / Bardow FVM: dt = 5 tau
     umax = T(0.01) / np.sqrt(T(3))
     nu = umax * T(ny) / T(100)
-    kx = T(2) * T(np.pi) / T(nx_global)
+    dt_step = T(1) if scheme == "lbm" else T(5) * (T(3) * nu)
     ky = T(2) * T(np.pi) / T(ny)
-    tg = p.TaylorGreen(nx_global, ny, kx, ky, umax, nu, dtype=dtype)
-    p.set_properties(g, nu, 1.0, magic=0.25)
+
+    def make_grid(n_lines, device):
+        g = p.alloc_grid(n_lines, ny, nf=2, precision=precision, device=device)
+        g.set_stream(stream.cuda_stream)
+        g.collision = {"bgk": p.collide_bgk, "trt": p.collide_trt, "rr": p.collide_rr}[collision]
+        g.streaming = {"lbm": p.lbm_stream, "fvm_bardow": p.stream_fvm_bardow, "dugks": None}[scheme]
+        if scheme == "dugks":
+            g.collision = None
+        p.set_properties(g, nu, dt_step, magic=0.25)
+        if args.variant:
+            g.set_variant(args.variant)
+        return g
+
+    g = make_grid(nxl, local)
+    if scheme == "lbm":
+        step = lambda n, gg=None: p.perform_lbm_step(gg or g, n)  # noqa: E731
+    elif scheme == "dugks":
+        step = lambda n, gg=None: p.perform_dugks_step(gg or g, n)  # noqa: E731
+    else:
+        step = lambda n, gg=None: p.perform_step(gg or g, n)  # noqa: E731
 
     # pinned host buffers for the macroscopic fields (the only data that crosses the boundary)
-    pin = [torch.empty((nxl, ny), dtype=torch.float64 if precision == "f64" else torch.float32, pin_memory=True) for _ in range(3)]
+    pin = [torch.empty((nxl, ny), dtype=tdt, pin_memory=True) for _ in range(3)]
     g.rho, g.ux, g.uy = (t.numpy() for t in pin)
-    tg.eval(0.0, x_offset=rank * nxl, nx_local=nxl, out=(g.rho, g.ux, g.uy))
-    g.rho[:] = g.rho / g.csqr + T(1)  # app/main_taylor_green.f90:145
 
+    def fill_ic(period_lines, x_offset):
+        """Taylor-Green with wavelength `period_lines` along x, evaluated on this rank's lines"""
+        tg = p.TaylorGreen(period_lines, ny, T(2) * T(np.pi) / T(period_lines), ky, umax, nu, dtype=dtype)
+        tg.eval(0.0, x_offset=x_offset, nx_local=nxl, out=(g.rho, g.ux, g.uy))
+        g.rho[:] = g.rho / g.csqr + T(1)  # app/main_taylor_green.f90:145
+
+    fill_ic(nx_global, rank * nxl)
+
+    transport = None
     if world > 1:
         from periodic_lbm_b200.capi import check, lib
         import ctypes as C
@@ -249,125 +304,187 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def timed(fn):
+        """device time of fn() on the library's stream, barrier + synchronize on both sides, max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        barrier()
+        return allmax([e0.elapsed_time(e1)])[0]
+
     p.set_pdf_to_equilibrium(g)
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- device-resident timing: `value` ---------------------------------------------------
-    p.perform_lbm_step(g, W)
+    step(W)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.12)
     l0 = p.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    p.perform_lbm_step(g, K)
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = timed(lambda: step(K))
     launches = p.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_total, launches = float(tmax[0]), int(tsum[1])
+        t = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t[0])
     ms_step = ms_total / K
     nodes_global = nx_global * ny
+    nodes_local = nxl * ny
     mlups = nodes_global / ms_step * 1e-3
-    # per-launch duration of the two kernels of the path (roofline), events on the launching stream
+
+    # ---- per-launch duration of the dominant kernel (roofline), events on the launching stream, median of 7 ---------
     def call_ms(nsteps):
-        ts = []
-        for _ in range(7):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a0.record(stream)
-            p.perform_lbm_step(g, nsteps)
-            a1.record(stream)
-            torch.cuda.synchronize()
-            ts.append(a0.elapsed_time(a1))
-        return sorted(ts)[len(ts) // 2]
-    pair_kernel_ms = None
-    if world == 1:
+        return sorted(timed(lambda: step(nsteps)) for _ in range(7))[3]
+
+    if scheme == "lbm":
+        # a 3-step call (one two-step launch + one k_lbm) minus a 1-step call (one k_lbm); under a ring the same
+        # difference is the boundary + interior launches of one pair (every rank issues the same sequence)
         t1, t3 = call_ms(1), call_ms(3)
-        pair_kernel_ms = (t3 - t1, t1)
-    else:  # under a ring the launches are split in boundary + interior: use the step average
-        pair_kernel_ms = (2 * ms_step, ms_step)
-    # physics sanity inside the bench: mass is conserved to round-off
+        dom_ms, dom_steps, single_ms = t3 - t1, 2, t1
+        dom_kernel = g.pair_kernel()
+        if dom_kernel == "k_lbm":  # grids the two-step kernels do not take: one step per launch
+            dom_ms, dom_steps = t1, 1
+    else:
+        t1, t5 = call_ms(1), call_ms(5)
+        dom_ms, dom_steps, single_ms = (t5 - t1) / 4, 1, t1
+        dom_kernel = {"dugks": "k_fv_tma<MODE_DUGKS>", "fvm_bardow": "k_fv_tma<MODE_BARDOW>"}[scheme]
+        if args.variant == 4:
+            dom_kernel = {"dugks": "k_fv_march<MODE_DUGKS>", "fvm_bardow": "k_fv_march<MODE_BARDOW>"}[scheme]
+
+    # ---- one step per call, the way the reference drivers call (app/main_taylor_green.f90:98-119) ---------------------
+    per_call = None
+    if scheme == "lbm":
+        ncalls = K
+        def calls():
+            for _ in range(ncalls):
+                step(1)
+        ms_eager = timed(calls)
+        per_call = {"calls": ncalls, "eager": {"ms_per_step": round(ms_eager / ncalls, 4), "mlups": round(nodes_global * ncalls / ms_eager * 1e-3, 1),
+                                               "what": "K x perform_lbm_step(1), default (eager): one k_lbm launch per call"}}
+        if world == 1:  # deferral is a single-GPU feature (a ring must issue identical launch sequences on every rank)
+            g.set_step_deferral(64)
+            def calls_deferred():
+                for _ in range(ncalls):
+                    step(1)
+                g.synchronize()  # any observer runs what is pending; the flush is inside the timed region
+            ms_def = timed(calls_deferred)
+            g.set_step_deferral(0)
+            per_call["deferred"] = {"ms_per_step": round(ms_def / ncalls, 4), "mlups": round(nodes_global * ncalls / ms_def * 1e-3, 1),
+                                    "what": "K x perform_lbm_step(1) with plbm_set_step_deferral(64) (on in the Fortran shim): the calls are counted "
+                                            "and run batched, two steps per pass over HBM, when 64 are pending or anything looks at the grid"}
+
+    # physics sanity inside the bench: mass is conserved to round-off (GLOBAL sum under a ring)
     p.update_macros(g, lagged=False)
     mass = float(g.diagnostics()["sum_rho"])
 
     # ---- end-to-end through the C ABI with host buffers: `e2e` ------------------------------
     # One driver cycle as the reference apps run it (app/main_taylor_green.f90:133-149, 98-118):
-    #   set_pdf_to_equilibrium(host rho,ux,uy) -> K x perform_lbm_step -> update_macros(host)
+    #   set_pdf_to_equilibrium(host rho,ux,uy) -> K steps -> update_macros(host)
     # H2D = 3 fields, D2H = 3 fields per cycle, from/to pinned host memory, all inside the timing.
-    tg.eval(0.0, x_offset=rank * nxl, nx_local=nxl, out=(g.rho, g.ux, g.uy))
-    g.rho[:] = g.rho / g.csqr + T(1)
-    barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    c0.record(stream)
-    p.set_pdf_to_equilibrium(g)
-    p.perform_lbm_step(g, K)
-    p.update_macros(g)  # lagged, like the reference driver
-    c1.record(stream)
-    barrier()
-    e2e_wall_ms = (time.perf_counter() - w0) * 1e3
-    e2e_ms = max(c0.elapsed_time(c1), 0.0)
-    t = torch.tensor([e2e_ms, e2e_wall_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t[0])
+    fill_ic(nx_global, rank * nxl)
+    def cycle():
+        p.set_pdf_to_equilibrium(g)
+        step(K)
+        p.update_macros(g)  # lagged, like the reference driver
+    e2e_ms = timed(cycle)
     field_bytes = nxl * ny * np.dtype(dtype).itemsize * 3
     e2e_mlups = nodes_global * K / e2e_ms * 1e-3
 
-    line = None
+    # ---- selfcheck: the slabs of the ring hold the single-GPU result, bit for bit ---------------------------------------
+    # Initial condition periodic along x with period nx_slow_per_gpu, so every slab of the ring sees exactly what a single
+    # GPU sees whose own periodic domain is that slab: after the same call every rank's lattice must have the same 64-bit
+    # checksum (plbm_lattice_hash, computed on the device) as that single-GPU run -- which rank 0 performs here, in the same
+    # process, on a second grid without a ring.  The hash is therefore also equal across N = 1, 2, 4, 8 of a weak-scaling run.
+    KS = 7 if scheme == "lbm" else 3
+    fill_ic(nxl, 0)
+    p.set_pdf_to_equilibrium(g)
+    step(KS)
+    h_ring = g.lattice_hash(g.iold)
+    hashes = [h_ring]
+    if world > 1:
+        t = torch.tensor([h_ring & 0xFFFFFFFF, h_ring >> 32], dtype=torch.int64, device="cuda")
+        allh = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        hashes = [int(a[0]) | (int(a[1]) << 32) for a in allh]
+    selfcheck = None
+    if rank == 0:
+        h_single = h_ring
+        if world > 1:
+            try:
+                g1 = make_grid(nxl, local)
+            except p.PlbmError:  # no room for a second slab next to the first (strong scaling at N = 2)
+                g1, h_single = None, None
+            if g1 is not None:
+                g1.rho, g1.ux, g1.uy = g.rho, g.ux, g.uy
+                p.set_pdf_to_equilibrium(g1)
+                step(KS, g1)
+                h_single = g1.lattice_hash(g1.iold)
+                p.dealloc_grid(g1)
+        selfcheck = {"hash": f"{h_ring:016x}", "ranks_equal": len(set(hashes)) == 1,
+                     "single_gpu_hash": None if h_single is None else f"{h_single:016x}",
+                     "equals_single_gpu": None if h_single is None else all(h == h_single for h in hashes), "steps": KS,
+                     "what": f"Taylor-Green periodic over the {nxl} lines of one slab; {KS} steps in one call; plbm_lattice_hash(iold) of every rank "
+                             "vs the same slab stepped alone on one GPU in this run"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         bpl = BYTES_PER_LUP[precision]
-        # Dominant kernel: k_lbm2, TWO fused stream+collide steps per launch (temporal blocking through a
-        # shared-memory ring); a K-step call runs (K-1)//2 of them and finishes with 1-2 single-step k_lbm
-        # launches.  Its launch duration is measured live below (CUDA events on its stream): a 3-step call
-        # (one k_lbm2 + one k_lbm) minus a 1-step call (one k_lbm), median of 7.
-        # algorithmic bytes = 9 reads + 9 writes per node PER STEP, so frac > 1 means the
-        # kernel moves fewer HBM bytes than the one-step-per-pass algorithm can; `traffic` (ncu) and
-        # `dram_frac` say how close the bytes it does move are to the HBM roof.
-        nodes_local = nxl * ny
-        pair_ms, single_ms = pair_kernel_ms
-        achieved = 2 * nodes_local * bpl / (pair_ms * 1e-3) / 1e9
-        pair_kernel = g.pair_kernel()  # k_lbm2 (raw columns by per-thread loads) or k_lbm2_bulk (by bulk async copies)
-        tr = ncu_traffic_per_lup(args.workload, pair_kernel)
-        traffic = None if tr is None else round(tr * 2 * nodes_local)
+        # algorithmic bytes (SURVEY 8d) = 9 reads + 9 writes per node PER STEP, so for the two-step LBM kernels frac > 1 means
+        # the kernel moves fewer HBM bytes than a one-step-per-pass algorithm can; `traffic` (ncu) and `dram_frac` say how
+        # close the bytes it does move are to the HBM roof.
+        achieved = dom_steps * nodes_local * bpl / (dom_ms * 1e-3) / 1e9
+        tr, tr_src = ncu_traffic_per_lup(args.workload, dom_kernel.split("<")[0])
+        traffic = None if tr is None else round(tr * dom_steps * nodes_local)
+        cfg = config_of(args.workload, world)
+        stepping = {"lbm": f"one perform_lbm_step(K={K}) call: {(K - 1) // 2} two-step launches + {K - 2 * ((K - 1) // 2)} single-step launches, bit-identical to K single steps",
+                    "dugks": f"one perform_dugks_step(K={K}) call: one fused launch per step (collide + face reconstruction + face relaxation + flux update)",
+                    "fvm_bardow": f"one perform_step(K={K}) call: one fused launch per step (stream_fvm_bardow + collide_bgk)"}[scheme]
+        cfg.update({"stepping": stepping, "variant": args.variant,
+                    "halo": f"2 lines x 9 populations per direction per launch, overlapped with the interior update; transport: {transport}" if world > 1 else "none (periodic index wrap)",
+                    "l2": f"inputs vs L2: {2 * 9 * nxl * ny * np.dtype(dtype).itemsize / 1e9:.3f} GB of PDFs per GPU vs 126 MB L2"
+                          + (" (larger than L2: no flush needed)" if 2 * 9 * nxl * ny * np.dtype(dtype).itemsize > 4 * 126e6 else " (L2-resident: a launch/latency figure, not a roofline case)"),
+                    "mass_sum_rho": mass})
         line = {
             "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS (1e6 lattice updates/s)", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": precision,
-            "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "ny_fast": ny, "nx_slow_per_gpu": nxl, "nx_slow_global": nx_global,
-                       "collision": collision, "lattice": "D2Q9, two lattices, SoA f(ld,nx,0:8)",
-                       "stepping": f"one perform_lbm_step(K={K}) call: {(K - 1) // 2} two-step launches + {K - 2 * ((K - 1) // 2)} single-step launches, bit-identical to K single steps",
-                       "halo": f"2 lines x 9 populations per direction per launch, overlapped with the interior update; transport: {transport}" if world > 1 else "none (periodic index wrap)",
-                       "l2": f"inputs larger than L2: {2 * 9 * nxl * ny * np.dtype(dtype).itemsize / 1e9:.1f} GB of PDFs per GPU vs 126 MB L2 (no flush needed)",
-                       "mass_sum_rho": mass},
-            "clocks": clocks,
+            "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": round(e2e_mlups, 1), "unit": "MLUPS", "h2d_bytes_per_step": int(field_bytes / K), "d2h_bytes_per_step": int(field_bytes / K),
                     "cycle": f"set_pdf_to_equilibrium(host) + {K} steps + update_macros(host) per GPU; {field_bytes} B H2D and {field_bytes} B D2H per cycle (pinned), amortised over the {K} steps",
                     "ms_per_cycle": round(e2e_ms, 3)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 2 * nodes_local * bpl, "kernel": f"{pair_kernel}<two fused stream+collide steps>",
-                         "launch_ms": round(pair_ms, 4), "per_gpu": True,
-                         "dram_frac": None if traffic is None else round(traffic / (pair_ms * 1e-3) / 1e9 / peak, 4),
-                         "single_step_kernel": {"kernel": "k_lbm<fused stream+collide>", "launch_ms": round(single_ms, 4),
-                                                "achieved": round(nodes_local * bpl / (single_ms * 1e-3) / 1e9, 1),
-                                                "frac": round(nodes_local * bpl / (single_ms * 1e-3) / 1e9 / peak, 4)}},
+                         "traffic": traffic, "traffic_source": tr_src and f"ncu --set full capture of this kernel on this workload, {tr_src} (a profiler constant, not measured in this run)",
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_steps * nodes_local * bpl,
+                         "kernel": f"{dom_kernel}<{'two fused stream+collide steps' if dom_steps == 2 else 'one step'}>" if scheme == "lbm" else dom_kernel,
+                         "launch_ms": round(dom_ms, 4), "per_gpu": True,
+                         "dram_frac": None if traffic is None else round(traffic / (dom_ms * 1e-3) / 1e9 / peak, 4)},
+            "selfcheck": selfcheck,
         }
+        if scheme == "lbm":
+            line["roofline"]["single_step_kernel"] = {"kernel": "k_lbm<fused stream+collide>", "launch_ms": round(single_ms, 4),
+                                                      "achieved": round(nodes_local * bpl / (single_ms * 1e-3) / 1e9, 1),
+                                                      "frac": round(nodes_local * bpl / (single_ms * 1e-3) / 1e9 / peak, 4)}
+            line["per_call"] = per_call
+        if scheme == "dugks":
+            ref_bpl = REF_DUGKS_BYTES_PER_LUP[precision]
+            line["roofline"]["vs_reference_3pass_model"] = {
+                "bytes_per_update": ref_bpl, "achieved": round(nodes_local * ref_bpl / (dom_ms * 1e-3) / 1e9, 1),
+                "frac": round(nodes_local * ref_bpl / (dom_ms * 1e-3) / 1e9 / peak, 4),
+                "what": "the reference author's accounting for DUGKS, 9*8*2*3 B per update (sim/standard_lbm.F90:331); `achieved`/`frac` above use the fused lower bound, state in + state out"}
         if world == 1 and not args.no_cpu:
-            v, cores, sample, _, _ = cpu_reference_mlups(ny, collision, precision, 12.0)
+            v, cores, sample, _, _ = cpu_reference_mlups(args.workload, 12.0)
             line["cpu_baseline"] = {"value": round(v, 2), "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -386,6 +503,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5_bgk_f64_slab", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0, help="plbm_set_variant: 0 = default (bit-identical) kernels; see include/plbm.h")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -165,6 +165,10 @@ int plbm_l2_sums(plbm_handle grid, const void* uxa, const void* uya, double out[
 
 /* ---- raw PDF access (checkpoint / tests) ---------------------------------------------- */
 /* which = 1-based lattice index; host buffer is f(ld,nx,0:8) */
+/* 64-bit checksum of lattice `which` (rows 1..ny of every (x,q) line; padding rows excluded), computed on the device:
+ * position-dependent and independent of the reduction order, so equal lattices <=> equal checksums.  Lets a caller compare
+ * device-resident states (two runs, the slabs of a ring against a single-GPU run) without downloading the PDFs. */
+int plbm_lattice_hash(plbm_handle grid, int which, unsigned long long* out);
 int plbm_upload_f(plbm_handle grid, int which, const void* host_f);
 int plbm_download_f(plbm_handle grid, int which, void* host_f);
 

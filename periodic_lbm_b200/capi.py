@@ -51,6 +51,7 @@ SIGNATURES = {
     "plbm_vorticity_host": (_I, [_H, _I, _P, _P, _P]),
     "plbm_diagnostics": (_I, [_H, C.POINTER(_D)]),
     "plbm_l2_sums": (_I, [_H, _P, _P, C.POINTER(_D)]),
+    "plbm_lattice_hash": (_I, [_H, _I, C.POINTER(C.c_ulonglong)]),
     "plbm_upload_f": (_I, [_H, _I, _P]),
     "plbm_download_f": (_I, [_H, _I, _P]),
     "plbm_set_stream": (_I, [_H, _P]),

@@ -187,8 +187,7 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
             int rc;
             if (g.variant == 8 && g.nx >= 8) {
                 // test knob: the launch sequence of the slab decomposition (boundary lines, then the interior) on one GPU
-                rc = launch_lbm_pair<T>(g, src, dst, 0, 2, nullptr, nullptr, model, cp, g.stream);
-                if (!rc) rc = launch_lbm_pair<T>(g, src, dst, g.nx - 2, g.nx, nullptr, nullptr, model, cp, g.stream);
+                rc = launch_lbm_pair_boundaries<T>(g, src, dst, 2, nullptr, nullptr, model, cp, g.stream);
                 if (!rc) rc = launch_lbm_pair<T>(g, src, dst, 2, g.nx - 2, nullptr, nullptr, model, cp, g.stream);
             } else if (g.variant == 11) {
                 rc = launch_lbm_pair_fma<T>(g, src, dst, 0, g.nx, nullptr, nullptr, model, cp, g.stream);  // opt-in, FMA-contracted
@@ -370,6 +369,16 @@ template <typename T> int set_pdf_to_equilibrium_t(Grid& g, const void* rho, con
     if ((rc = upload_field<T>(g, g.ux<T>(), ux))) return rc;
     if ((rc = upload_field<T>(g, g.uy<T>(), uy))) return rc;
     return launch_init_eq<T>(g, g.lat<T>(g.iold), g.stream);
+}
+
+template <typename T> static int vorticity_t(Grid& g, int order, void* omega)
+{
+    int rc;
+    const T *lo = nullptr, *hi = nullptr;
+    // slab decomposition: the neighbours' two nearest lines of uy (every rank of the ring calls this)
+    if (g.comm && (rc = comm_field_exchange2<T>(g, g.uy<T>(), &lo, &hi))) return rc;
+    if ((rc = launch_vorticity<T>(g, order, g.ux<T>(), g.uy<T>(), (T*)g.aux, g.stream, lo, hi))) return rc;
+    return download_field<T>(g, omega, (T*)g.aux);
 }
 
 }  // namespace
@@ -789,18 +798,12 @@ int plbm_vorticity(plbm_handle g, int order, void* omega)
 {
     int rc = check(g);
     if (rc) return rc;
-    if (g->comm) {
-        set_error("vorticity: single-GPU only (gather the macroscopic fields first)");
+    if (order != 2 && order != 4) {
+        set_error("vorticity: order must be 2 or 4");
         return PLBM_ERR_ARG;
     }
     if ((rc = need_aux(*g, 1))) return rc;
-    if (g->prec == PLBM_F64) {
-        if ((rc = launch_vorticity<double>(*g, order, g->ux<double>(), g->uy<double>(), (double*)g->aux, g->stream))) return rc;
-        if ((rc = download_field<double>(*g, omega, (double*)g->aux))) return rc;
-    } else {
-        if ((rc = launch_vorticity<float>(*g, order, g->ux<float>(), g->uy<float>(), (float*)g->aux, g->stream))) return rc;
-        if ((rc = download_field<float>(*g, omega, (float*)g->aux))) return rc;
-    }
+    if ((rc = DISPATCH(g, vorticity_t<double>(*g, order, omega), vorticity_t<float>(*g, order, omega)))) return rc;
     if (omega) PLBM_CUDA(cudaStreamSynchronize(g->stream));
     return PLBM_OK;
 }
@@ -852,6 +855,19 @@ int plbm_l2_sums(plbm_handle g, const void* uxa, const void* uya, double out[2])
     if ((rc = upload_field<float>(*g, (float*)g->aux, uxa))) return rc;
     if ((rc = upload_field<float>(*g, (float*)g->aux2, uya))) return rc;
     return launch_l2_sums<float>(*g, (const float*)g->aux, (const float*)g->aux2, out, g->stream);
+}
+
+int plbm_lattice_hash(plbm_handle g, int which, unsigned long long* out)
+{
+    int rc = check(g);
+    if (rc) return rc;
+    if (which < 1 || which > g->nf || !out) {
+        set_error("lattice_hash: bad lattice index or null pointer");
+        return PLBM_ERR_ARG;
+    }
+    if (which == g->inew && (rc = materialize_inew(*g))) return rc;
+    return DISPATCH(g, launch_lattice_hash<double>(*g, g->lat<double>(which), out, g->stream),
+                    launch_lattice_hash<float>(*g, g->lat<float>(which), out, g->stream));
 }
 
 int plbm_upload_f(plbm_handle g, int which, const void* host_f)

@@ -63,10 +63,12 @@ template <typename T> int launch_macros(const Grid& g, const T* f, cudaStream_t 
 }
 
 // ---- vorticity ---------------------------------------------------------------------------
-// Single-GPU periodic wrap in both directions (the multi-GPU slab path gathers macros first).
+// Periodic wrap in both directions on one GPU.  Under a slab decomposition the x-derivative of uy reaches into the ring
+// neighbours' slabs: their two nearest lines of uy arrive in uy_lo (lines -2, -1) and uy_hi (lines nx, nx + 1), [2][ny] each.
 template <typename T, int ORDER>
 __global__ void __launch_bounds__(256) k_vorticity(const T* __restrict__ ux, const T* __restrict__ uy,
-                                                   T* __restrict__ om, int nx, int ny)
+                                                   T* __restrict__ om, int nx, int ny, const T* __restrict__ uy_lo,
+                                                   const T* __restrict__ uy_hi)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int x = (int)(g / (size_t)ny);
@@ -74,31 +76,40 @@ __global__ void __launch_bounds__(256) k_vorticity(const T* __restrict__ ux, con
     if (x >= nx) return;
     auto wp = [](int i, int n) { return i >= n ? i - n : i; };
     auto wm = [](int i, int n) { return i < 0 ? i + n : i; };
-    const int xp1 = wp(x + 1, nx), xm1 = wm(x - 1, nx), yp1 = wp(y + 1, ny), ym1 = wm(y - 1, ny);
+    const int yp1 = wp(y + 1, ny), ym1 = wm(y - 1, ny);
 #define M(yy, xx) ((size_t)(xx) * ny + (yy))
+    // uy on line xx in [-2, nx + 1]: the neighbours' lines under a ring, the periodic image otherwise
+    // (mod(x+1,nx)+1 etc. on 1-based indices in the reference; the +-2 neighbours may wrap twice when nx < 2)
+    auto uyx = [&](int xx) -> T {
+        if (uy_lo != nullptr) {
+            if (xx < 0) return uy_lo[M(y, xx + 2)];
+            if (xx >= nx) return uy_hi[M(y, xx - nx)];
+            return uy[M(y, xx)];
+        }
+        return uy[M(y, ((xx % nx) + nx) % nx)];
+    };
     T duydx, duxdy;
     if (ORDER == 2) {
-        duydx = T(0.5) * (uy[M(y, xp1)] - uy[M(y, xm1)]);
+        duydx = T(0.5) * (uyx(x + 1) - uyx(x - 1));
         duxdy = T(0.5) * (ux[M(yp1, x)] - ux[M(ym1, x)]);
     } else {
         const T t1 = T(1) / T(12), t2 = T(2) / T(3);
-        // mod(x+1,nx)+1 etc. on 1-based indices: +-2 neighbours (may wrap twice when n < 2)
-        const int xp2 = (x + 2) % nx, xm2 = (nx + x - 2 + nx) % nx, yp2 = (y + 2) % ny, ym2 = (ny + y - 2 + ny) % ny;
-        duydx = t1 * (uy[M(y, xp1)] - uy[M(y, xm1)]) + t2 * (uy[M(y, xm2)] - uy[M(y, xp2)]);
+        const int yp2 = (y + 2) % ny, ym2 = (ny + y - 2 + ny) % ny;
+        duydx = t1 * (uyx(x + 1) - uyx(x - 1)) + t2 * (uyx(x - 2) - uyx(x + 2));
         duxdy = t1 * (ux[M(yp1, x)] - ux[M(ym1, x)]) + t2 * (ux[M(ym2, x)] - ux[M(yp2, x)]);
     }
 #undef M
     om[(size_t)x * ny + y] = duydx - duxdy;
 }
 
-template <typename T> int launch_vorticity(const Grid& g, int order, const T* ux, const T* uy, T* out, cudaStream_t s)
+template <typename T> int launch_vorticity(const Grid& g, int order, const T* ux, const T* uy, T* out, cudaStream_t s, const T* uy_lo, const T* uy_hi)
 {
     const size_t n = (size_t)g.nx * g.ny;
     const unsigned nb = (unsigned)((n + 255) / 256);
     if (order == 2)
-        k_vorticity<T, 2><<<nb, 256, 0, s>>>(ux, uy, out, g.nx, g.ny);
+        k_vorticity<T, 2><<<nb, 256, 0, s>>>(ux, uy, out, g.nx, g.ny, uy_lo, uy_hi);
     else if (order == 4)
-        k_vorticity<T, 4><<<nb, 256, 0, s>>>(ux, uy, out, g.nx, g.ny);
+        k_vorticity<T, 4><<<nb, 256, 0, s>>>(ux, uy, out, g.nx, g.ny, uy_lo, uy_hi);
     else {
         set_error("vorticity: order must be 2 or 4");
         return PLBM_ERR_ARG;
@@ -254,10 +265,58 @@ template <typename T> int launch_l2_sums(Grid& g, const T* uxa, const T* uya, do
     return PLBM_OK;
 }
 
+// ---- lattice checksum ------------------------------------------------------------------------
+// 64-bit checksum of the rows 0..ny-1 of one lattice (padding rows excluded): sum over all values of
+// splitmix64(bits + golden * local_index), modulo 2^64.  Integer addition commutes, so the result does not depend on the
+// reduction order: two lattices have the same checksum iff (up to 2^-64) they hold the same bits at the same places.
+// Used by bench.py's selfcheck (multi-GPU slabs == the single-GPU result without moving 38 GB to the host) and by tests.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_lattice_hash(const T* __restrict__ f, int nx, int ny, int ld, unsigned long long* __restrict__ out)
+{
+    const size_t n = (size_t)9 * nx * ny;
+    unsigned long long h = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t line = i / ny;            // q * nx + x
+        const int y = (int)(i - line * ny);
+        const T v = f[line * (size_t)ld + y];
+        unsigned long long bits;
+        if (sizeof(T) == 8) bits = (unsigned long long)__double_as_longlong((double)v);
+        else bits = (unsigned long long)__float_as_uint((float)v);
+        h += splitmix64(bits + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
+}
+
+template <typename T> int launch_lattice_hash(Grid& g, const T* f, unsigned long long* out, cudaStream_t s)
+{
+    unsigned long long* dev = static_cast<unsigned long long*>(g.partial);
+    PLBM_CUDA(cudaMemsetAsync(dev, 0, sizeof(unsigned long long), s));
+    const size_t n = (size_t)9 * g.nx * g.ny;
+    int nb = (int)((n + 255) / 256);
+    if (nb > 8 * g.sm_count) nb = 8 * g.sm_count;
+    k_lattice_hash<T><<<nb, 256, 0, s>>>(f, g.nx, g.ny, g.ld, dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLBM_CUDA(cudaGetLastError());
+    PLBM_CUDA(cudaMemcpyAsync(g.partial_host, dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    PLBM_CUDA(cudaStreamSynchronize(s));
+    *out = *static_cast<const unsigned long long*>(g.partial_host);
+    return PLBM_OK;
+}
+template int launch_lattice_hash<double>(Grid&, const double*, unsigned long long*, cudaStream_t);
+template int launch_lattice_hash<float>(Grid&, const float*, unsigned long long*, cudaStream_t);
+
 #define INST(T)                                                                                   \
     template int launch_init_eq<T>(const Grid&, T*, cudaStream_t);                                \
     template int launch_macros<T>(const Grid&, const T*, cudaStream_t);                           \
-    template int launch_vorticity<T>(const Grid&, int, const T*, const T*, T*, cudaStream_t);     \
+    template int launch_vorticity<T>(const Grid&, int, const T*, const T*, T*, cudaStream_t, const T*, const T*); \
     template int launch_diagnostics<T>(Grid&, double[PLBM_DIAG_COUNT], cudaStream_t);             \
     template int launch_l2_sums<T>(Grid&, const T*, const T*, double[2], cudaStream_t);
 INST(double)

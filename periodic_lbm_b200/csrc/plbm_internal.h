@@ -80,6 +80,9 @@ template <typename T> struct LbmArgs {
     T* dst;
     int nx, ny, ld;        // lines in this slab, rows, leading dimension
     int x_begin, x_end;    // lines updated by this launch
+    // two line ranges in one launch (both boundaries of a slab): lines at or beyond x_split are shifted by x_skip, i.e. the
+    // launch covers [x_begin, x_split) and [x_split + x_skip, x_end); no split: x_split = INT_MAX, x_skip = 0
+    int x_split = 0x7fffffff, x_skip = 0;
     // the ring neighbours' two nearest lines, all nine populations, [2][9][ld] each (lo: lines -2, -1;
     // hi: lines nx, nx+1); nullptr = periodic self-wrap by index arithmetic (single GPU)
     const T* halo_lo;
@@ -92,9 +95,12 @@ template <typename T> struct LbmArgs {
 template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream_pdfs, int variant, cudaStream_t s);
 template <typename T> int launch_init_eq(const Grid& g, T* f, cudaStream_t s);
 template <typename T> int launch_macros(const Grid& g, const T* f, cudaStream_t s);
-template <typename T> int launch_vorticity(const Grid& g, int order, const T* ux, const T* uy, T* out, cudaStream_t s);
+template <typename T>
+int launch_vorticity(const Grid& g, int order, const T* ux, const T* uy, T* out, cudaStream_t s, const T* uy_lo = nullptr,
+                     const T* uy_hi = nullptr);  // uy_lo / uy_hi: the ring neighbours' two nearest lines of uy, [2][ny]
 template <typename T> int launch_diagnostics(Grid& g, double out[PLBM_DIAG_COUNT], cudaStream_t s);
 template <typename T> int launch_l2_sums(Grid& g, const T* uxa, const T* uya, double out[2], cudaStream_t s);
+template <typename T> int launch_lattice_hash(Grid& g, const T* f, unsigned long long* out, cudaStream_t s);
 template <typename T>
 int launch_fvm_bardow(const Grid& g, const T* fold, T* fnew, T dt, int model, const CollideParams<T>& cp, cudaStream_t s,
                       int mode = 2 /* 2 Bardow FVM, 4 Bardow FDM (Lax-Wendroff), 5 Sofonea FDM */);
@@ -118,6 +124,9 @@ int lbm_pair_flavour(const Grid& g);  // 0 one step per launch, 1 k_lbm2, 2 k_lb
 template <typename T>
 int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
                     const CollideParams<T>& cp, cudaStream_t s);
+template <typename T>
+int launch_lbm_pair_boundaries(const Grid& g, const T* src, T* dst, int nb, const T* halo_lo, const T* halo_hi, int model,
+                               const CollideParams<T>& cp, cudaStream_t s);  // columns [0, nb) and [nx - nb, nx) in one launch
 template <typename T>
 int launch_lbm_pair_fma(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
                         const CollideParams<T>& cp, cudaStream_t s);  // plbm_lbm2_fma.cu: within tolerance, not bit-identical
@@ -151,6 +160,8 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
 // one FVM/DUGKS halo exchange: all nine populations of lines 0 and nx-1 of `f` -> g.fv_halo_lo/hi
 template <typename T> int comm_fv_exchange(Grid& g, const T* f);
 template <typename T> int launch_halo_pack9(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s);
+// two lines of a macroscopic field ((nx, ny), unpadded) per direction: lines 0, 1 -> rank lo's *hi, lines nx-2, nx-1 -> rank hi's *lo
+template <typename T> int comm_field_exchange2(Grid& g, const T* field, const T** lo, const T** hi);
 
 }  // namespace plbm
 

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256, 3) k_lbm(const LbmArgs<T> a)
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int xrel = (int)(g / (size_t)ldv);
     int x = a.x_begin + xrel;
+    if (x >= a.x_split) x += a.x_skip;  // second range of a split launch (both boundaries of a slab)
     int y0 = ((int)(g - (size_t)xrel * ldv)) * V;
     const bool active = (x < a.x_end) && (y0 < a.ny);
     if (!active) {  // keep the lane alive for the shuffles, on a harmless address
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256, 3) k_lbm(const LbmArgs<T> a)
 
 template <typename T, int MODEL, bool STREAM, int V, int LM> static int launch_one(const LbmArgs<T>& a, cudaStream_t s, bool pre = false)
 {
-    const size_t nthreads = (size_t)(a.x_end - a.x_begin) * (size_t)(a.ld / V);
+    const size_t nthreads = (size_t)(a.x_end - a.x_begin - a.x_skip) * (size_t)(a.ld / V);
     if (nthreads == 0) return PLBM_OK;
     const int block = 256;
     const size_t nblocks = (nthreads + block - 1) / block;

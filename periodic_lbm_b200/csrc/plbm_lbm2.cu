@@ -41,6 +41,7 @@
 // 0.28 per issue), and the kernel moves 6.2-6.4 TB/s of DRAM traffic = 0.95-0.97 of the measured copy peak:
 // BGK / TRT / RR fp64 83.0 / 82.7 / 68.5 GLUPS at 8192^2 (k_lbm2: 63.9 / 64.1 / 58.5), fp32 BGK 147 (119).
 // k_lbm2_bulk is the default; k_lbm2 serves the launches that read a neighbour's halo lines and tiny ny.
+#include <climits>
 #include <cstdint>
 #include <cstdlib>
 
@@ -74,6 +75,9 @@ template <typename T> struct Lbm2Args {
     T* dst;
     int nx, ny, ld;
     int x_begin, x_end;  // columns whose step-2 state this launch writes
+    // two column ranges in one launch (both boundaries of a slab): segments that start at or beyond x_split are shifted by
+    // x_skip columns, i.e. the launch covers [x_begin, x_split) and [x_split + x_skip, x_end); no split: x_split = INT_MAX
+    int x_split, x_skip;
     int ty;              // interior rows per strip (multiple of V)
     int nstrips;         // strips along y
     int seglen;          // columns per x segment
@@ -184,8 +188,12 @@ __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
     const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
     const int y_lo = strip * a.ty;
     const int y_hi = min(y_lo + a.ty, a.ny);
-    const int xs = a.x_begin + seg * a.seglen;
-    const int xe = min(xs + a.seglen, a.x_end);
+    int xs = a.x_begin + seg * a.seglen;
+    int xe = min(xs + a.seglen, min(a.x_split, a.x_end));
+    if (xs >= a.x_split) {  // second range of a split launch (the launcher makes no segment straddle the split)
+        xs += a.x_skip;
+        xe = min(xs + a.seglen, a.x_end);
+    }
     const int t = threadIdx.x;
     const int yl = y_lo - V + t * V;                                    // logical first row of this thread
     const bool act_a = yl < y_hi + V;                                   // strip + V halo rows on both sides
@@ -445,25 +453,51 @@ int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end
     a.ld = g.ld;
     a.x_begin = x_begin;
     a.x_end = x_end;
+    a.x_split = INT_MAX;
+    a.x_skip = 0;
     a.halo_lo = a.halo_hi = nullptr;
     a.cp = cp;
-    // the fewest strips (2V redundant rows each), 64-column segments (two warm-up columns each): ~19 waves
-    // of 148 x 3 blocks at 32768 x 4096, so the block scheduler evens out the SMs
+    // Strips x segments.  All blocks take about the same time and an SM holds MINB of them, so the launch finishes in
+    // ceil(blocks / slots) rounds, slots = MINB x SMs: a last, mostly empty round costs as much as a full one.  Measured on
+    // B200 with 64-column segments throughout (fp64, GLUPS): 8192^2 = 9.5 rounds 83; 4096^2 = 2.45 rounds 77; 2048^2 = 0.65
+    // round 63; 1024^2 = 0.18 round 21 (k_lbm2: 49) -- and 64 at 1024^2 once the segments are cut to fill the round.
+    //  * at least one round of 64-column blocks: the fewest strips (4V redundant rows each), and the segment count that
+    //    makes the blocks fill a whole number of rounds, from below (segments get slightly shorter than 64 columns);
+    //  * less than one round: one round exactly, choosing among up to 8 extra strips the split whose blocks have the least
+    //    work (a narrower strip recomputes 4V rows, a shorter segment two warm-up columns; at least 8 columns per segment).
     const int ncols = x_end - x_begin;
     const int ty_max = (NT - 2) * V;
-    a.nstrips = (g.ny + ty_max - 1) / ty_max;
-    a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
-    a.nstrips = (g.ny + a.ty - 1) / a.ty;
-    int nseg = (ncols + 63) / 64;
-    // measurement knob (PLBM_PAIR_BULK_FILL=1, with PLBM_PAIR_BULK=2 to force this kernel on small grids): shorter
-    // segments, down to 8 columns, until one wave of 3 blocks per SM is filled
-    static const int fill = env_int("PLBM_PAIR_BULK_FILL", 0);
-    if (fill && a.nstrips * nseg < 3 * g.sm_count) {
-        nseg = (3 * g.sm_count + a.nstrips - 1) / a.nstrips;
-        if (nseg > (ncols + 7) / 8) nseg = (ncols + 7) / 8;
-        if (nseg < 1) nseg = 1;
+    const int slots = MINB * g.sm_count;
+    const int nstrips_min = (g.ny + ty_max - 1) / ty_max;
+    static const int fill = env_int("PLBM_PAIR_BULK_FILL", 1);  // 0: 64-column segments always (the round-1 launcher, for A/B)
+    int nstrips = nstrips_min, nseg = (ncols + 63) / 64;
+    if (fill) {
+        const long long blocks64 = (long long)nstrips_min * nseg;
+        if (blocks64 >= slots) {
+            const long long rounds = (blocks64 + slots - 1) / slots;
+            nseg = (int)(rounds * slots / nstrips_min);
+        } else {
+            double best_cost = 1e300;
+            for (int ns = nstrips_min; ns <= nstrips_min + 8 && ns * V <= g.ny; ++ns) {
+                const int ty = ((g.ny + ns - 1) / ns + V - 1) / V * V;
+                int sg = slots / ns;
+                if (sg < 1) sg = 1;
+                int sl = (ncols + sg - 1) / sg;
+                if (sl < 8) sl = 8;
+                const double cost = (double)(ty + 4 * V) * (sl + 2);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    nstrips = ns;
+                    nseg = sg;
+                }
+            }
+        }
     }
+    a.ty = ((g.ny + nstrips - 1) / nstrips + V - 1) / V * V;
+    a.nstrips = (g.ny + a.ty - 1) / a.ty;
+    if (nseg < 1) nseg = 1;
     a.seglen = (ncols + nseg - 1) / nseg;
+    if (a.seglen < 8) a.seglen = ncols < 8 ? ncols : 8;
     nseg = (ncols + a.seglen - 1) / a.seglen;
     kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -500,7 +534,7 @@ int env_int(const char* name, int dflt)
 
 template <typename T, int MODEL, bool HALO>
 int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
-                cudaStream_t s)
+                cudaStream_t s, int nb_split = 0)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int NT = 128, MINB = 4;
@@ -525,7 +559,15 @@ int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, con
     a.halo_lo = halo_lo;
     a.halo_hi = halo_hi;
     a.cp = cp;
-    const int ncols = x_end - x_begin;
+    a.x_split = INT_MAX;
+    a.x_skip = 0;
+    if (nb_split > 0) {  // both boundaries of a slab: columns [0, nb) and [nx - nb, nx), one segment each
+        a.x_begin = 0;
+        a.x_end = g.nx;
+        a.x_split = nb_split;
+        a.x_skip = g.nx - 2 * nb_split;
+    }
+    const int ncols = nb_split > 0 ? 2 * nb_split : x_end - x_begin;
     const int ty_max = (NT - 2) * V;
     const int slots = g.sm_count * MINB;  // resident blocks of one wave
     // Strips: among the counts from the minimum upwards take the one whose busiest block has the least work
@@ -557,6 +599,10 @@ int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, con
     a.seglen = (ncols + nseg - 1) / nseg;
     if (a.seglen < 8) a.seglen = ncols < 8 ? ncols : 8;
     nseg = (ncols + a.seglen - 1) / a.seglen;
+    if (nb_split > 0) {
+        a.seglen = nb_split;
+        nseg = 2;
+    }
     kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
@@ -565,15 +611,15 @@ int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, con
 
 template <typename T, bool HALO>
 int dispatch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
-                  const CollideParams<T>& cp, cudaStream_t s)
+                  const CollideParams<T>& cp, cudaStream_t s, int nb_split = 0)
 {
     switch (model) {
-    case M_BGK: return launch_pair<T, M_BGK, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_TRT: return launch_pair<T, M_TRT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_RR: return launch_pair<T, M_RR, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_BGK_SPLIT: return launch_pair<T, M_BGK_SPLIT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_TRT_SPLIT: return launch_pair<T, M_TRT_SPLIT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_BGK_IMPROVED: return launch_pair<T, M_BGK_IMPROVED, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_BGK: return launch_pair<T, M_BGK, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
+    case M_TRT: return launch_pair<T, M_TRT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
+    case M_RR: return launch_pair<T, M_RR, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
+    case M_BGK_SPLIT: return launch_pair<T, M_BGK_SPLIT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
+    case M_TRT_SPLIT: return launch_pair<T, M_TRT_SPLIT, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
+    case M_BGK_IMPROVED: return launch_pair<T, M_BGK_IMPROVED, HALO>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
     }
     set_error("launch_lbm_pair: unknown collision model");
     return PLBM_ERR_ARG;
@@ -600,11 +646,11 @@ int lbm_pair_flavour(const Grid& g)
     if (g.variant == 7 || g.variant == 8) return 2;
     if (bulk_default == 0) return 1;
     if (bulk_default >= 2) return 2;  // PLBM_PAIR_BULK=2: on every grid (A/B measurements)
-    // k_lbm2_bulk walks 64-column segments of full-height strips, three blocks per SM: measured on grids that give it
-    // many waves (8192^2: 9.5, the bench slab: 18.9).  Grids with fewer than two waves of such blocks stay on k_lbm2,
-    // whose launcher cuts strips and segments to fill one wave (measured 48 GLUPS at 1024^2).
-    const long long strips = (g.ny + 126 * v - 1) / (126 * v), segs = (g.nx + 63) / 64;
-    return strips * segs >= 2LL * 3 * g.sm_count ? 2 : 1;
+    // k_lbm2_bulk wherever its launcher can fill one round of blocks (three per SM) with segments of at least 8 columns:
+    // measured (fp64, GLUPS, k_lbm2 -> k_lbm2_bulk) 1024^2 TRT 49 -> 64, 2048^2 63, 4096^2 59 -> 77, 8192^2 64 -> 83.  Smaller
+    // grids stay on k_lbm2, whose launcher trades strips for segments down to a few hundred nodes per block.
+    const long long strips = (g.ny + 126 * v - 1) / (126 * v) + 8, segs = (g.nx + 7) / 8;
+    return strips * segs >= 3LL * g.sm_count ? 2 : 1;
 }
 
 #endif  // !PLBM_FMA_BUILD
@@ -621,6 +667,22 @@ int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end,
     if (halo_lo && halo_hi) return dispatch_pair<T, true>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s);
     return dispatch_pair<T, false>(g, src, dst, x_begin, x_end, nullptr, nullptr, model, cp, s);
 }
+
+#ifndef PLBM_FMA_BUILD
+// Both boundaries of a slab in ONE launch: two fused steps for columns [0, nb) and [nx - nb, nx), reading the ring
+// neighbours' halo lines (nullptr: periodic self-wrap, the single-GPU emulation of the slab schedule, variant 8).
+template <typename T>
+int launch_lbm_pair_boundaries(const Grid& g, const T* src, T* dst, int nb, const T* halo_lo, const T* halo_hi, int model,
+                               const CollideParams<T>& cp, cudaStream_t s)
+{
+    if (halo_lo && halo_hi) return dispatch_pair<T, true>(g, src, dst, 0, g.nx, halo_lo, halo_hi, model, cp, s, nb);
+    return dispatch_pair<T, false>(g, src, dst, 0, g.nx, nullptr, nullptr, model, cp, s, nb);
+}
+template int launch_lbm_pair_boundaries<double>(const Grid&, const double*, double*, int, const double*, const double*, int,
+                                                const CollideParams<double>&, cudaStream_t);
+template int launch_lbm_pair_boundaries<float>(const Grid&, const float*, float*, int, const float*, const float*, int,
+                                               const CollideParams<float>&, cudaStream_t);
+#endif
 
 template int launch_lbm_pair<double>(const Grid&, const double*, double*, int, int, const double*, const double*, int,
                                      const CollideParams<double>&, cudaStream_t);

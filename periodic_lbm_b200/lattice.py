@@ -104,6 +104,12 @@ class LatticeGrid:
         assert f.shape == (9, self.nx, self.ld), f.shape
         check(lib.plbm_upload_f(self._h, which, _ptr(f)), "upload_f")
 
+    def lattice_hash(self, which):
+        """64-bit checksum of lattice `which` computed on the device (plbm_lattice_hash)."""
+        out = C.c_ulonglong()
+        check(lib.plbm_lattice_hash(self._h, int(which), C.byref(out)), "lattice_hash")
+        return int(out.value)
+
     def synchronize(self):
         check(lib.plbm_synchronize(self._h), "synchronize")
 

@@ -57,7 +57,8 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p
     diag = g.diagnostics()
     uxa, uya = _analytic_fields(nxg, ny, g.dtype)
     l2 = g.l2_sums(np.ascontiguousarray(uxa[sl.x_offset:sl.x_end]), np.ascontiguousarray(uya[sl.x_offset:sl.x_end]))
-    outq.put((rank, sl.x_offset, got, transport, diag, l2))
+    om2, om4 = p.vorticity_2nd(None, None, grid=g), p.vorticity_4th(None, None, grid=g)  # d(uy)/dx crosses the slab boundaries
+    outq.put((rank, sl.x_offset, got, transport, diag, l2, om2, om4))
     check(lib.plbm_comm_finalize(g._h), "comm_finalize")
     p.dealloc_grid(g)
 
@@ -103,8 +104,9 @@ def _single(plbm, nxg, ny, steps, coll_id, prec, seed):
     diag = g.diagnostics()
     uxa, uya = _analytic_fields(nxg, ny, g.dtype)
     l2 = g.l2_sums(uxa, uya)
+    om = (plbm.vorticity_2nd(None, None, grid=g), plbm.vorticity_4th(None, None, grid=g))
     plbm.dealloc_grid(g)
-    return single, diag, l2
+    return single, diag, l2, om
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -121,8 +123,10 @@ def test_slabs_with_bulk_interior_bitwise_equal_single_gpu(plbm, world, prec, co
     parts = _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, "p2p", env={"PLBM_PAIR_BULK": "2"}, expect_kernel="k_lbm2_bulk")
     assert all(t[3] == 1 for t in parts)
     multi = np.concatenate([t[2] for t in parts], axis=1)
-    single, diag, l2 = _single(plbm, nxg, ny, steps, coll_id, prec, seed)
+    single, diag, l2, om = _single(plbm, nxg, ny, steps, coll_id, prec, seed)
     assert np.array_equal(multi[:, :, :ny], single[:, :, :ny])
+    assert np.array_equal(np.concatenate([t[6] for t in parts], axis=0), om[0])  # vorticity_2nd over the ring
+    assert np.array_equal(np.concatenate([t[7] for t in parts], axis=0), om[1])  # vorticity_4th (weights as shipped, F9)
     for t in parts:
         d, l = t[4], t[5]
         assert d["max_speed"] == diag["max_speed"] and d["min_speed"] == diag["min_speed"]

@@ -597,6 +597,43 @@ def test_unfused_dugks_stream_after_a_fused_step(plbm):
     plbm.dealloc_grid(g)
 
 
+def numpy_lattice_hash(f, ny):
+    """restatement of plbm_lattice_hash (csrc/plbm_diag.cu): sum of splitmix64(bits + golden * (i + 1)) mod 2^64 over the
+    rows 0..ny-1 of every line, i = (q * nx + x) * ny + y"""
+    v = np.ascontiguousarray(f[:, :, :ny]).reshape(-1)
+    bits = v.view(np.uint64) if v.dtype == np.float64 else v.view(np.uint32).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        z = bits + np.uint64(0x9E3779B97F4A7C15) * np.arange(1, v.size + 1, dtype=np.uint64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(np.add.reduce(z, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_lattice_hash_matches_its_numpy_restatement(plbm, prec):
+    """plbm_lattice_hash: device-side 64-bit checksum (bench.py's selfcheck compares rings with single-GPU runs through it).
+    Equal to the numpy restatement, blind to the padding rows, sensitive to one flipped bit and to a transposition."""
+    nx, ny = 37, 53
+    og, g = make_pair(plbm, nx, ny, prec)
+    f = g.download_f(g.iold)
+    h = g.lattice_hash(g.iold)
+    assert h == numpy_lattice_hash(f, ny)
+    f2 = f.copy()
+    f2[:, :, ny:] = 123.0                      # padding rows do not count
+    g.upload_f(g.iold, f2)
+    assert g.lattice_hash(g.iold) == h
+    f3 = f.copy()
+    f3[4, 7, 11] = np.nextafter(f3[4, 7, 11], 2)  # one ulp somewhere
+    g.upload_f(g.iold, f3)
+    assert g.lattice_hash(g.iold) not in (h,) and g.lattice_hash(g.iold) == numpy_lattice_hash(f3, ny)
+    f4 = f.copy()
+    f4[2, 3, 5], f4[2, 3, 6] = f[2, 3, 6], f[2, 3, 5]  # same values, swapped places
+    g.upload_f(g.iold, f4)
+    assert g.lattice_hash(g.iold) != h
+    plbm.dealloc_grid(g)
+
+
 def test_error_paths(plbm):
     with pytest.raises(plbm.PlbmError):
         plbm.alloc_grid(0, 8)

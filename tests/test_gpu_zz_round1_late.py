@@ -105,14 +105,15 @@ def test_changes_between_deferred_steps_take_effect_in_order(plbm):
 
 
 def test_pair_kernel_selection(plbm):
-    """plbm_lbm_pair_kernel: which kernel a call of >= 3 steps uses (bench accounting).  Large grids (>= 2 waves of
-    k_lbm2_bulk blocks) get the bulk-copy flavour, smaller ones k_lbm2; the variants force either."""
+    """plbm_lbm_pair_kernel: which kernel a call of >= 3 steps uses (bench accounting).  Grids on which the
+    launcher of k_lbm2_bulk can fill one round of blocks get the bulk-copy flavour, smaller ones k_lbm2; the variants force either."""
     if os.environ.get("PLBM_PAIR_BULK", "") not in ("", "1"):
         pytest.skip("PLBM_PAIR_BULK overrides the default selection")
     for shape, prec, variant, want in (((64, 64), "f64", 0, "k_lbm2"), ((64, 64), "f64", 7, "k_lbm2_bulk"), ((64, 64), "f64", 6, "k_lbm2"),
                                        ((64, 64), "f64", 1, "k_lbm"), ((64, 8), "f64", 7, "k_lbm2"), ((64, 16), "f32", 7, "k_lbm2"),
-                                       ((64, 67), "f64", 0, "k_lbm"), ((1024, 1024), "f64", 0, "k_lbm2"), ((4096, 4096), "f64", 0, "k_lbm2_bulk"),
-                                       ((4096, 4096), "f32", 0, "k_lbm2"), ((8192, 8192), "f32", 0, "k_lbm2_bulk")):
+                                       ((64, 67), "f64", 0, "k_lbm"), ((256, 256), "f64", 0, "k_lbm2"), ((1024, 1024), "f64", 0, "k_lbm2_bulk"),
+                                       ((4096, 4096), "f64", 0, "k_lbm2_bulk"), ((4096, 4096), "f32", 0, "k_lbm2_bulk"),
+                                       ((8192, 8192), "f32", 0, "k_lbm2_bulk")):
         g = plbm.alloc_grid(*shape, precision=prec)
         g.set_variant(variant)
         assert g.pair_kernel() == want, (shape, prec, variant, g.pair_kernel())
