@@ -261,7 +261,9 @@ template <typename T> int fv_sweep(Grid& g, int streaming, int model, const Coll
         return launch_lbm<T>(c, model, false, g.variant, g.stream);
     }
     if (g.comm && (rc = comm_fv_exchange<T>(g, g.lat<T>(g.iold)))) return rc;  // slab: neighbours' boundary lines
-    if (g.variant == 3 && !g.comm && g.tmap_ok)  // opt-in: the tile kernel with FMA contraction (within tolerance, not bit-identical)
+    if (g.variant == 4 && fv_march_applicable(mode, kmodel))  // opt-in: marching kernel with shared faces (within tolerance, not bit-identical)
+        rc = launch_fv_march<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), mode, kmodel, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
+    else if (g.variant == 3 && !g.comm && g.tmap_ok)  // opt-in: the tile kernel with FMA contraction (within tolerance, not bit-identical)
         rc = launch_fv_tma_fma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), mode, kmodel, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
     else if ((g.variant == 0 || g.comm) && g.tmap_ok)  // TMA + mbarrier pipelined tile kernel
         rc = launch_fv_tma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), mode, kmodel, (T)g.dt, T(0), T(0), T(0), cp, g.stream);
@@ -299,6 +301,11 @@ template <typename T> int step_dugks_t(Grid& g, bool dugks, int nsteps)
             rc = launch_dugks_collide<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), of, oh, g.stream);
             if (rc) return rc;
             rc = launch_dugks_stream<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), (T)g.dt, oc, dugks, g.stream);
+        } else if (g.variant == 4) {
+            // opt-in: marching kernel, every face reconstructed and relaxed once and shared by its two cells (within tolerance
+            // of the reference, not bit-identical; plbm_fvm_march.cu)
+            rc = launch_fv_march<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), dugks ? 0 : 1, M_NONE, (T)g.dt, of, oh, oc,
+                                    CollideParams<T>{T(0), T(0)}, g.stream);
         } else if (g.variant == 3 && !g.comm && g.tmap_ok) {
             // opt-in: the same kernel with FMA contraction (within tolerance of the non-FMA result, not bit-identical)
             rc = launch_fv_tma_fma<T>(g, g.iold, g.lat<T>(g.iold), g.lat<T>(g.inew), dugks ? 0 : 1, M_NONE, (T)g.dt, of, oh, oc,

@@ -144,6 +144,11 @@ int launch_fv_tma(const Grid& g, int which_src, const T* fin, T* fout, int mode,
 template <typename T>
 int launch_fv_tma_fma(const Grid& g, int which_src, const T* fin, T* fout, int mode, int model, T dt, T omega_full, T omega_half,
                       T omega_face, const CollideParams<T>& cp, cudaStream_t s);
+// OPT-IN (variant 4), tolerance-gated: marching DUGKS / Bardow-FVM kernel with shared cell faces (plbm_fvm_march.cu)
+bool fv_march_applicable(int mode, int model);
+template <typename T>
+int launch_fv_march(const Grid& g, const T* fin, T* fout, int mode, int model, T dt, T omega_full, T omega_half, T omega_face,
+                    const CollideParams<T>& cp, cudaStream_t s);
 template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s);
 
 // multi-GPU ring exchange (plbm_comm.cu)

@@ -461,37 +461,19 @@ int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end
     // ceil(blocks / slots) rounds, slots = MINB x SMs: a last, mostly empty round costs as much as a full one.  Measured on
     // B200 with 64-column segments throughout (fp64, GLUPS): 8192^2 = 9.5 rounds 83; 4096^2 = 2.45 rounds 77; 2048^2 = 0.65
     // round 63; 1024^2 = 0.18 round 21 (k_lbm2: 49) -- and 64 at 1024^2 once the segments are cut to fill the round.
-    //  * at least one round of 64-column blocks: the fewest strips (4V redundant rows each), and the segment count that
-    //    makes the blocks fill a whole number of rounds, from below (segments get slightly shorter than 64 columns);
-    //  * less than one round: one round exactly, choosing among up to 8 extra strips the split whose blocks have the least
-    //    work (a narrower strip recomputes 4V rows, a shorter segment two warm-up columns; at least 8 columns per segment).
+    // Always the fewest strips (a block costs the same per column whether its 128 threads own 252 rows or fewer: measured,
+    // 1024^2 fp64 with 8 strips of 128 rows 51, with 5 strips of 206 rows 64), and the segment count that makes the blocks
+    // fill a whole number of rounds, from below; at least 8 columns per segment (two warm-up columns each).
     const int ncols = x_end - x_begin;
     const int ty_max = (NT - 2) * V;
     const int slots = MINB * g.sm_count;
-    const int nstrips_min = (g.ny + ty_max - 1) / ty_max;
+    const int nstrips = (g.ny + ty_max - 1) / ty_max;
     static const int fill = env_int("PLBM_PAIR_BULK_FILL", 1);  // 0: 64-column segments always (the round-1 launcher, for A/B)
-    int nstrips = nstrips_min, nseg = (ncols + 63) / 64;
+    int nseg = (ncols + 63) / 64;
     if (fill) {
-        const long long blocks64 = (long long)nstrips_min * nseg;
-        if (blocks64 >= slots) {
-            const long long rounds = (blocks64 + slots - 1) / slots;
-            nseg = (int)(rounds * slots / nstrips_min);
-        } else {
-            double best_cost = 1e300;
-            for (int ns = nstrips_min; ns <= nstrips_min + 8 && ns * V <= g.ny; ++ns) {
-                const int ty = ((g.ny + ns - 1) / ns + V - 1) / V * V;
-                int sg = slots / ns;
-                if (sg < 1) sg = 1;
-                int sl = (ncols + sg - 1) / sg;
-                if (sl < 8) sl = 8;
-                const double cost = (double)(ty + 4 * V) * (sl + 2);
-                if (cost < best_cost) {
-                    best_cost = cost;
-                    nstrips = ns;
-                    nseg = sg;
-                }
-            }
-        }
+        const long long blocks64 = (long long)nstrips * nseg;
+        const long long rounds = blocks64 >= slots ? (blocks64 + slots - 1) / slots : 1;
+        nseg = (int)(rounds * slots / nstrips);
     }
     a.ty = ((g.ny + nstrips - 1) / nstrips + V - 1) / V * V;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
@@ -646,10 +628,11 @@ int lbm_pair_flavour(const Grid& g)
     if (g.variant == 7 || g.variant == 8) return 2;
     if (bulk_default == 0) return 1;
     if (bulk_default >= 2) return 2;  // PLBM_PAIR_BULK=2: on every grid (A/B measurements)
-    // k_lbm2_bulk wherever its launcher can fill one round of blocks (three per SM) with segments of at least 8 columns:
-    // measured (fp64, GLUPS, k_lbm2 -> k_lbm2_bulk) 1024^2 TRT 49 -> 64, 2048^2 63, 4096^2 59 -> 77, 8192^2 64 -> 83.  Smaller
-    // grids stay on k_lbm2, whose launcher trades strips for segments down to a few hundred nodes per block.
-    const long long strips = (g.ny + 126 * v - 1) / (126 * v) + 8, segs = (g.nx + 7) / 8;
+    // k_lbm2_bulk wherever its launcher can fill one round of blocks (three per SM) with full-height strips and segments of
+    // at least 8 columns.  Measured (GLUPS, k_lbm2 -> k_lbm2_bulk): fp64 1024^2 TRT 46 -> 64, 2048^2 54 -> 73, 4096^2 58 -> 79,
+    // 8192^2 64 -> 83; fp32 4096^2 96 -> 129, 8192^2 119 -> 147.  Smaller grids stay on k_lbm2, whose launcher trades strips for
+    // segments down to a few hundred nodes per block (fp64 768^2: 41 vs 26; fp32 1024^2: 68 vs 54).
+    const long long strips = (g.ny + 126 * v - 1) / (126 * v), segs = (g.nx + 7) / 8;
     return strips * segs >= 3LL * g.sm_count ? 2 : 1;
 }
 

@@ -574,7 +574,7 @@ def test_diagnostics_propagate_nan(plbm):
     plbm.update_macros(g, lagged=False)
     d = g.diagnostics()
     assert np.isnan(d["max_speed"]) and np.isnan(d["min_speed"]) and np.isnan(d["sum_rho"]) and np.isnan(d["kinetic_energy"])
-    g.ux[7, 3] = 0.01
+    g.rho[:], g.ux[:], g.uy[:] = 1.0, 0.01, 0.02  # update_macros overwrote the host views (rho, uy of that node are NaN too)
     plbm.set_pdf_to_equilibrium(g)
     plbm.update_macros(g, lagged=False)
     d = g.diagnostics()

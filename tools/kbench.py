@@ -34,6 +34,7 @@ def run(nx, ny, prec, scheme, coll, variant, steps, warmup=3, dugks=True):
     p.set_pdf_to_equilibrium(g)
     g.set_variant(variant)
     g.dugks = dugks
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("PLBM_")}
     g.collision = {"bgk": p.collide_bgk, "trt": p.collide_trt, "rr": p.collide_rr, "split": p.collide_bgk_split}[coll]
     if scheme == "lbm":
         g.streaming = p.lbm_stream
@@ -56,7 +57,7 @@ def run(nx, ny, prec, scheme, coll, variant, steps, warmup=3, dugks=True):
     bpl = 144 if prec == "f64" else 72
     gbs = mlups * 1e6 * bpl / 1e9
     p.dealloc_grid(g)
-    return dict(nx=nx, ny=ny, prec=prec, scheme=scheme, coll=coll, variant=variant, ms=round(ms, 4), mlups=round(mlups, 1),
+    return dict(nx=nx, ny=ny, prec=prec, scheme=scheme, coll=coll, variant=variant, env=knobs, ms=round(ms, 4), mlups=round(mlups, 1),
                 gbs=round(gbs, 1), frac=round(gbs / PEAK, 4))
 
 
