@@ -189,7 +189,8 @@ long long plbm_launch_count(void);
  *                      by bulk async copies (k_lbm2_bulk); 8 = 7 issued as the three line ranges of the slab schedule;
  *                      9 / 10 = EXPERIMENTAL depth-generic kernel k_lbmn_bulk (bgk/trt/rr, one GPU): pairs / triples;
  *                      11 = EXPERIMENTAL the two-step kernels compiled with FMA contraction (one GPU; within 1e-12 /
- *                      1e-5 relative of the non-FMA result, NOT bit-identical)
+ *                      1e-5 relative of the non-FMA result, NOT bit-identical);
+ *                      12 = like 5, fp32 collisions in scalar instead of packed (two nodes per FFMA2) form: same bits, A/B only
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
  *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused
  *   both                   : 3 = EXPERIMENTAL the TMA-pipelined kernel compiled with FMA contraction (fewer fp64

@@ -119,7 +119,8 @@ bool lbm_pair_applicable(const Grid& g);
 // 6 per-thread loads forced, 7 bulk async copies forced, 8 = 7 issued as the slab schedule's three x ranges
 // (9 / 10: the experimental depth-generic kernel of plbm_lbmn.cu on one GPU, pairs / triples; like 5 otherwise)
 // (11: the default two-step kernels compiled with FMA contraction, plbm_lbm2_fma.cu, one GPU; like 5 otherwise)
-inline bool lbm_pair_variant(int variant) { return variant == 0 || (variant >= 5 && variant <= 11); }
+// (12: like 5 with the OTHER fp32 collision code: scalar where packed FFMA2 pairs are the default, plbm_f32x2.cuh)
+inline bool lbm_pair_variant(int variant) { return variant == 0 || (variant >= 5 && variant <= 12); }
 int lbm_pair_flavour(const Grid& g);  // 0 one step per launch, 1 k_lbm2, 2 k_lbm2_bulk
 template <typename T>
 int launch_lbm_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,

@@ -178,7 +178,7 @@ template <typename T, int V, int W> __device__ __forceinline__ void pull_ring(co
     }
 }
 
-template <typename T, int MODEL, int V, int NT, int MINB, bool HALO>
+template <typename T, int MODEL, int V, int NT, int MINB, bool HALO, bool PK>
 __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
 {
     constexpr int W = NT * V;
@@ -205,15 +205,13 @@ __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
     // warm-up: step-1 state of columns xs-1 and xs
     if (act_a) {
         load_column<T, V, HALO>(a, xs - 1, yp, n);
-#pragma unroll
-        for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
+        collide_nodes<T, MODEL, V, PK>(n, a.cp);
         park_column<T, V, W>(ring, rp, t, n);
     }
     rp.advance();
     if (act_a) {
         load_column<T, V, HALO>(a, xs, yp, n);
-#pragma unroll
-        for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
+        collide_nodes<T, MODEL, V, PK>(n, a.cp);
         park_column<T, V, W>(ring, rp, t, n);
         load_column<T, V, HALO>(a, xs + 1, yp, n);
     }
@@ -222,8 +220,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
     for (int x = xs; x < xe; ++x) {
         // A: step-1 state of column x+1 (operands were loaded one iteration ago)
         if (act_a) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
+            collide_nodes<T, MODEL, V, PK>(n, a.cp);
             park_column<T, V, W>(ring, rp, t, n);
         }
         __syncthreads();
@@ -232,8 +229,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbm2(const Lbm2Args<T> a)
         if (act_b) {
             T f[V][9];
             pull_ring<T, V, W>(ring, rp, t, f);
-#pragma unroll
-            for (int v = 0; v < V; ++v) collide<T, MODEL>(f[v], a.cp);
+            collide_nodes<T, MODEL, V, PK>(f, a.cp);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 Vec<T, V> p;
@@ -292,7 +288,8 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
-template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_lbm2_bulk(const Lbm2Args<T> a)
+template <typename T, int MODEL, int V, int NT, int MINB, bool PK>
+__global__ void __launch_bounds__(NT, MINB) k_lbm2_bulk(const Lbm2Args<T> a)
 {
     constexpr int W = NT * V;       // rows of one ring column: logical rows y_lo - V .. y_lo - V + W - 1
     constexpr int WS = W + 2 * V;   // rows of one staged raw column: logical rows y_lo - 2V .. (one extra vector each side)
@@ -358,8 +355,7 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
                     for (int v = 0; v < V; ++v) n[v][q] = col[v - cy];
                 }
             }
-#pragma unroll
-            for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
+            collide_nodes<T, MODEL, V, PK>(n, a.cp);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 const int slot = ringb_depth(q) == 1 ? 0 : (ringb_depth(q) == 2 ? w2 : w3);
@@ -413,8 +409,7 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
                     for (int v = 0; v < V; ++v) f[v][q] = col[v - cy];
                 }
             }
-#pragma unroll
-            for (int v = 0; v < V; ++v) collide<T, MODEL>(f[v], a.cp);
+            collide_nodes<T, MODEL, V, PK>(f, a.cp);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 Vec<T, V> p;
@@ -430,15 +425,44 @@ template <typename T, int MODEL, int V, int NT, int MINB> __global__ void __laun
 
 int env_int(const char* name, int dflt);
 
-template <typename T, int MODEL>
-int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
+// Packed fp32 collisions (two nodes per FFMA2, plbm_f32x2.cuh; bit-identical to the scalar ones): the default for fp32
+// (PLBM_F32_PACKED=0/1 overrides); variant 12 selects the other one, for A/B measurements.  Never in the FMA build.
+#ifndef PLBM_F32_PACKED_DEFAULT
+#define PLBM_F32_PACKED_DEFAULT 1
+#endif
+#ifndef PLBM_BULK_WIDE_DEFAULT
+#define PLBM_BULK_WIDE_DEFAULT 0
+#endif
+template <typename T> bool packed_collisions(const Grid& g)
 {
-    constexpr int V = 16 / (int)sizeof(T);
-    constexpr int NT = 128, MINB = 3;
+#ifdef PLBM_FMA_BUILD
+    return false;
+#else
+    if (sizeof(T) != 4) return false;
+    static const int dflt = env_int("PLBM_F32_PACKED", PLBM_F32_PACKED_DEFAULT);
+    return g.variant == 12 ? !dflt : (dflt != 0);
+#endif
+}
+#ifdef PLBM_FMA_BUILD
+template <typename T> struct can_pack {
+    static constexpr bool value = false;
+};
+#else
+template <typename T> struct can_pack {
+    static constexpr bool value = sizeof(T) == 4;
+};
+#endif
+
+// V rows per thread, NT threads: (16 bytes, 128) or -- "wide", twice the warps on the same shared memory -- (8 bytes, 256)
+template <typename T, int MODEL, bool PK, int V, int NT>
+int launch_pair_bulk_t(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
+{
+    constexpr int VA = 16 / (int)sizeof(T);  // strips begin and end on 16-byte boundaries (bulk copies)
+    constexpr int MINB = 3;
     constexpr int W = NT * V, WS = W + 2 * V;
     constexpr size_t smem = ((size_t)RINGB_SLOTS * W + 2 * 9 * WS) * sizeof(T) + 16;
     if (x_end <= x_begin) return PLBM_OK;
-    auto kern = k_lbm2_bulk<T, MODEL, V, NT, MINB>;
+    auto kern = k_lbm2_bulk<T, MODEL, V, NT, MINB, PK>;
     static bool configured[64] = {false};
     if (g.device < 64 && !configured[g.device]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -475,7 +499,7 @@ int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end
         const long long rounds = blocks64 >= slots ? (blocks64 + slots - 1) / slots : 1;
         nseg = (int)(rounds * slots / nstrips);
     }
-    a.ty = ((g.ny + nstrips - 1) / nstrips + V - 1) / V * V;
+    a.ty = ((g.ny + nstrips - 1) / nstrips + VA - 1) / VA * VA;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
     if (nseg < 1) nseg = 1;
     a.seglen = (ncols + nseg - 1) / nseg;
@@ -485,6 +509,19 @@ int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
+}
+
+template <typename T, int MODEL>
+int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    static const int wide = env_int("PLBM_BULK_WIDE", PLBM_BULK_WIDE_DEFAULT);
+    if (wide) {
+        if (packed_collisions<T>(g)) return launch_pair_bulk_t<T, MODEL, can_pack<T>::value, V / 2, 256>(g, src, dst, x_begin, x_end, cp, s);
+        return launch_pair_bulk_t<T, MODEL, false, V / 2, 256>(g, src, dst, x_begin, x_end, cp, s);
+    }
+    if (packed_collisions<T>(g)) return launch_pair_bulk_t<T, MODEL, can_pack<T>::value, V, 128>(g, src, dst, x_begin, x_end, cp, s);
+    return launch_pair_bulk_t<T, MODEL, false, V, 128>(g, src, dst, x_begin, x_end, cp, s);
 }
 
 template <typename T>
@@ -514,16 +551,16 @@ int env_int(const char* name, int dflt)
     return e && *e ? atoi(e) : dflt;
 }
 
-template <typename T, int MODEL, bool HALO>
-int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
-                cudaStream_t s, int nb_split = 0)
+template <typename T, int MODEL, bool HALO, bool PK>
+int launch_pair_t(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
+                  cudaStream_t s, int nb_split)
 {
     constexpr int V = 16 / (int)sizeof(T);
     constexpr int NT = 128, MINB = 4;
     constexpr int W = NT * V;
     constexpr size_t smem = (size_t)RING_SLOTS * W * sizeof(T);
     if (x_end <= x_begin) return PLBM_OK;
-    auto kern = k_lbm2<T, MODEL, V, NT, MINB, HALO>;
+    auto kern = k_lbm2<T, MODEL, V, NT, MINB, HALO, PK>;
     static bool configured[64] = {false};
     if (g.device < 64 && !configured[g.device]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -589,6 +626,14 @@ int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, con
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());
     return PLBM_OK;
+}
+
+template <typename T, int MODEL, bool HALO>
+int launch_pair(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
+                cudaStream_t s, int nb_split = 0)
+{
+    if (packed_collisions<T>(g)) return launch_pair_t<T, MODEL, HALO, can_pack<T>::value>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
+    return launch_pair_t<T, MODEL, HALO, false>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, nb_split);
 }
 
 template <typename T, bool HALO>

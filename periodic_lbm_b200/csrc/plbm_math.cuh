@@ -17,6 +17,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "plbm_f32x2.cuh"
+
 namespace plbm {
 
 // D2Q9 velocity set, src/fvm_bardow.F90:87-88
@@ -149,12 +151,18 @@ template <typename T, bool EW> __device__ __forceinline__ void face_relax(T (&f)
 // Two-relaxation-time, incompressible equilibrium (velocity = momentum).
 template <typename T> __device__ __forceinline__ void collide_trt(T (&f)[9], T lambda_e, T lambda_d)
 {
-    const T t0 = T(4) / T(9);
-    const T t1x2 = (T(1) / T(9)) * T(2);
-    const T t2x2 = (T(1) / T(36)) * T(2);
-    const T inv2csq2 = T(1) / (T(2) * (T(1) / T(3)) * (T(1) / T(3)));
-    const T fac1 = t1x2 * inv2csq2;
-    const T fac2 = t2x2 * inv2csq2;
+    // compile-time constants, evaluated in the scalar working precision (S = T except for the packed pair type F2)
+    typedef typename scalar_of<T>::type S;
+    const S t1x2_s = (S(1) / S(9)) * S(2);
+    const S t2x2_s = (S(1) / S(36)) * S(2);
+    const S inv2csq2_s = S(1) / (S(2) * (S(1) / S(3)) * (S(1) / S(3)));
+    const T t0 = T(S(4) / S(9));
+    const T t1x2 = T(t1x2_s);
+    const T t2x2 = T(t2x2_s);
+    const T fac1 = T(t1x2_s * inv2csq2_s);
+    const T fac2 = T(t2x2_s * inv2csq2_s);
+    const T three_t1x2 = T(S(3) * t1x2_s);
+    const T three_t2x2 = T(S(3) * t2x2_s);
 
     T lambda_e_scaled = T(0.5) * lambda_e;
     T lambda_d_scaled = T(0.5) * lambda_d;
@@ -173,23 +181,23 @@ template <typename T> __device__ __forceinline__ void collide_trt(T (&f)[9], T l
 
     T velXPY = velX + velY;
     T sym_NE_SW = lambda_e_scaled * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common);
-    T asym_NE_SW = lambda_d_scaled * (vNE - vSW - T(3) * t2x2 * velXPY);
+    T asym_NE_SW = lambda_d_scaled * (vNE - vSW - three_t2x2 * velXPY);
     f[5] = vNE - sym_NE_SW - asym_NE_SW;
     f[7] = vSW - sym_NE_SW + asym_NE_SW;
 
     T velXMY = velX - velY;
     T sym_SE_NW = lambda_e_scaled * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common);
-    T asym_SE_NW = lambda_d_scaled * (vSE - vNW - T(3) * t2x2 * velXMY);
+    T asym_SE_NW = lambda_d_scaled * (vSE - vNW - three_t2x2 * velXMY);
     f[8] = vSE - sym_SE_NW - asym_SE_NW;
     f[6] = vNW - sym_SE_NW + asym_SE_NW;
 
     T sym_N_S = lambda_e_scaled * (vN + vS - fac1 * velY2 - t1x2 * feq_common);
-    T asym_N_S = lambda_d_scaled * (vN - vS - T(3) * t1x2 * velY);
+    T asym_N_S = lambda_d_scaled * (vN - vS - three_t1x2 * velY);
     f[2] = vN - sym_N_S - asym_N_S;
     f[4] = vS - sym_N_S + asym_N_S;
 
     T sym_E_W = lambda_e_scaled * (vE + vW - fac1 * velX2 - t1x2 * feq_common);
-    T asym_E_W = lambda_d_scaled * (vE - vW - T(3) * t1x2 * velX);
+    T asym_E_W = lambda_d_scaled * (vE - vW - three_t1x2 * velX);
     f[1] = vE - sym_E_W - asym_E_W;
     f[3] = vW - sym_E_W + asym_E_W;
 }
@@ -294,12 +302,18 @@ template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T om
 // fac1*(vel*vel) -- a last-bit difference, reproduced.
 template <typename T> __device__ __forceinline__ void collide_trt_split(T (&f)[9], T lambda_e, T lambda_d)
 {
-    const T t0 = T(4) / T(9);
-    const T t1x2 = (T(1) / T(9)) * T(2);
-    const T t2x2 = (T(1) / T(36)) * T(2);
-    const T inv2csq2 = T(1) / (T(2) * (T(1) / T(3)) * (T(1) / T(3)));
-    const T fac1 = t1x2 * inv2csq2;
-    const T fac2 = t2x2 * inv2csq2;
+    // compile-time constants, evaluated in the scalar working precision (S = T except for the packed pair type F2)
+    typedef typename scalar_of<T>::type S;
+    const S t1x2_s = (S(1) / S(9)) * S(2);
+    const S t2x2_s = (S(1) / S(36)) * S(2);
+    const S inv2csq2_s = S(1) / (S(2) * (S(1) / S(3)) * (S(1) / S(3)));
+    const T t0 = T(S(4) / S(9));
+    const T t1x2 = T(t1x2_s);
+    const T t2x2 = T(t2x2_s);
+    const T fac1 = T(t1x2_s * inv2csq2_s);
+    const T fac2 = T(t2x2_s * inv2csq2_s);
+    const T three_t1x2 = T(S(3) * t1x2_s);
+    const T three_t2x2 = T(S(3) * t2x2_s);
     T lambda_e_scaled = T(0.5) * lambda_e;
     T lambda_d_scaled = T(0.5) * lambda_d;
 
@@ -313,23 +327,23 @@ template <typename T> __device__ __forceinline__ void collide_trt_split(T (&f)[9
 
     T velXPY = velX + velY;
     T sym_NE_SW = lambda_e_scaled * (vNE + vSW - fac2 * velXPY * velXPY - t2x2 * feq_common);
-    T asym_NE_SW = lambda_d_scaled * (vNE - vSW - T(3) * t2x2 * velXPY);
+    T asym_NE_SW = lambda_d_scaled * (vNE - vSW - three_t2x2 * velXPY);
     f[5] = vNE - sym_NE_SW - asym_NE_SW;
     f[7] = vSW - sym_NE_SW + asym_NE_SW;
 
     T velXMY = velX - velY;
     T sym_SE_NW = lambda_e_scaled * (vSE + vNW - fac2 * velXMY * velXMY - t2x2 * feq_common);
-    T asym_SE_NW = lambda_d_scaled * (vSE - vNW - T(3) * t2x2 * velXMY);
+    T asym_SE_NW = lambda_d_scaled * (vSE - vNW - three_t2x2 * velXMY);
     f[8] = vSE - sym_SE_NW - asym_SE_NW;
     f[6] = vNW - sym_SE_NW + asym_SE_NW;
 
     T sym_N_S = lambda_e_scaled * (vN + vS - fac1 * velY * velY - t1x2 * feq_common);
-    T asym_N_S = lambda_d_scaled * (vN - vS - T(3) * t1x2 * velY);
+    T asym_N_S = lambda_d_scaled * (vN - vS - three_t1x2 * velY);
     f[2] = vN - sym_N_S - asym_N_S;
     f[4] = vS - sym_N_S + asym_N_S;
 
     T sym_E_W = lambda_e_scaled * (vE + vW - fac1 * velX * velX - t1x2 * feq_common);
-    T asym_E_W = lambda_d_scaled * (vE - vW - T(3) * t1x2 * velX);
+    T asym_E_W = lambda_d_scaled * (vE - vW - three_t1x2 * velX);
     f[1] = vE - sym_E_W - asym_E_W;
     f[3] = vW - sym_E_W + asym_E_W;
 }
@@ -388,6 +402,42 @@ template <typename T, int MODEL> __device__ __forceinline__ void collide(T (&f)[
     else if (MODEL == M_BGK_SPLIT) collide_bgk_split(f, p.omega);
     else if (MODEL == M_TRT_SPLIT) collide_trt_split(f, p.omega, p.lambda_d);
     else if (MODEL == M_BGK_IMPROVED) collide_bgk_improved(f, p.omega);
+}
+
+// Collision of the V vertically adjacent nodes a thread owns.  PACKED (fp32 only, V even): two nodes per instruction
+// through the packed pair type F2 (plbm_f32x2.cuh) -- the same individually rounded operations on the same operands, so
+// bit-identical to the scalar loop.
+template <typename T, int MODEL, int V, bool PACKED> struct CollideNodes {
+    static __device__ __forceinline__ void run(T (&n)[V][9], const CollideParams<T>& p)
+    {
+#pragma unroll
+        for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], p);
+    }
+};
+template <int MODEL, int V> struct CollideNodes<float, MODEL, V, true> {
+    static __device__ __forceinline__ void run(float (&n)[V][9], const CollideParams<float>& p)
+    {
+        static_assert(V % 2 == 0, "packed fp32 collisions take the nodes in pairs");
+        CollideParams<F2> p2;
+        p2.omega = F2(p.omega);
+        p2.lambda_d = F2(p.lambda_d);
+#pragma unroll
+        for (int v = 0; v < V; v += 2) {
+            F2 f[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) f[q] = F2(n[v][q], n[v + 1][q]);
+            collide<F2, MODEL>(f, p2);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                n[v][q] = f[q].lo();
+                n[v + 1][q] = f[q].hi();
+            }
+        }
+    }
+};
+template <typename T, int MODEL, int V, bool PACKED> __device__ __forceinline__ void collide_nodes(T (&n)[V][9], const CollideParams<T>& p)
+{
+    CollideNodes<T, MODEL, V, PACKED>::run(n, p);
 }
 
 // 2nd-order, half-step back-traced face reconstruction of one population from its 3x3
