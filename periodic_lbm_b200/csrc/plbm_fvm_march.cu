@@ -241,6 +241,11 @@ int launch_march(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T oc, c
     static bool configured[64] = {false};
     if (g.device < 64 && !configured[g.device]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // Carve-out left to the driver (it sizes it for three 128-thread blocks; the rest stays L1 for the raw-column loads).
+        // Measured, DUGKS fp64 2048^2 (r02a / r02d): default carve-out 24.4 GLUPS; carve-out 100 % 22.5, and with it 4 x 128, 6 or 8 x 64,
+        // 12 or 16 x 32 threads per SM all land on 22.3 - 23.6: the kernel is not bound by occupancy or by barrier coupling.
+        if (env_int("PLBM_MARCH_CARVEOUT", 0) > 0)
+            PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, env_int("PLBM_MARCH_CARVEOUT", 0)));
         configured[g.device] = true;
     }
     MarchArgs<T> a;
@@ -291,6 +296,16 @@ int launch_march_shape(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T
     if (nt == 256) {
         if (minb >= 2) return launch_march<T, MODE, MODEL, 256, 2>(g, fin, fout, dt, of, oh, oc, cp, s);
         return launch_march<T, MODE, MODEL, 256, 1>(g, fin, fout, dt, of, oh, oc, cp, s);
+    }
+    // small blocks: the two barriers per column couple fewer warps, so the load and the arithmetic phases of different
+    // blocks overlap on an SM
+    if (nt == 64) {
+        if (minb >= 8) return launch_march<T, MODE, MODEL, 64, 8>(g, fin, fout, dt, of, oh, oc, cp, s);
+        return launch_march<T, MODE, MODEL, 64, 6>(g, fin, fout, dt, of, oh, oc, cp, s);
+    }
+    if (nt == 32) {
+        if (minb >= 16) return launch_march<T, MODE, MODEL, 32, 16>(g, fin, fout, dt, of, oh, oc, cp, s);
+        return launch_march<T, MODE, MODEL, 32, 12>(g, fin, fout, dt, of, oh, oc, cp, s);
     }
     if (minb >= 4) return launch_march<T, MODE, MODEL, 128, 4>(g, fin, fout, dt, of, oh, oc, cp, s);
     if (minb == 3) return launch_march<T, MODE, MODEL, 128, 3>(g, fin, fout, dt, of, oh, oc, cp, s);

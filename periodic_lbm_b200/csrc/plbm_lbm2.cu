@@ -433,6 +433,9 @@ int env_int(const char* name, int dflt);
 #ifndef PLBM_BULK_WIDE_DEFAULT
 #define PLBM_BULK_WIDE_DEFAULT 0
 #endif
+#ifndef PLBM_BULK_NT_DEFAULT
+#define PLBM_BULK_NT_DEFAULT 128
+#endif
 template <typename T> bool packed_collisions(const Grid& g)
 {
 #ifdef PLBM_FMA_BUILD
@@ -458,7 +461,7 @@ template <typename T, int MODEL, bool PK, int V, int NT>
 int launch_pair_bulk_t(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
 {
     constexpr int VA = 16 / (int)sizeof(T);  // strips begin and end on 16-byte boundaries (bulk copies)
-    constexpr int MINB = 3;
+    constexpr int MINB = NT >= 128 ? 3 : (NT == 64 ? 6 : 12);  // what the shared memory of an SM holds
     constexpr int W = NT * V, WS = W + 2 * V;
     constexpr size_t smem = ((size_t)RINGB_SLOTS * W + 2 * 9 * WS) * sizeof(T) + 16;
     if (x_end <= x_begin) return PLBM_OK;
@@ -515,13 +518,19 @@ template <typename T, int MODEL>
 int launch_pair_bulk(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
 {
     constexpr int V = 16 / (int)sizeof(T);
+    // block shape (measurement knobs): PLBM_BULK_WIDE=1: 8 bytes per thread, 256 threads; PLBM_BULK_NT=64 / 32: small blocks, six /
+    // twelve per SM, whose barriers couple fewer warps
     static const int wide = env_int("PLBM_BULK_WIDE", PLBM_BULK_WIDE_DEFAULT);
-    if (wide) {
-        if (packed_collisions<T>(g)) return launch_pair_bulk_t<T, MODEL, can_pack<T>::value, V / 2, 256>(g, src, dst, x_begin, x_end, cp, s);
-        return launch_pair_bulk_t<T, MODEL, false, V / 2, 256>(g, src, dst, x_begin, x_end, cp, s);
-    }
-    if (packed_collisions<T>(g)) return launch_pair_bulk_t<T, MODEL, can_pack<T>::value, V, 128>(g, src, dst, x_begin, x_end, cp, s);
-    return launch_pair_bulk_t<T, MODEL, false, V, 128>(g, src, dst, x_begin, x_end, cp, s);
+    static const int nt = env_int("PLBM_BULK_NT", PLBM_BULK_NT_DEFAULT);
+    const bool pk = packed_collisions<T>(g);
+#define PLBM_BULK_SHAPE(VV, NN)                                                                                              \
+    return pk ? launch_pair_bulk_t<T, MODEL, can_pack<T>::value, VV, NN>(g, src, dst, x_begin, x_end, cp, s)                  \
+              : launch_pair_bulk_t<T, MODEL, false, VV, NN>(g, src, dst, x_begin, x_end, cp, s)
+    if (wide) PLBM_BULK_SHAPE(V / 2, 256);
+    if (nt == 64) PLBM_BULK_SHAPE(V, 64);
+    if (nt == 32) PLBM_BULK_SHAPE(V, 32);
+    PLBM_BULK_SHAPE(V, 128);
+#undef PLBM_BULK_SHAPE
 }
 
 template <typename T>
