@@ -227,17 +227,169 @@ template <typename T, int MODE, int MODEL, int NT, int MINB> __global__ void __l
     }
 }
 
+// ---- k_fv_march_s: the same step with the face stencils written as sums -----------------------------------------------
+// k_fv_march reads every operand of a face from the shared-memory ring: 42 loads per face, 105 shared-memory operations per node
+// and column, and ncu (r02a) shows the shared-memory pipe 60 % busy next to the fp64 pipe at 50 % -- the two do not overlap.  Here
+// a thread keeps its OWN row of the last two fbar columns in registers and the neighbours' contributions are exchanged as sums:
+//   west face of column X:   fc + fw = SW(t),  cross term = SW(t+1) - SW(t-1),   SW(t) = fbar[X-1][t] + fbar[X][t]
+//   south face of node (X,t): cross term = DS(t) + DS(t-1),                      DS(t) = fbar[X+1][t] - fbar[X-1][t]
+// so that per node and column 27 values are stored and 33 loaded (60 operations instead of 105).  The sums re-associate
+// the reference's cross terms (last-bit differences, like the shared faces themselves): same tolerance gate as k_fv_march.
+__host__ __device__ constexpr int xidx(int q) { return q == 1 ? 0 : (q == 3 ? 1 : q - 3); }  // populations with cx != 0
+
+template <typename T, int MODE, int MODEL, int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_fv_march_s(const MarchArgs<T> a)
+{
+    constexpr bool HALF = MODE != MODE_BARDOW;
+    constexpr bool RELAX = MODE == MODE_DUGKS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* const ring = reinterpret_cast<T*>(smem_raw);  // [2 columns][9][NT]: fbar, for the row below (fs of the south face)
+    T* const sw = ring + 18 * NT;                    // [6][NT] SW of the populations with cy != 0
+    T* const ds = sw + 6 * NT;                       // [6][NT] DS of the populations with cx != 0
+    T* const sface = ds + 6 * NT;                    // [6][NT] relaxed south faces of the column being updated
+
+    const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
+    const int y_lo = strip * a.ty;
+    const int y_hi = min(y_lo + a.ty, a.ny);
+    const int xs = a.x_begin + seg * a.seglen;
+    const int xe = min(xs + a.seglen, a.x_end);
+    const int t = threadIdx.x;
+    const int yl = y_lo - 1 + t;
+    const int yp = pmod(yl, a.ny);
+    const bool act_f = yl <= y_hi;
+    const bool act_s = t >= 1 && yl <= y_hi;
+    const bool act_u = t >= 1 && yl < y_hi;
+
+    T raw[9];
+    auto fetch = [&](int c) {
+        size_t qs;
+        const T* base = column_base<T>(a, c, qs) + yp;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) raw[q] = base[q * qs];
+    };
+    // raw column -> fbar (b) and the node's own post-collision state (fp)
+    auto stage1 = [&](T (&b)[9], T (&fp)[9]) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            b[q] = raw[q];
+            fp[q] = raw[q];
+        }
+        if (HALF) {
+            collide_bgk_split(b, a.omega_half);
+            collide_bgk_split(fp, a.omega_full);
+        }
+    };
+    // west face of the column whose fbar is bB, from the column before it (bA) and the SW sums of the rows above and below
+    auto west = [&](const T (&bA)[9], const T (&bB)[9], const T (&swv)[9], T (&cf)[9]) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int CX = cxi(q), CY = cyi(q);
+            if (!RELAX && CX == 0) continue;
+            T v = T(0.5) * swv[q];
+            if (CX != 0) v = v - (T(0.5) * (a.dt * T(CX))) * (bB[q] - bA[q]);
+            if (CY != 0) v = v - (T(0.125) * (a.dt * T(CY))) * (sw[sidx(q) * NT + t + 1] - sw[sidx(q) * NT + t - 1]);
+            cf[q] = v;
+        }
+        if (RELAX) face_relax<T, true>(cf, a.omega_face);
+    };
+
+    T bL[9] = {}, bC[9] = {}, b[9] = {}, swv[9] = {}, dsv[9] = {};
+    T fp_cur[9] = {}, fp_next[9] = {}, cw[9] = {}, ce[9] = {};
+    int slot_c = 0;  // ring slot of column x
+
+    // ---- warm-up: fbar of columns xs - 1 (bL) and xs (bC), west face of column xs --------------------------------------
+    if (act_f) {
+        fetch(xs - 1);
+        stage1(bL, fp_next);  // fp of the halo column is not used
+        fetch(xs);
+        stage1(bC, fp_cur);
+        if (xs + 1 <= xe) fetch(xs + 1);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            swv[q] = bL[q] + bC[q];
+            if (cyi(q) != 0) sw[sidx(q) * NT + t] = swv[q];
+            ring[(slot_c * 9 + q) * NT + t] = bC[q];
+        }
+    }
+    __syncthreads();
+    if (act_u) west(bL, bC, swv, cw);
+    __syncthreads();  // the loop overwrites sw
+
+    for (int x = xs; x < xe; ++x) {
+        // 1. column x + 1: fbar and own post-collision state; what the neighbours need, as sums; prefetch column x + 2
+        if (act_f) {
+            stage1(b, fp_next);
+            if (x + 2 <= xe) fetch(x + 2);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                ring[((slot_c ^ 1) * 9 + q) * NT + t] = b[q];
+                swv[q] = bC[q] + b[q];
+                if (cyi(q) != 0) sw[sidx(q) * NT + t] = swv[q];
+                if (cxi(q) != 0) {
+                    dsv[q] = b[q] - bL[q];
+                    ds[xidx(q) * NT + t] = dsv[q];
+                }
+            }
+        }
+        __syncthreads();
+        // 2. east face of column x = west face of column x + 1
+        if (act_u) west(bC, b, swv, ce);
+        // 3. south face of node (x, y); the node below reads it as its north face
+        T cs[9] = {};
+        if (act_s) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int CX = cxi(q), CY = cyi(q);
+                if (!RELAX && CY == 0) continue;
+                const T fc = bC[q], fs = ring[(slot_c * 9 + q) * NT + t - 1];
+                T v = T(0.5) * (fc + fs);
+                if (CY != 0) v = v - (T(0.5) * (a.dt * T(CY))) * (fc - fs);
+                if (CX != 0) v = v - (T(0.125) * (a.dt * T(CX))) * (dsv[q] + ds[xidx(q) * NT + t - 1]);
+                cs[q] = v;
+            }
+            if (RELAX) face_relax<T, false>(cs, a.omega_face);
+#pragma unroll
+            for (int q = 1; q < 9; ++q)
+                if (cyi(q) != 0) sface[sidx(q) * NT + t] = cs[q];
+        }
+        __syncthreads();
+        // 4. flux update of column x (src/periodic_dugks.F90:297), collision for the Bardow scheme, store
+        if (act_u) {
+#pragma unroll
+            for (int q = 1; q < 9; ++q)
+                if (cxi(q) != 0) fp_cur[q] = fp_cur[q] - (a.dt * T(cxi(q))) * (ce[q] - cw[q]);
+#pragma unroll
+            for (int q = 1; q < 9; ++q)
+                if (cyi(q) != 0) fp_cur[q] = fp_cur[q] - (a.dt * T(cyi(q))) * (sface[sidx(q) * NT + t + 1] - cs[q]);
+            if (MODE == MODE_BARDOW && MODEL != M_NONE) collide<T, MODEL>(fp_cur, a.cp);
+            T* out = a.fout + (size_t)x * a.ld + yp;
+            const size_t qs = (size_t)a.nx * a.ld;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) out[q * qs] = fp_cur[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            cw[q] = ce[q];
+            fp_cur[q] = fp_next[q];
+            bL[q] = bC[q];
+            bC[q] = b[q];
+        }
+        slot_c ^= 1;
+    }
+}
+
 int env_int(const char* name, int dflt)
 {
     const char* e = getenv(name);
     return e && *e ? atoi(e) : dflt;
 }
 
-template <typename T, int MODE, int MODEL, int NT, int MINB>
+template <typename T, int MODE, int MODEL, int NT, int MINB, bool SUMS = false>
 int launch_march(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T oc, const CollideParams<T>& cp, cudaStream_t s)
 {
-    constexpr size_t smem = (size_t)(27 + 6) * NT * sizeof(T);
-    auto kern = k_fv_march<T, MODE, MODEL, NT, MINB>;
+    constexpr size_t smem = (size_t)(SUMS ? 18 + 18 : 27 + 6) * NT * sizeof(T);
+    void (*kern)(const MarchArgs<T>);
+    if constexpr (SUMS) kern = k_fv_march_s<T, MODE, MODEL, NT, MINB>;
+    else kern = k_fv_march<T, MODE, MODEL, NT, MINB>;
     static bool configured[64] = {false};
     if (g.device < 64 && !configured[g.device]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -293,6 +445,13 @@ int launch_march_shape(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T
     // block shape: measurement knobs PLBM_MARCH_NT (128 / 256) and PLBM_MARCH_MINB
     static const int nt = env_int("PLBM_MARCH_NT", 128);
     static const int minb = env_int("PLBM_MARCH_MINB", sizeof(T) == 8 ? 3 : 4);
+    // PLBM_MARCH_FORM=1: k_fv_march_s (faces from sums, own rows in registers): 128 threads x 2 / 3 blocks, 64 threads x 5 blocks
+    static const int form = env_int("PLBM_MARCH_FORM", 0);
+    if (form == 1) {
+        if (nt == 64) return launch_march<T, MODE, MODEL, 64, 5, true>(g, fin, fout, dt, of, oh, oc, cp, s);
+        if (minb >= 3) return launch_march<T, MODE, MODEL, 128, 3, true>(g, fin, fout, dt, of, oh, oc, cp, s);
+        return launch_march<T, MODE, MODEL, 128, 2, true>(g, fin, fout, dt, of, oh, oc, cp, s);
+    }
     if (nt == 256) {
         if (minb >= 2) return launch_march<T, MODE, MODEL, 256, 2>(g, fin, fout, dt, of, oh, oc, cp, s);
         return launch_march<T, MODE, MODEL, 256, 1>(g, fin, fout, dt, of, oh, oc, cp, s);
