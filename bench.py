@@ -351,11 +351,16 @@ def run_ours(args):
 
     if scheme == "lbm":
         # a 3-step call (one two-step launch + one k_lbm) minus a 1-step call (one k_lbm); under a ring the same
-        # difference is the boundary + interior launches of one pair (every rank issues the same sequence)
-        t1, t3 = call_ms(1), call_ms(3)
-        dom_ms, dom_steps, single_ms = t3 - t1, 2, t1
-        dom_kernel = g.pair_kernel()
-        if dom_kernel == "k_lbm":  # grids the two-step kernels do not take: one step per launch
+        # difference is the boundary + interior launches of one pair (every rank issues the same sequence).  Where the
+        # call advances three steps per pass (k_lbmn_bulk): a 4-step call (one triple + one k_lbm) minus a 1-step call.
+        spp = g.steps_per_pass()
+        t1 = call_ms(1)
+        if spp == 3:
+            dom_ms, dom_steps, single_ms, dom_kernel = call_ms(4) - t1, 3, t1, "k_lbmn_bulk"
+        else:
+            dom_ms, dom_steps, single_ms = call_ms(3) - t1, 2, t1
+            dom_kernel = g.pair_kernel()
+        if dom_kernel == "k_lbm":  # grids the multi-step kernels do not take: one step per launch
             dom_ms, dom_steps = t1, 1
         if world == 1 and launches == 1 and K >= 4:
             # grids that fit in the shared memory of one thread-block cluster: ALL K steps ran in one launch (csrc/plbm_small.cu)
@@ -388,7 +393,7 @@ def run_ours(args):
             g.set_step_deferral(0)
             per_call["deferred"] = {"ms_per_step": round(ms_def / ncalls, 4), "mlups": round(nodes_global * ncalls / ms_def * 1e-3, 1),
                                     "what": "K x perform_lbm_step(1) with plbm_set_step_deferral(64) (on in the Fortran shim): the calls are counted "
-                                            "and run batched, two steps per pass over HBM, when 64 are pending or anything looks at the grid"}
+                                            "and run batched, two or three steps per pass over HBM, when 64 are pending or anything looks at the grid"}
 
     # ---- C4: the opt-in, tolerance-gated kernels next to the bit-identical default, same grid, same call ----------------
     fast = None
@@ -483,11 +488,18 @@ def run_ours(args):
         tr, tr_src = ncu_traffic_per_lup(args.workload, dom_kernel.split("<")[0])
         traffic = None if tr is None else round(tr * dom_steps * nodes_local)
         cfg = config_of(args.workload, world)
-        stepping = {"lbm": f"one perform_lbm_step(K={K}) call: {(K - 1) // 2} two-step launches + {K - 2 * ((K - 1) // 2)} single-step launches, bit-identical to K single steps",
+        def lbm_schedule(k, depth):
+            """launches of one perform_lbm_step(k) call: triples while more than three steps remain (depth 3), pairs while more than two"""
+            n3 = (k - 1) // 3 if depth == 3 else 0
+            rest = k - 3 * n3
+            n2 = (rest - 1) // 2 if depth >= 2 else 0
+            return n3, n2, rest - 2 * n2
+        n3, n2, n1 = lbm_schedule(K, dom_steps if scheme == "lbm" else 1)
+        stepping = {"lbm": f"one perform_lbm_step(K={K}) call: {n3} three-step launches + {n2} two-step launches + {n1} single-step launches, bit-identical to K single steps",
                     "dugks": f"one perform_dugks_step(K={K}) call: one fused launch per step (collide + face reconstruction + face relaxation + flux update)",
                     "fvm_bardow": f"one perform_step(K={K}) call: one fused launch per step (stream_fvm_bardow + collide_bgk)"}[scheme]
         cfg.update({"stepping": stepping, "variant": args.variant,
-                    "halo": f"2 lines x 9 populations per direction per launch, overlapped with the interior update; transport: {transport}" if world > 1 else "none (periodic index wrap)",
+                    "halo": f"3 lines x 9 populations per direction per launch (a launch of one, two or three steps reads one, two or three of them), overlapped with the interior update; transport: {transport}" if world > 1 else "none (periodic index wrap)",
                     "l2": f"inputs vs L2: {2 * 9 * nxl * ny * np.dtype(dtype).itemsize / 1e9:.3f} GB of PDFs per GPU vs 126 MB L2"
                           + (" (larger than L2: no flush needed)" if 2 * 9 * nxl * ny * np.dtype(dtype).itemsize > 4 * 126e6 else " (L2-resident: a launch/latency figure, not a roofline case)"),
                     "mass_sum_rho": mass})
@@ -506,7 +518,7 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": tr_src and f"ncu --set full capture of this kernel on this workload, {tr_src} (a profiler constant, not measured in this run)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_steps * nodes_local * bpl,
-                         "kernel": f"{dom_kernel}<{ {1: 'one step', 2: 'two fused stream+collide steps'}.get(dom_steps, f'all {dom_steps} steps of the call in one launch, lattices resident in distributed shared memory') }>" if scheme == "lbm" else dom_kernel,
+                         "kernel": f"{dom_kernel}<{ {1: 'one step', 2: 'two fused stream+collide steps', 3: 'three fused stream+collide steps'}.get(dom_steps if dom_kernel != 'k_lbm_cluster' else 0, f'all {dom_steps} steps of the call in one launch, lattices resident in distributed shared memory') }>" if scheme == "lbm" else dom_kernel,
                          "launch_ms": round(dom_ms, 4), "per_gpu": True,
                          "dram_frac": None if traffic is None else round(traffic / (dom_ms * 1e-3) / 1e9 / peak, 4)},
             "selfcheck": selfcheck,

@@ -202,6 +202,10 @@ int plbm_set_variant(plbm_handle grid, int variant);
  * resident kernel instead when variant == 0 and nsteps >= 4; this query does not look at that.  For bench accounting;
  * -1 on a null handle. */
 int plbm_lbm_pair_kernel(plbm_handle grid);
+/* how many time steps one pass over HBM advances in a perform_lbm_step call of many steps with this collision: 3 = k_lbmn_bulk
+ * (three fused steps: fp64 BGK / TRT on large grids, see csrc/plbm_api.cu lbm_triples_wanted), 2 = k_lbm2 / k_lbm2_bulk, 1 = k_lbm.
+ * For bench accounting; -1 on a null handle. */
+int plbm_lbm_steps_per_pass(plbm_handle grid, int collision);
 /* derivative stencil of stream_fdm_bardow: the reference selects it at compile time with -DFDM_WLS,
  * -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660); default = none of them. */
 enum plbm_fdm_stencil { PLBM_FDM_DEFAULT = 0, PLBM_FDM_WLS = 1, PLBM_FDM_WLS_GAUSS_V1 = 2, PLBM_FDM_WLS_GAUSS_V2 = 3, PLBM_FDM_ISO = 4 };

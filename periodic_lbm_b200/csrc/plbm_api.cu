@@ -2,6 +2,7 @@
 // derivation, step orchestration (iold/inew bookkeeping identical to the reference) and
 // host <-> device staging of the macroscopic fields.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -157,18 +158,19 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         }
     }
     int s = 0;
-    if ((g.variant == 9 || g.variant == 10) && lbm_multi_applicable(g, model, g.variant == 9 ? 2 : 3)) {
-        // EXPERIMENTAL (plbm_lbmn.cu): the depth-generic multi-step kernel.  9: pairs through its NSTEP = 2 instance;
-        // 10: triples (three reference swaps = one swap of the indices; the result sits in lattice `inew`), then pairs.
+    const bool triples = g.variant == 10 || lbm_triples_wanted(g, lbm_triples_level(g), model);
+    if ((g.variant == 9 || triples) && lbm_multi_applicable(g, model, triples ? 3 : 2)) {
+        // the depth-generic multi-step kernel.  9: pairs through its NSTEP = 2 instance (measurement);
+        // triples (three reference swaps = one swap of the indices; the result sits in lattice `inew`), then pairs.
         const CollideParams<T> cp = collide_params<T>(g, model);
-        if (g.variant == 10) {
+        if (triples) {
             for (; s + 3 < nsteps; s += 3) {
                 int rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 3, g.stream);
                 if (rc) return rc;
                 swap_lattices(g);
             }
         }
-        for (; s + 2 < nsteps; s += 2) {
+        for (; (g.variant == 9 || g.variant == 10) && s + 2 < nsteps; s += 2) {
             int rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 2, g.stream);
             if (rc) return rc;
             std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
@@ -967,6 +969,19 @@ int plbm_lbm_pair_kernel(plbm_handle g)
     }
     if (g->comm && !comm_pairs_agreed(*g)) return 0;
     return lbm_pair_flavour(*g);
+}
+
+int plbm_lbm_steps_per_pass(plbm_handle g, int collision)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return -1;
+    }
+    int level = lbm_triples_level(*g);
+    if (g->comm && !comm_triples_level(*g, &level)) level = -1;
+    if (level >= 0 && lbm_multi_applicable(*g, collision, 3) && (g->variant == 10 || lbm_triples_wanted(*g, level, collision))) return 3;
+    if (g->comm && !comm_pairs_agreed(*g)) return 1;
+    return lbm_pair_flavour(*g) ? 2 : 1;
 }
 
 int plbm_comm_unique_id(void* id128) { return comm_unique_id(id128); }

@@ -134,6 +134,7 @@ struct Comm {
     int parity = 0;        // halo slot holding the neighbours' lines of lattice `iold`
     bool halo_valid = false;
     bool pairs_ok = false;  // every slab of the ring can run the two-step kernel (agreed at init)
+    int triples_level = -1;  // minimum over the slabs of lbm_triples_level (agreed at init): three steps per pass
     int halo_of_lattice = 0;
 };
 
@@ -160,21 +161,22 @@ __host__ __device__ inline size_t off_hi(size_t slot_bytes, int p) { return (siz
 __host__ __device__ inline size_t off_flag_lo(size_t slot_bytes, int p) { return 4 * slot_bytes + 4 * (size_t)p; }
 __host__ __device__ inline size_t off_flag_hi(size_t slot_bytes, int p) { return 4 * slot_bytes + 8 + 4 * (size_t)p; }
 
-// Store the two boundary lines of each side of `f` (all nine populations, [2][9][ld]) into the neighbours'
+// Store the three boundary lines of each side of `f` (all nine populations, [PLBM_HALO_LINES][9][ld]) into the neighbours'
 // halo slots over NVLink (peer pointers), then -- last block to finish -- publish the epoch in their flags.
-//   lines 0, 1 -> rank lo's halo_hi[slot]      lines nx-2, nx-1 -> rank hi's halo_lo[slot]
-// One step consumes the nearest line only; a fused pair of steps (plbm_lbm2.cu) consumes both.
+//   lines 0, 1, 2 -> rank lo's halo_hi[slot]      lines nx-2, nx-1, nx-3 -> rank hi's halo_lo[slot]
+// One step consumes the nearest line only, a fused pair of steps (plbm_lbm2.cu) two, a fused triple (plbm_lbmn.cu) all three.
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_halo_push(const T* __restrict__ f, T* __restrict__ peer_lo_halo_hi, T* __restrict__ peer_hi_halo_lo, int nx, int ld,
                 unsigned* peer_lo_flag_hi, unsigned* peer_hi_flag_lo, unsigned epoch, unsigned* ticket)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 18 * ld) {
+    if (i < PLBM_HALO_LINES * 9 * ld) {
         const int lq = i / ld, y = i - lq * ld;
         const int l = lq / 9, q = lq - 9 * l;
-        peer_lo_halo_hi[i] = f[((size_t)q * nx + l) * (size_t)ld + y];
-        peer_hi_halo_lo[i] = f[((size_t)q * nx + (nx - 2 + l)) * (size_t)ld + y];
+        const int line_lo = min(l, nx - 1), line_hi = max(halo_lo_source_line(l, nx), 0);  // thin slabs repeat a line (unused)
+        peer_lo_halo_hi[i] = f[((size_t)q * nx + line_lo) * (size_t)ld + y];
+        peer_hi_halo_lo[i] = f[((size_t)q * nx + line_hi) * (size_t)ld + y];
     }
     __threadfence_system();
     __syncthreads();
@@ -276,6 +278,9 @@ static int p2p_setup(Grid& g)
     int pairs = lbm_pair_applicable(g) ? 1 : 0;
     if ((rc = agree_min(g, &pairs))) return rc;
     c->pairs_ok = pairs != 0;
+    int level = lbm_triples_level(g) + 1;  // agree_min works on non-negative flags
+    if ((rc = agree_min(g, &level))) return rc;
+    c->triples_level = level - 1;
     if (c->p2p) {
         for (int p = 0; p < 2; ++p) {  // the halo slots now live inside the exported block
             cudaFree(c->halo_lo[p]);
@@ -321,6 +326,12 @@ int comm_allreduce(Grid& g, double* values, int n, int op)
 
 int comm_transport_is_p2p(const Grid& g) { return g.comm && g.comm->p2p ? 1 : 0; }
 bool comm_pairs_agreed(const Grid& g) { return g.comm && g.comm->pairs_ok; }
+bool comm_triples_level(const Grid& g, int* level)
+{
+    if (!g.comm) return false;
+    *level = g.comm->triples_level;
+    return true;
+}
 
 int comm_unique_id(void* id128)
 {
@@ -357,7 +368,7 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
     c->nranks = nranks;
     c->lo = (rank + nranks - 1) % nranks;
     c->hi = (rank + 1) % nranks;
-    c->bytes = 18 * (size_t)g.ld * g.esize();   // [2 lines][9 populations][ld]
+    c->bytes = (size_t)PLBM_HALO_LINES * 9 * g.ld * g.esize();   // [3 lines][9 populations][ld]
     c->bytes9 = 9 * (size_t)g.ld * g.esize();
     NcclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
@@ -470,7 +481,7 @@ template <typename T> static int p2p_push(Grid& g, const T* f, cudaStream_t s)
     const unsigned e = ++c->epoch;
     const int slot = (int)(e & 1u);
     const size_t sb = c->slot_bytes;
-    const int n = 18 * g.ld;
+    const int n = PLBM_HALO_LINES * 9 * g.ld;
     k_halo_push<T><<<(n + 255) / 256, 256, 0, s>>>(f, (T*)(c->peer_lo + off_hi(sb, slot)), (T*)(c->peer_hi + off_lo(sb, slot)), g.nx, g.ld,
                                                   (unsigned*)(c->peer_lo + off_flag_hi(sb, slot)),
                                                   (unsigned*)(c->peer_hi + off_flag_lo(sb, slot)), e, c->ticket);
@@ -493,22 +504,27 @@ static int p2p_wait(Grid& g, unsigned e, cudaStream_t s)
     return PLBM_OK;
 }
 
-// One launch of the step kernel (pair = false) or of the two-step kernel (pair = true) over lines [x0, x1).
-template <typename T> static int lbm_range(Grid& g, LbmArgs<T> a, bool pair, int x0, int x1, int model, cudaStream_t s)
+// One launch over lines [x0, x1): the step kernel (depth 1), the two-step kernel (2) or the three-step kernel (3).
+template <typename T> static int lbm_range(Grid& g, LbmArgs<T> a, int depth, int x0, int x1, int model, cudaStream_t s)
 {
     if (x1 <= x0) return PLBM_OK;
-    if (pair) return launch_lbm_pair<T>(g, a.src, a.dst, x0, x1, a.halo_lo, a.halo_hi, model, a.cp, s);
+    if (depth == 3) return launch_lbm_multi<T>(g, a.src, a.dst, x0, x1, model, a.cp, 3, s, a.halo_lo, a.halo_hi);
+    if (depth == 2) return launch_lbm_pair<T>(g, a.src, a.dst, x0, x1, a.halo_lo, a.halo_hi, model, a.cp, s);
     a.x_begin = x0;
     a.x_end = x1;
     return launch_lbm<T>(a, model, true, g.variant, s);
 }
 
-// Both boundaries of the slab, lines [0, nb) and [nx - nb, nx), in ONE launch (they are two lines each: a launch per side
-// would leave the GPU four fifths empty twice).
-template <typename T> static int lbm_boundaries(Grid& g, LbmArgs<T> a, bool pair, int nb, int model, cudaStream_t s)
+// Both boundaries of the slab, lines [0, nb) and [nx - nb, nx): ONE launch for depths 1 and 2 (they are two lines each: a launch
+// per side would leave the GPU four fifths empty twice), one launch per side for depth 3.
+template <typename T> static int lbm_boundaries(Grid& g, LbmArgs<T> a, int depth, int nb, int model, cudaStream_t s)
 {
-    if (2 * nb >= g.nx) return lbm_range<T>(g, a, pair, 0, g.nx, model, s);  // the boundaries are the whole slab
-    if (pair) return launch_lbm_pair_boundaries<T>(g, a.src, a.dst, nb, a.halo_lo, a.halo_hi, model, a.cp, s);
+    if (2 * nb >= g.nx) return lbm_range<T>(g, a, depth, 0, g.nx, model, s);  // the boundaries are the whole slab
+    if (depth == 3) {
+        int rc = lbm_range<T>(g, a, 3, 0, nb, model, s);
+        return rc ? rc : lbm_range<T>(g, a, 3, g.nx - nb, g.nx, model, s);
+    }
+    if (depth == 2) return launch_lbm_pair_boundaries<T>(g, a.src, a.dst, nb, a.halo_lo, a.halo_hi, model, a.cp, s);
     a.x_begin = 0;
     a.x_end = g.nx;
     a.x_split = nb;
@@ -516,17 +532,30 @@ template <typename T> static int lbm_boundaries(Grid& g, LbmArgs<T> a, bool pair
     return launch_lbm<T>(a, model, true, g.variant, s);
 }
 
-// Lattice roles after one step (index swap) or after a fused pair (two reference swaps = the indices stay,
-// the result sits in the buffer that was `inew`: the buffers trade places).
-static void finish_steps(Grid& g, bool pair)
+// Lattice roles after one step or a fused triple (an odd number of reference swaps = one index swap) or after a fused pair (two
+// reference swaps = the indices stay, the result sits in the buffer that was `inew`: the buffers trade places).
+static void finish_steps(Grid& g, int depth)
 {
-    if (pair) {
+    if (depth == 2) {
         std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
         for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
     } else {
         std::swap(g.iold, g.inew);
     }
     g.comm->halo_of_lattice = g.iold;
+}
+
+// How many steps the next launch of a call advances: three while more than three remain and the ring takes triples for this
+// collision, two while more than two remain, else one (the last step stays single so that lattice `inew` ends up holding state
+// n-1 like the reference, see step_lbm_t).  Every rank computes the same sequence.
+static int next_depth(const Grid& g, int model, int s, int nsteps)
+{
+    const Comm* c = g.comm;
+    const bool triples = c->triples_level >= 0 && lbm_multi_applicable(g, model, 3) &&
+                         (g.variant == 10 || lbm_triples_wanted(g, c->triples_level, model));
+    if (triples && s + 3 < nsteps) return 3;
+    const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
+    return pairs && s + 2 < nsteps ? 2 : 1;
 }
 
 // p2p transport, two streams per rank:
@@ -553,12 +582,9 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
     }
     // everything enqueued on M so far (previous calls, the push above) precedes the first boundary launch
     PLBM_CUDA(cudaEventRecord(c->ev_interior, M));
-    const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
     bool first = true;
     for (int s = 0; s < nsteps;) {
-        // two steps per pass over HBM while at least one single step remains (the last step stays single so
-        // that lattice `inew` ends up holding state n-1 like the reference, see step_lbm_t)
-        const bool pair = pairs && s + 2 < nsteps;
+        const int depth = next_depth(g, model, s, nsteps);
         const unsigned e = c->epoch;
         const int slot = (int)(e & 1u);
         LbmArgs<T> a;
@@ -570,20 +596,20 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         a.halo_lo = (const T*)c->halo_lo[slot];
         a.halo_hi = (const T*)c->halo_hi[slot];
         a.cp = cp;
-        // two boundary lines per side (a single step would need only one, but the message always carries two so that a
-        // pair may follow): they need the halo, and they are what the neighbours get next
-        const int nb = g.nx >= 4 ? 2 : g.nx;
+        // boundary lines per side: as many as the launch advances steps, two for a single step (it would need only one; the
+        // message always carries three so that any launch may follow).  They need the halo, and they are what the neighbours get next
+        const int nb = depth == 3 ? 3 : (g.nx >= 4 ? 2 : g.nx);
         PLBM_CUDA(cudaStreamWaitEvent(B, c->ev_interior, 0));                  // interior of the previous launch (wrote src, read dst)
         if (!first) PLBM_CUDA(cudaStreamWaitEvent(M, c->ev_boundary, 0));      // boundaries of the previous launch (wrote src)
         if ((rc = p2p_wait(g, e, B))) return rc;                               // the neighbours' lines of lattice `iold` have landed
-        if ((rc = lbm_boundaries<T>(g, a, pair, nb, model, B))) return rc;
+        if ((rc = lbm_boundaries<T>(g, a, depth, nb, model, B))) return rc;
         if ((rc = p2p_push<T>(g, a.dst, B))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_boundary, B));
         a.halo_lo = a.halo_hi = nullptr;
-        if ((rc = lbm_range<T>(g, a, pair, nb, g.nx - nb, model, M))) return rc;
+        if ((rc = lbm_range<T>(g, a, depth, nb, g.nx - nb, model, M))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_interior, M));
-        finish_steps(g, pair);
-        s += pair ? 2 : 1;
+        finish_steps(g, depth);
+        s += depth;
         first = false;
     }
     PLBM_CUDA(cudaStreamWaitEvent(M, c->ev_boundary, 0));  // whatever follows on the grid's stream sees the whole lattice
@@ -603,9 +629,8 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         c->halo_valid = true;
         c->halo_of_lattice = g.iold;
     }
-    const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
     for (int s = 0; s < nsteps;) {
-        const bool pair = pairs && s + 2 < nsteps;
+        const int depth = next_depth(g, model, s, nsteps);
         const int p = c->parity;
         LbmArgs<T> a;
         a.src = g.lat<T>(g.iold);
@@ -616,10 +641,10 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         a.halo_lo = (const T*)c->halo_lo[p];
         a.halo_hi = (const T*)c->halo_hi[p];
         a.cp = cp;
-        const int nb = g.nx >= 4 ? 2 : g.nx;
-        // two boundary lines per side first: they need the neighbours' lines, and produce what must be sent
+        const int nb = depth == 3 ? 3 : (g.nx >= 4 ? 2 : g.nx);
+        // the boundary lines of each side first: they need the neighbours' lines, and produce what must be sent
         PLBM_CUDA(cudaStreamWaitEvent(g.stream, c->ev_halo[p], 0));
-        if ((rc = lbm_boundaries<T>(g, a, pair, nb, model, g.stream))) return rc;
+        if ((rc = lbm_boundaries<T>(g, a, depth, nb, model, g.stream))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_consumed[p], g.stream));
         if ((rc = launch_halo_pack<T>(g, a.dst, (T*)c->send_lo, (T*)c->send_hi, g.stream))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_packed, g.stream));
@@ -627,10 +652,10 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         // interior, overlapped with the exchange
         // (the send buffers are re-packed next step, ordered after ev_halo[p^1], recorded after the sends completed)
         a.halo_lo = a.halo_hi = nullptr;
-        if ((rc = lbm_range<T>(g, a, pair, nb, g.nx - nb, model, g.stream))) return rc;
-        finish_steps(g, pair);
+        if ((rc = lbm_range<T>(g, a, depth, nb, g.nx - nb, model, g.stream))) return rc;
+        finish_steps(g, depth);
         c->parity = p ^ 1;
-        s += pair ? 2 : 1;
+        s += depth;
     }
     return PLBM_OK;
 }

@@ -445,11 +445,15 @@ int launch_march_shape(const Grid& g, const T* fin, T* fout, T dt, T of, T oh, T
     // block shape: measurement knobs PLBM_MARCH_NT (128 / 256) and PLBM_MARCH_MINB
     static const int nt = env_int("PLBM_MARCH_NT", 128);
     static const int minb = env_int("PLBM_MARCH_MINB", sizeof(T) == 8 ? 3 : 4);
-    // PLBM_MARCH_FORM=1: k_fv_march_s (faces from sums, own rows in registers): 128 threads x 2 / 3 blocks, 64 threads x 5 blocks
-    static const int form = env_int("PLBM_MARCH_FORM", 0);
+    // PLBM_MARCH_FORM: 0 = k_fv_march (operands from the ring), 1 = k_fv_march_s (faces from sums, own rows in registers; 128 threads
+    // x 2 / 3 blocks, 64 threads x 5 blocks).  Measured at 2048^2 (r02e, GLUPS, form 0 -> form 1 with two blocks per SM): DUGKS fp32
+    // 36.1 -> 40.3, Bardow fp32 31.6 -> 38.8, DUGKS fp64 24.3 -> 23.9 (226 registers: 18.2 when capped at 168 for three blocks),
+    // Bardow fp64 23.5 -> 19.9.  Default: the sum form in fp32, the ring form in fp64.
+    static const int form = env_int("PLBM_MARCH_FORM", sizeof(T) == 4 ? 1 : 0);
     if (form == 1) {
+        static const int minb_s = env_int("PLBM_MARCH_MINB", 2);
         if (nt == 64) return launch_march<T, MODE, MODEL, 64, 5, true>(g, fin, fout, dt, of, oh, oc, cp, s);
-        if (minb >= 3) return launch_march<T, MODE, MODEL, 128, 3, true>(g, fin, fout, dt, of, oh, oc, cp, s);
+        if (minb_s >= 3) return launch_march<T, MODE, MODEL, 128, 3, true>(g, fin, fout, dt, of, oh, oc, cp, s);
         return launch_march<T, MODE, MODEL, 128, 2, true>(g, fin, fout, dt, of, oh, oc, cp, s);
     }
     if (nt == 256) {

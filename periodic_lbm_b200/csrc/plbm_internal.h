@@ -135,7 +135,19 @@ int launch_lbm_pair_fma(const Grid& g, const T* src, T* dst, int x_begin, int x_
 bool lbm_multi_applicable(const Grid& g, int model, int nstep);
 template <typename T>
 int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, int nstep,
-                     cudaStream_t s);
+                     cudaStream_t s, const T* halo_lo = nullptr, const T* halo_hi = nullptr);
+// Halo message of the slab decomposition: the PLBM_HALO_LINES nearest lines of each neighbour, all nine populations,
+// [PLBM_HALO_LINES][9][ld].  halo_lo holds lines -2, -1, -3 in that order (the first two are what one step / a fused pair read --
+// k_lbm, k_lbm2 --, the third was appended for three steps per pass); halo_hi holds lines nx, nx+1, nx+2.
+constexpr int PLBM_HALO_LINES = 3;
+__host__ __device__ constexpr int halo_lo_index(int col) { return col == -3 ? 2 : col + 2; }          // col in [-3, -1]
+__host__ __device__ constexpr int halo_lo_source_line(int l, int nx) { return l < 2 ? nx - 2 + l : nx - 3; }  // sender's line of slot l
+// Three steps per pass (k_lbmn_bulk) where they were measured to win, see step_lbm_t.  Level of a grid / slab: -1 the kernel does
+// not apply, 0 below 2048^2 nodes, 1 from 2048^2, 2 from 4096^2 (a ring agrees on the minimum over its slabs: every rank must issue
+// the same launches); lbm_triples_wanted: does this collision / precision / variant take triples at that level.
+int lbm_triples_level(const Grid& g);
+bool lbm_triples_wanted(const Grid& g, int level, int model);
+bool comm_triples_level(const Grid& g, int* level);  // the ring's agreed level
 // TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice
 int make_tensor_maps(Grid& g);
 template <typename T>

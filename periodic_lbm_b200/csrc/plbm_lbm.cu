@@ -233,22 +233,23 @@ template <typename T> int launch_lbm(const LbmArgs<T>& a, int model, bool stream
 template int launch_lbm<double>(const LbmArgs<double>&, int, bool, int, cudaStream_t);
 template int launch_lbm<float>(const LbmArgs<float>&, int, bool, int, cudaStream_t);
 
-// Pack the two boundary lines of each side into contiguous send buffers (multi-GPU ring, NCCL transport):
-// send_lo <- lines 0, 1 (become the low neighbour's halo_hi), send_hi <- lines nx-2, nx-1 (the high
-// neighbour's halo_lo), all nine populations, [2][9][ld].
+// Pack the PLBM_HALO_LINES boundary lines of each side into contiguous send buffers (multi-GPU ring, NCCL transport):
+// send_lo <- lines 0, 1, 2 (become the low neighbour's halo_hi), send_hi <- lines nx-2, nx-1, nx-3 (the high neighbour's
+// halo_lo, in the order of plbm_internal.h), all nine populations.  Slabs thinner than three lines repeat a line (unused).
 template <typename T> __global__ void k_halo_pack(const T* f, T* send_lo, T* send_hi, int nx, int ld)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 18 * ld) return;
+    if (i >= PLBM_HALO_LINES * 9 * ld) return;
     const int lq = i / ld, y = i - lq * ld;
     const int l = lq / 9, q = lq - 9 * l;
-    send_lo[i] = f[((size_t)q * nx + l) * (size_t)ld + y];
-    send_hi[i] = f[((size_t)q * nx + (nx - 2 + l)) * (size_t)ld + y];
+    const int line_lo = min(l, nx - 1), line_hi = max(halo_lo_source_line(l, nx), 0);
+    send_lo[i] = f[((size_t)q * nx + line_lo) * (size_t)ld + y];
+    send_hi[i] = f[((size_t)q * nx + line_hi) * (size_t)ld + y];
 }
 
 template <typename T> int launch_halo_pack(const Grid& g, const T* f, T* send_lo, T* send_hi, cudaStream_t s)
 {
-    const int n = 18 * g.ld;
+    const int n = PLBM_HALO_LINES * 9 * g.ld;
     k_halo_pack<T><<<(n + 255) / 256, 256, 0, s>>>(f, send_lo, send_hi, g.nx, g.ld);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLBM_CUDA(cudaGetLastError());

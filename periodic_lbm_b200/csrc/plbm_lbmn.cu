@@ -47,6 +47,10 @@ template <typename T> struct LbmNArgs {
     int ty;              // interior rows per strip (multiple of V)
     int nstrips;         // strips along y
     int seglen;          // columns per x segment
+    // slab decomposition: the ring neighbours' three nearest lines, all nine populations, [PLBM_HALO_LINES][9][ld] in the order
+    // of plbm_internal.h (lo: lines -2, -1, -3; hi: lines nx, nx+1, nx+2).  nullptr = periodic self-wrap.
+    const T* halo_lo;
+    const T* halo_hi;
     CollideParams<T> cp;
 };
 
@@ -105,7 +109,12 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
     static_assert(NSTEP >= 2, "depth of the temporal blocking");
     constexpr int NR = NSTEP - 1;  // rings
     constexpr int W = NT * V;      // rows of one ring column: logical rows y_lo - NR V .. y_lo - NR V + W - 1
-    constexpr int WS = W + 2 * V;  // rows of one staged raw column: logical rows y_lo - NSTEP V .. (one more vector each side)
+    // staged raw column: level 1 works on the strip +- NR V rows and pulls one more row on each side; the staged range is rounded
+    // out to 16 bytes (bulk copies): HS rows beyond the strip on each side, thread 0's first row sits at stage row OFF
+    constexpr int VA = 16 / (int)sizeof(T);
+    constexpr int HS = (NR * V + 1 + VA - 1) / VA * VA;
+    constexpr int OFF = HS - NR * V;
+    constexpr int WS = W + 2 * OFF;
     extern __shared__ __align__(128) unsigned char smem_n[];
     T* ring = reinterpret_cast<T*>(smem_n);  // [NR][RN_SLOTS][W]
     T* stage = ring + NR * RN_SLOTS * W;     // [2][9][WS]
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
         return yl >= y_lo - h && yl < y_hi + h;
     };
     // staged logical rows [r0, r1): what level 1 reads, whole vectors
-    const int r0 = y_lo - NSTEP * V, r1 = y_hi + NSTEP * V;
+    const int r0 = y_lo - HS, r1 = y_hi + HS;
 
     if (t == 0) {
         mbarrier_init(bar(0), 1);
@@ -142,8 +151,15 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
             int col = xl - cxi(q);
-            col = col < 0 ? col + a.nx : (col >= a.nx ? col - a.nx : col);
-            const T* line = a.src + ((size_t)q * a.nx + col) * (size_t)a.ld;
+            const T* line;
+            if (a.halo_lo && col < 0) {
+                line = a.halo_lo + ((size_t)halo_lo_index(col) * 9 + q) * (size_t)a.ld;
+            } else if (a.halo_hi && col >= a.nx) {
+                line = a.halo_hi + ((size_t)(col - a.nx) * 9 + q) * (size_t)a.ld;
+            } else {
+                col = col < 0 ? col + a.nx : (col >= a.nx ? col - a.nx : col);
+                line = a.src + ((size_t)q * a.nx + col) * (size_t)a.ld;
+            }
             T* dst = stage + (s * 9 + q) * WS;
             // periodic pieces of [r0, r1): below 0, inside, beyond ny (all multiples of V rows = 16 bytes)
             if (r0 < 0) bulk_copy_g2s(smem_addr(dst), line + (a.ny + r0), (uint32_t)(-r0 * sizeof(T)), bar(s));
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
         mbarrier_wait(bar(k & 1), (uint32_t)((k >> 1) & 1));
         if (active(1)) {
             T n[V][9];
-            const T* st = stage + ((k & 1) * 9) * WS + V + t * V;  // stage row of this thread's first row
+            const T* st = stage + ((k & 1) * 9) * WS + OFF + t * V;  // stage row of this thread's first row
             pull_rows<T, V>([&](int q) { return st + q * WS; }, n);
 #pragma unroll
             for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
@@ -225,6 +241,9 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
     }
 }
 
+#ifndef PLBM_MULTI_WIDE_DEFAULT
+#define PLBM_MULTI_WIDE_DEFAULT 1
+#endif
 int env_knob(const char* name, int dflt)
 {
     const char* e = getenv(name);
@@ -233,14 +252,22 @@ int env_knob(const char* name, int dflt)
 
 // NT = 128: 74 KB (NSTEP 2, three blocks per SM) / 111 KB (NSTEP 3, two blocks per SM) of shared memory per block;
 // NT = 256 (NSTEP 3 only, PLBM_MULTI_NT=256): one 222 KB block of eight warps per SM, strips of up to 504 rows (fp64)
-template <typename T, int MODEL, int NSTEP, int NT>
-int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
+// WIDE: 8 bytes per thread and 256 threads -- the shared memory of the 128-thread shape with twice the warps (NSTEP 3: two blocks
+// = sixteen warps per SM instead of eight)
+template <typename T, int MODEL, int NSTEP, int NT, bool WIDE = false>
+int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
+             cudaStream_t s)
 {
-    constexpr int V = 16 / (int)sizeof(T);
-    constexpr int MINB = NT == 256 ? 1 : (NSTEP == 2 ? 3 : 2);
-    constexpr int W = NT * V, WS = W + 2 * V;
+    constexpr int VA = 16 / (int)sizeof(T);
+    constexpr int V = WIDE ? VA / 2 : VA;
+    constexpr int HS = ((NSTEP - 1) * V + 1 + VA - 1) / VA * VA;
+    constexpr int W = NT * V, WS = W + 2 * (HS - (NSTEP - 1) * V);
     constexpr size_t smem = ((size_t)(NSTEP - 1) * RN_SLOTS * W + 2 * 9 * WS) * sizeof(T) + 16;
     static_assert(smem <= 227 * 1024, "shared memory of one block");
+    // blocks per SM: what the shared memory holds (1 KB per block is the system's), at most 2048 threads and 24 blocks
+    constexpr int by_smem = (int)((size_t)(228 * 1024) / (smem + 1024));
+    constexpr int by_threads = 2048 / NT;
+    constexpr int MINB = by_smem < by_threads ? (by_smem < 24 ? by_smem : 24) : (by_threads < 24 ? by_threads : 24);
     if (x_end <= x_begin) return PLBM_OK;
     auto kern = k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP>;
     static bool configured[64] = {false};
@@ -257,12 +284,14 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     a.ld = g.ld;
     a.x_begin = x_begin;
     a.x_end = x_end;
+    a.halo_lo = halo_lo;
+    a.halo_hi = halo_hi;
     a.cp = cp;
     // the fewest strips (2 (NSTEP-1) V redundant rows each), 64-column segments (2 (NSTEP-1) warm-up columns each)
     const int ncols = x_end - x_begin;
     const int ty_max = (NT - 2 * (NSTEP - 1)) * V;
     a.nstrips = (g.ny + ty_max - 1) / ty_max;
-    a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + V - 1) / V * V;
+    a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + VA - 1) / VA * VA;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
     static const int seg_cols = env_knob("PLBM_MULTI_SEGLEN", 64) < 1 ? 64 : env_knob("PLBM_MULTI_SEGLEN", 64);
     int nseg = (ncols + seg_cols - 1) / seg_cols;
@@ -274,13 +303,14 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     return PLBM_OK;
 }
 
-template <typename T, int NSTEP, int NT>
-int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, cudaStream_t s)
+template <typename T, int NSTEP, int NT, bool WIDE = false>
+int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
+               const CollideParams<T>& cp, cudaStream_t s)
 {
     switch (model) {
-    case M_BGK: return launch_n<T, M_BGK, NSTEP, NT>(g, src, dst, x_begin, x_end, cp, s);
-    case M_TRT: return launch_n<T, M_TRT, NSTEP, NT>(g, src, dst, x_begin, x_end, cp, s);
-    case M_RR: return launch_n<T, M_RR, NSTEP, NT>(g, src, dst, x_begin, x_end, cp, s);
+    case M_BGK: return launch_n<T, M_BGK, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_TRT: return launch_n<T, M_TRT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_RR: return launch_n<T, M_RR, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
     }
     set_error("launch_lbm_multi: collision model not instantiated for the experimental multi-step kernel");
     return PLBM_ERR_ARG;
@@ -297,22 +327,61 @@ bool lbm_multi_applicable(const Grid& g, int model, int nstep)
            g.ny >= 8 * v;
 }
 
-// `nstep` (2 or 3) fused steps src -> dst for columns [x_begin, x_end), periodic self-wrap (single GPU).
+// THREE steps per pass over HBM (k_lbmn_bulk; bit-identical like the pairs) where they were measured to win on B200.  Shape: one
+// row (fp64) per thread, 128-thread blocks, four blocks = sixteen warps per SM ("wide"): the 128-thread, 16-byte shape has the shared
+// memory for two blocks = eight warps per SM only and is bound by latency (ncu r02a: fp64 pipe 47 %, DRAM 62 %, nothing saturated),
+// 256-thread blocks of one row per thread wait at the three barriers per column (ncu r02f: barrier stall 2.1 per issue).
+// GLUPS, pairs (k_lbm2_bulk) -> triples, 16-byte/128 | one-row/256 | one-row/128 (r02a, r02f, r02g):
+//   BGK fp64  8192^2  83.3 -> 80.5 |  91.5 |  97.9     bench slab 32768 x 4096  85.3 -> 83.8 | 93.6 | 99.2     2048^2  72.4 -> 68.1 | 73.0 | 75.6
+//   TRT fp64  8192^2  83.4 -> 93.6 | 102.5 | 112.7     RR fp64  8192^2  68.5 -> 57.8 | 66.4 | 69.1
+//   BGK fp32  8192^2 149.3 -> 119.5 | 136.4 | 148.2    RR fp32  8192^2 102.5 -> 83.8 | 100.6 | 107.6
+// TRT has no division and BGK one, so a third collision fits under the fp64 pipe once enough warps hide its latency; RR fp64 is at
+// the fp64 pipe either way and fp32 gains little: both stay on pairs, and so do small grids (1024^2 TRT: 63.0 -> 25.3, too few
+// blocks for 64-column segments).  PLBM_TRIPLES=0: never; 2: BGK / TRT fp64 at every size (tests).
+int lbm_triples_level(const Grid& g)
+{
+    if (g.nx < 2 * PLBM_HALO_LINES || !lbm_multi_applicable(g, M_BGK, 3)) return -1;
+    const long long nodes = (long long)g.nx * g.ny;
+    return nodes >= 4096LL * 4096LL ? 2 : (nodes >= 2048LL * 2048LL ? 1 : 0);
+}
+
+bool lbm_triples_wanted(const Grid& g, int level, int model)
+{
+    static const int mode = env_knob("PLBM_TRIPLES", 1);
+    if (mode == 0 || level < 0 || g.variant != 0 || g.prec != PLBM_F64) return false;
+    if (mode >= 2) return model == M_TRT || model == M_BGK;
+    return (model == M_TRT || model == M_BGK) && level >= 1;
+}
+
+// `nstep` (2 or 3) fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' nearest lines
+// under a slab decomposition ([PLBM_HALO_LINES][9][ld]), nullptr = periodic self-wrap.
 template <typename T>
 int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, int nstep,
-                     cudaStream_t s)
+                     cudaStream_t s, const T* halo_lo, const T* halo_hi)
 {
     if (!lbm_multi_applicable(g, model, nstep)) {
         set_error("launch_lbm_multi: not applicable to this grid / collision / depth");
         return PLBM_ERR_ARG;
     }
-    if (nstep == 2) return dispatch_n<T, 2, 128>(g, src, dst, x_begin, x_end, model, cp, s);
-    static const int nt = env_knob("PLBM_MULTI_NT", 128);
-    if (nt == 256) return dispatch_n<T, 3, 256>(g, src, dst, x_begin, x_end, model, cp, s);
-    return dispatch_n<T, 3, 128>(g, src, dst, x_begin, x_end, model, cp, s);
+#define PLBM_N(NS, NT, WD) return dispatch_n<T, NS, NT, WD>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s)
+    if (nstep == 2) PLBM_N(2, 128, false);
+    static const int nt = env_knob("PLBM_MULTI_NT", 0);  // 0: the default of the shape (128 threads)
+    static const int wide = env_knob("PLBM_MULTI_WIDE", PLBM_MULTI_WIDE_DEFAULT);
+    // small blocks (measurement knobs): the barriers of a level couple two warps / one warp instead of eight
+    if (wide && nt == 64) PLBM_N(3, 64, true);
+    if (wide && nt == 32) PLBM_N(3, 32, true);
+    if (wide && nt == 256) PLBM_N(3, 256, true);
+    if (wide) PLBM_N(3, 128, true);  // the default: four blocks of four warps per SM
+    if (nt == 64) PLBM_N(3, 64, false);
+    if (nt == 32) PLBM_N(3, 32, false);
+    if (nt == 256) PLBM_N(3, 256, false);
+    PLBM_N(3, 128, false);
+#undef PLBM_N
 }
 
-template int launch_lbm_multi<double>(const Grid&, const double*, double*, int, int, int, const CollideParams<double>&, int, cudaStream_t);
-template int launch_lbm_multi<float>(const Grid&, const float*, float*, int, int, int, const CollideParams<float>&, int, cudaStream_t);
+template int launch_lbm_multi<double>(const Grid&, const double*, double*, int, int, int, const CollideParams<double>&, int, cudaStream_t,
+                                      const double*, const double*);
+template int launch_lbm_multi<float>(const Grid&, const float*, float*, int, int, int, const CollideParams<float>&, int, cudaStream_t,
+                                     const float*, const float*);
 
 }  // namespace plbm

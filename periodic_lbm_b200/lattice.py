@@ -134,6 +134,15 @@ class LatticeGrid:
             check(k, "lbm_pair_kernel")
         return ("k_lbm", "k_lbm2", "k_lbm2_bulk")[k]
 
+    def steps_per_pass(self, collision=None):
+        """Time steps one pass over HBM advances in a many-step perform_lbm_step call: 3 (k_lbmn_bulk), 2 (k_lbm2 / k_lbm2_bulk)
+        or 1 (k_lbm).  `collision`: a collide_* procedure (default: grid.collision)."""
+        coll = collision if collision is not None else self.collision
+        k = lib.plbm_lbm_steps_per_pass(self._h, _COLLISION_ID[coll] if callable(coll) else int(coll))
+        if k < 0:
+            check(k, "lbm_steps_per_pass")
+        return k
+
     def set_fdm_stencil(self, stencil):
         """Derivative stencil of stream_fdm_bardow; the reference picks it at compile time with -DFDM_WLS,
         -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660)."""

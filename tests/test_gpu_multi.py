@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p2p", env=None, expect_kernel=None):
+def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p2p", env=None, expect_kernel=None, expect_steps_per_pass=None):
     os.environ["PLBM_HALO"] = halo
     os.environ.update(env or {})
     import periodic_lbm_b200 as p
@@ -48,6 +48,8 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p
         g.streaming = p.lbm_stream
         if expect_kernel is not None:
             assert g.pair_kernel() == expect_kernel, (g.pair_kernel(), expect_kernel)
+        if expect_steps_per_pass is not None:
+            assert g.steps_per_pass() == expect_steps_per_pass, (g.steps_per_pass(), expect_steps_per_pass)
         # two calls: exercises the "halo already in flight" path between calls
         p.perform_lbm_step(g, steps // 2)
         p.perform_lbm_step(g, steps - steps // 2)
@@ -70,12 +72,12 @@ def _analytic_fields(nxg, ny, dtype):
     return (0.02 * np.cos(x) * np.sin(y)).astype(dtype), (-0.02 * np.sin(x) * np.cos(y)).astype(dtype)
 
 
-def _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, halo, env=None, expect_kernel=None):
+def _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, halo, env=None, expect_kernel=None, expect_steps_per_pass=None):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     idq, outq = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo, env, expect_kernel))
+    procs = [ctx.Process(target=_worker, args=(r, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo, env, expect_kernel, expect_steps_per_pass))
              for r in range(world)]
     for pr in procs:
         pr.start()
@@ -132,6 +134,27 @@ def test_slabs_with_bulk_interior_bitwise_equal_single_gpu(plbm, world, prec, co
         assert d["max_speed"] == diag["max_speed"] and d["min_speed"] == diag["min_speed"]
         np.testing.assert_allclose([d["sum_rho"], d["kinetic_energy"]], [diag["sum_rho"], diag["kinetic_energy"]], rtol=1e-12)
         np.testing.assert_allclose(l, l2, rtol=1e-12)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+@pytest.mark.parametrize("nxg,ny,steps,coll_id", [(512, 2048, 10, 0), (64, 64, 11, 1), (48, 132, 8, 0), (24, 36, 7, 1)])
+def test_slabs_with_three_steps_per_pass_bitwise_equal_single_gpu(plbm, world, halo, nxg, ny, steps, coll_id):
+    """Three steps per pass under a slab decomposition (fp64 BGK / TRT; PLBM_TRIPLES=2 forces them at every size): k_lbmn_bulk on the
+    interior and, reading the neighbours' three halo lines, on the three boundary lines of each side; message of three lines per
+    direction per launch.  The slabs hold the single-GPU result (default kernels of the single GPU: pairs / cluster) bit for bit."""
+    if plbm.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    if nxg // world < 6:
+        pytest.skip("slabs thinner than six lines do not take triples")
+    seed = 11
+    parts = _run_ring(plbm, world, nxg, ny, steps, coll_id, "f64", seed, halo, env={"PLBM_TRIPLES": "2"}, expect_steps_per_pass=3)
+    assert all(t[3] == (1 if halo == "p2p" else 0) for t in parts)
+    multi = np.concatenate([t[2] for t in parts], axis=1)
+    single, diag, l2, om = _single(plbm, nxg, ny, steps, coll_id, "f64", seed)
+    assert np.array_equal(multi[:, :, :ny], single[:, :, :ny])
+    for t in parts:
+        assert t[4]["max_speed"] == diag["max_speed"]
 
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])

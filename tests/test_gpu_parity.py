@@ -157,13 +157,12 @@ def test_two_step_kernel(plbm, nx, ny, prec):
             plbm.dealloc_grid(g)
 
 
-@pytest.mark.skipif(os.environ.get("PLBM_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="experimental depth-generic multi-step kernel (csrc/plbm_lbmn.cu): set PLBM_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("nx,ny", [(64, 64), (16, 132), (40, 516), (300, 260), (5, 1024), (37, 2048), (70, 16), (8, 32), (4, 48)])
 def test_multi_step_kernel_experimental(plbm, nx, ny, prec):
     """k_lbmn_bulk: variant 9 = pairs through its NSTEP = 2 instance, variant 10 = triples (+ pairs for the rest);
-    the schedule itself is pinned on the CPU by tests/test_multi_step_schedule.py."""
+    the schedule itself is pinned on the CPU by tests/test_multi_step_schedule.py.  (First run on a B200 in round 2, green:
+    profiles/r02_a_pytest_experimental.txt; the name is kept.)"""
     for nsteps, (coll, ocoll) in zip((3, 4, 5, 8, 9, 11), collisions(plbm)[:3] * 2):
         og, g0 = make_pair(plbm, nx, ny, prec)
         f0 = g0.download_f(g0.iold)
@@ -184,6 +183,32 @@ def test_multi_step_kernel_experimental(plbm, nx, ny, prec):
             plbm.update_macros(g)
             assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v), f"variant {variant}"
             plbm.dealloc_grid(g)
+
+
+@pytest.mark.parametrize("coll_name", ["bgk", "trt"])
+@pytest.mark.parametrize("nsteps", [8, 10, 4])
+def test_fp64_default_takes_three_steps_per_pass_and_stays_bit_identical(plbm, nsteps, coll_name):
+    """Default stepping (variant 0) of collide_bgk / collide_trt in fp64 from 2048^2 nodes up advances THREE steps per pass over
+    HBM (k_lbmn_bulk<3>, csrc/plbm_lbmn.cu lbm_triples_wanted): lattices, indices and lagged macros equal the oracle's bit for
+    bit, and the launch count is the triples schedule's (8 steps: 2 triples + 2 single steps; 10: 3 triples + 1; 4: 1 triple + 1)."""
+    nx, ny = 2048, 2048
+    og, g = make_pair(plbm, nx, ny, "f64")
+    coll, ocoll = {"bgk": (plbm.collide_bgk, Oracle.BGK), "trt": (plbm.collide_trt, Oracle.TRT)}[coll_name]
+    g.collision, g.streaming = coll, plbm.lbm_stream
+    assert g.steps_per_pass() == 3
+    assert g.steps_per_pass(plbm.collide_rr) == 2
+    l0 = plbm.launch_count()
+    plbm.perform_lbm_step(g, nsteps)
+    launches = plbm.launch_count() - l0
+    assert launches == (nsteps - 1) // 3 + (nsteps - 3 * ((nsteps - 1) // 3)), launches
+    og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
+    assert (g.iold, g.inew) == (og.iold, og.inew)
+    assert_same_lattice(g, og, g.iold, og.iold, ny)
+    assert_same_lattice(g, og, g.inew, og.inew, ny)
+    plbm.update_macros(g)
+    r, u, v = og.update_macros(lagged=True)
+    assert np.array_equal(g.rho, r) and np.array_equal(g.ux, u) and np.array_equal(g.uy, v)
+    plbm.dealloc_grid(g)
 
 
 @pytest.mark.parametrize("prec", PRECS)

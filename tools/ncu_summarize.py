@@ -31,7 +31,10 @@ SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1.0, 
 
 
 def summarise(path, nodes, steps):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):  # a raw page already exported (profiles/*_ncu_full_*.csv)
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, first = rows[0], rows[1], rows[2]
     out = {"kernel": first[head.index("Kernel Name")], "nodes_per_launch": nodes, "steps_per_launch": steps}

@@ -10,12 +10,15 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import periodic_lbm_b200 as p  # noqa: E402
 
+# 9 / 10: depth-generic two / three steps per pass; 11: FMA twin of the two-step kernels; 12: scalar fp32 collisions (packed is the
+# default); 3 / 4 on the FVM / DUGKS paths: FMA twin of the tile kernel / marching kernel (PLBM_MARCH_FORM=1: its sum form)
+VARIANTS = tuple(int(v) for v in os.environ.get("PLBM_SANITIZE_VARIANTS", "0,1,2,3,4,5,6,7,8,9,10,11,12").split(","))
 rng = np.random.default_rng(1)
 for prec in ("f64", "f32"):
     for nx, ny in ((67, 53), (5, 3), (64, 64), (40, 130), (36, 520)):
         # 5..8: the two-step kernels also on grids the cluster kernel would take (6 per-thread loads, 7 bulk async
         # copies, 8 = 7 over the slab schedule's line ranges)
-        for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):
+        for variant in VARIANTS:
             g = p.alloc_grid(nx, ny, nf=3, precision=prec)
             p.set_properties(g, 0.02, 0.3, 0.25)
             g.rho[:] = 1.0 + 0.01 * rng.random((nx, ny))
@@ -25,11 +28,11 @@ for prec in ("f64", "f32"):
             g.set_variant(variant)
             for coll in (p.collide_bgk, p.collide_trt, p.collide_rr, p.collide_bgk_split, p.collide_trt_split, p.collide_bgk_improved):
                 g.collision, g.streaming = coll, p.lbm_stream
-                p.perform_lbm_step(g, 5)
+                p.perform_lbm_step(g, 8 if variant == 10 else 5)
                 p.perform_lbm_step(g, 1)
                 p.lbm_stream(g)
                 coll(g)
-            if variant in (0, 2):
+            if variant in (0, 2, 3, 4):
                 for stream in (p.stream_fvm_bardow, p.stream_fdm_bardow, p.stream_fdm_sofonea):
                     g.collision, g.streaming = p.collide_rr, stream
                     p.perform_step(g, 2)
@@ -40,7 +43,7 @@ for prec in ("f64", "f32"):
                     p.perform_step(g, 1)
                 g.collision, g.streaming = p.collide_bgk, p.lbm_stream
                 p.perform_triple_step(g, 2)
-            if variant in (0, 1, 2):
+            if variant in (0, 1, 2, 3, 4):
                 g.collision = g.streaming = None
                 for dugks in (True, False):
                     g.dugks = dugks
