@@ -142,9 +142,9 @@ int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end
 constexpr int PLBM_HALO_LINES = 3;
 __host__ __device__ constexpr int halo_lo_index(int col) { return col == -3 ? 2 : col + 2; }          // col in [-3, -1]
 __host__ __device__ constexpr int halo_lo_source_line(int l, int nx) { return l < 2 ? nx - 2 + l : nx - 3; }  // sender's line of slot l
-// Three steps per pass (k_lbmn_bulk) where they were measured to win, see step_lbm_t.  Level of a grid / slab: -1 the kernel does
-// not apply, 0 below 2048^2 nodes, 1 from 2048^2, 2 from 4096^2 (a ring agrees on the minimum over its slabs: every rank must issue
-// the same launches); lbm_triples_wanted: does this collision / precision / variant take triples at that level.
+// Three steps per pass (k_lbmn_bulk), see plbm_lbmn.cu.  Level of a grid / slab: -1 the kernel does not apply, 0 below 512^2
+// nodes, 1 from 512^2 (a ring agrees on the minimum over its slabs: every rank must issue the same launches);
+// lbm_triples_wanted: does this collision / variant take triples at that level.
 int lbm_triples_level(const Grid& g);
 bool lbm_triples_wanted(const Grid& g, int level, int model);
 bool comm_triples_level(const Grid& g, int* level);  // the ring's agreed level

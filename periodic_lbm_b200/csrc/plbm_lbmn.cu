@@ -103,10 +103,18 @@ template <typename T, int V, typename ColOf> __device__ __forceinline__ void pul
     }
 }
 
-template <typename T, int MODEL, int V, int NT, int MINB, int NSTEP>
+// HALO: columns below 0 / beyond nx - 1 come from the ring neighbours' halo lines (the boundary launches of a slab).  A template
+// parameter, not a run-time test: the copies are issued by ONE thread after the first barrier of every column while its warp
+// waits, and with the extra branches in that path the interior launch of the bench slab ran 4.75 ms instead of 4.0 (r02h).
+template <typename T, int MODEL, int V, int NT, int MINB, int NSTEP, bool HALO>
 __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
 {
     static_assert(NSTEP >= 2, "depth of the temporal blocking");
+    // fp32: two nodes per instruction (FFMA2 pairs, plbm_f32x2.cuh; bit-identical to the scalar collisions)
+    // -- except for the recursive-regularized collision, which is bound by the fp32 pipe here and loses with the pairs (an FFMA2
+    // occupies the pipe for two cycles and the pairing costs register moves): RR fp32 8192^2 112.8 scalar vs 104.3 packed GLUPS,
+    // BGK fp32 160.6 vs 164.3 (r02j / r02k)
+    constexpr bool PACKED = sizeof(T) == 4 && (V % 2) == 0 && MODEL != M_RR;
     constexpr int NR = NSTEP - 1;  // rings
     constexpr int W = NT * V;      // rows of one ring column: logical rows y_lo - NR V .. y_lo - NR V + W - 1
     // staged raw column: level 1 works on the strip +- NR V rows and pulls one more row on each side; the staged range is rounded
@@ -138,23 +146,32 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
     // staged logical rows [r0, r1): what level 1 reads, whole vectors
     const int r0 = y_lo - HS, r1 = y_hi + HS;
 
+    // The copies of a column are issued by lane 0 of EVERY warp, population q by warp q mod NW: the address arithmetic of nine
+    // population lines (up to three pieces each) is several hundred instructions, and one thread issuing all of it while its
+    // warp waits made warp 0 the slowest of every column.  Each issuing lane announces its own bytes: NW arrivals per phase.
+    constexpr int NW = NT / 32;
+    static_assert(NW >= 1 && NW <= 9, "one to nine issuing warps");
+    const int warp = t >> 5;
+    const bool issuer = (t & 31) == 0;
     if (t == 0) {
-        mbarrier_init(bar(0), 1);
-        mbarrier_init(bar(1), 1);
+        mbarrier_init(bar(0), NW);
+        mbarrier_init(bar(1), NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // one raw column (all nine populations, pulled: population q from column xl - cx_q) into stage s
     auto issue = [&](int xl, int s) {
-        mbarrier_expect_tx(bar(s), (uint32_t)(9 * (r1 - r0) * sizeof(T)));
+        const int np = (9 - warp + NW - 1) / NW;  // populations warp, warp + NW, ... < 9
+        mbarrier_expect_tx(bar(s), (uint32_t)(np * (r1 - r0) * sizeof(T)));
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
+            if (q % NW != warp) continue;
             int col = xl - cxi(q);
             const T* line;
-            if (a.halo_lo && col < 0) {
+            if (HALO && col < 0) {
                 line = a.halo_lo + ((size_t)halo_lo_index(col) * 9 + q) * (size_t)a.ld;
-            } else if (a.halo_hi && col >= a.nx) {
+            } else if (HALO && col >= a.nx) {
                 line = a.halo_hi + ((size_t)(col - a.nx) * 9 + q) * (size_t)a.ld;
             } else {
                 col = col < 0 ? col + a.nx : (col >= a.nx ? col - a.nx : col);
@@ -171,9 +188,58 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
 
     const int x_first = xs - 2 * NR;  // first iteration (warm-up of the rings)
     const int c_last = xe - 1 + NR;   // raw column of the last iteration; iteration x consumes raw column x + NR
-    if (t == 0) {
-        issue(x_first + NR, 0);
-        if (x_first + NR + 1 <= c_last) issue(x_first + NR + 1, 1);
+
+    // Without halo lines (every launch but the boundary launches of a slab) the raw columns are issued strictly one after the
+    // other, so an issuing lane keeps the line address of the NEXT column of each population it owns and the three periodic
+    // pieces of the staged rows (block constants) instead of redoing the index arithmetic per column: ncu (r02i) counted a fifth of
+    // all issued instructions on the uniform datapath, i.e. in that arithmetic.
+    const int npop = (9 - warp + NW - 1) / NW;
+    const T* nxt[3] = {nullptr, nullptr, nullptr};
+    int ncol[3] = {0, 0, 0};
+    uint32_t dsto[3] = {0, 0, 0};
+    const int m0 = max(r0, 0), m1 = min(r1, a.ny);
+    const uint32_t p1_bytes = r0 < 0 ? (uint32_t)(-r0 * sizeof(T)) : 0u, p3_bytes = r1 > a.ny ? (uint32_t)((r1 - a.ny) * sizeof(T)) : 0u;
+    const uint32_t p2_bytes = (uint32_t)((m1 - m0) * sizeof(T));
+    const uint32_t p2_dst = (uint32_t)((m0 - r0) * sizeof(T)), p3_dst = (uint32_t)((a.ny - r0) * sizeof(T));
+    if (!HALO && issuer) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j >= npop) continue;
+            const int q = warp + j * NW;
+            int col = x_first + NR - cxi(q);
+            col = col < 0 ? col + a.nx : (col >= a.nx ? col - a.nx : col);
+            ncol[j] = col;
+            nxt[j] = a.src + ((size_t)q * a.nx + col) * (size_t)a.ld;
+            dsto[j] = smem_addr(stage + q * WS);
+        }
+    }
+    auto issue_next = [&](int s) {
+        mbarrier_expect_tx(bar(s), (uint32_t)(npop * (r1 - r0) * sizeof(T)));
+        const uint32_t so = (uint32_t)(s * 9 * WS * sizeof(T));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j >= npop) continue;
+            const T* line = nxt[j];
+            const uint32_t d = dsto[j] + so;
+            if (p1_bytes) bulk_copy_g2s(d, line + (a.ny + r0), p1_bytes, bar(s));
+            bulk_copy_g2s(d + p2_dst, line + m0, p2_bytes, bar(s));
+            if (p3_bytes) bulk_copy_g2s(d + p3_dst, line, p3_bytes, bar(s));
+            if (++ncol[j] == a.nx) {  // the next column wraps around x
+                ncol[j] = 0;
+                nxt[j] -= (size_t)(a.nx - 1) * (size_t)a.ld;
+            } else {
+                nxt[j] += a.ld;
+            }
+        }
+    };
+    // column xl into stage s; the calls walk through the columns x_first + NR, x_first + NR + 1, ... without gaps
+    auto issue_col = [&](int xl, int s) {
+        if (HALO) issue(xl, s);
+        else issue_next(s);
+    };
+    if (issuer) {
+        issue_col(x_first + NR, 0);
+        if (x_first + NR + 1 <= c_last) issue_col(x_first + NR + 1, 1);
     }
     int w2 = 0, w3 = 0;  // slot of the column written in this iteration (two- and three-column populations), all rings
     for (int x = x_first; x < xe; ++x) {
@@ -186,8 +252,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
             T n[V][9];
             const T* st = stage + ((k & 1) * 9) * WS + OFF + t * V;  // stage row of this thread's first row
             pull_rows<T, V>([&](int q) { return st + q * WS; }, n);
-#pragma unroll
-            for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], a.cp);
+            collide_nodes<T, MODEL, V, PACKED>(n, a.cp);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 const int slot = rn_depth(q) == 1 ? 0 : (rn_depth(q) == 2 ? w2 : w3);
@@ -199,7 +264,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // stage reads before the async refill
         __syncthreads();
-        if (t == 0 && x + NR + 2 <= c_last) issue(x + NR + 2, k & 1);  // lands during the next two iterations
+        if (issuer && x + NR + 2 <= c_last) issue_col(x + NR + 2, k & 1);  // lands during the next two iterations
         // ---- levels 2 .. NSTEP: column x + NSTEP - l from ring l-2 -> ring l-1 (the last one -> dst)
 #pragma unroll
         for (int l = 2; l <= NSTEP; ++l) {
@@ -212,8 +277,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
                         return rin + (rn_base(q) + slot) * W;
                     },
                     f);
-#pragma unroll
-                for (int v = 0; v < V; ++v) collide<T, MODEL>(f[v], a.cp);
+                collide_nodes<T, MODEL, V, PACKED>(f, a.cp);
                 if (l == NSTEP) {
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {
@@ -269,12 +333,13 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     constexpr int by_threads = 2048 / NT;
     constexpr int MINB = by_smem < by_threads ? (by_smem < 24 ? by_smem : 24) : (by_threads < 24 ? by_threads : 24);
     if (x_end <= x_begin) return PLBM_OK;
-    auto kern = k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP>;
-    static bool configured[64] = {false};
-    if (g.device < 64 && !configured[g.device]) {
+    const bool halo = halo_lo && halo_hi;
+    auto kern = halo ? k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP, true> : k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP, false>;
+    static bool configured[64][2] = {{false}};
+    if (g.device < 64 && !configured[g.device][halo]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured[g.device] = true;
+        configured[g.device][halo] = true;
     }
     LbmNArgs<T> a;
     a.src = src;
@@ -295,7 +360,18 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
     static const int seg_cols = env_knob("PLBM_MULTI_SEGLEN", 64) < 1 ? 64 : env_knob("PLBM_MULTI_SEGLEN", 64);
     int nseg = (ncols + seg_cols - 1) / seg_cols;
+    // like k_lbm2_bulk's launcher: the segment count that makes the blocks fill a whole number of rounds of MINB blocks per SM,
+    // from below (a last, mostly empty round costs as much as a full one); at least 8 columns per segment
+    static const int fill = env_knob("PLBM_MULTI_FILL", 1);
+    if (fill) {
+        const long long slots = (long long)MINB * g.sm_count;
+        const long long blocks64 = (long long)a.nstrips * nseg;
+        const long long rounds = blocks64 >= slots ? (blocks64 + slots - 1) / slots : 1;
+        nseg = (int)(rounds * slots / a.nstrips);
+        if (nseg < 1) nseg = 1;
+    }
     a.seglen = (ncols + nseg - 1) / nseg;
+    if (a.seglen < 8) a.seglen = ncols < 8 ? ncols : 8;
     nseg = (ncols + a.seglen - 1) / a.seglen;
     kern<<<(unsigned)(a.nstrips * nseg), NT, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -327,30 +403,38 @@ bool lbm_multi_applicable(const Grid& g, int model, int nstep)
            g.ny >= 8 * v;
 }
 
-// THREE steps per pass over HBM (k_lbmn_bulk; bit-identical like the pairs) where they were measured to win on B200.  Shape: one
-// row (fp64) per thread, 128-thread blocks, four blocks = sixteen warps per SM ("wide"): the 128-thread, 16-byte shape has the shared
-// memory for two blocks = eight warps per SM only and is bound by latency (ncu r02a: fp64 pipe 47 %, DRAM 62 %, nothing saturated),
-// 256-thread blocks of one row per thread wait at the three barriers per column (ncu r02f: barrier stall 2.1 per issue).
-// GLUPS, pairs (k_lbm2_bulk) -> triples, 16-byte/128 | one-row/256 | one-row/128 (r02a, r02f, r02g):
-//   BGK fp64  8192^2  83.3 -> 80.5 |  91.5 |  97.9     bench slab 32768 x 4096  85.3 -> 83.8 | 93.6 | 99.2     2048^2  72.4 -> 68.1 | 73.0 | 75.6
-//   TRT fp64  8192^2  83.4 -> 93.6 | 102.5 | 112.7     RR fp64  8192^2  68.5 -> 57.8 | 66.4 | 69.1
-//   BGK fp32  8192^2 149.3 -> 119.5 | 136.4 | 148.2    RR fp32  8192^2 102.5 -> 83.8 | 100.6 | 107.6
-// TRT has no division and BGK one, so a third collision fits under the fp64 pipe once enough warps hide its latency; RR fp64 is at
-// the fp64 pipe either way and fp32 gains little: both stay on pairs, and so do small grids (1024^2 TRT: 63.0 -> 25.3, too few
-// blocks for 64-column segments).  PLBM_TRIPLES=0: never; 2: BGK / TRT fp64 at every size (tests).
+// THREE steps per pass over HBM (k_lbmn_bulk; bit-identical like the pairs) is the default of perform_lbm_step wherever the kernel
+// applies, from 512^2 nodes (smaller grids: the cluster-resident kernel or k_lbm2).  Shape: one row (fp64) / two rows (fp32) per
+// thread, 128-thread blocks, four blocks = sixteen warps per SM; the copies of a column are issued by lane 0 of every warp from
+// running line addresses; the segments are cut so that the blocks fill whole rounds.  How it got there (BGK fp64 8192^2, GLUPS;
+// two steps per pass, k_lbm2_bulk: 83.3 at 0.97 of the HBM peak in real bytes):
+//   16 bytes per thread, 128 threads, 2 blocks per SM (round 1's shape)      80.5   ncu r02a: 8 warps per SM, fp64 pipe 47 %, DRAM 62 %:
+//                                                                                   nothing saturated, bound by latency
+//   one row per thread, 256 threads, 2 blocks                                91.5   ncu r02f: barrier stall 2.1 per issue
+//   one row per thread, 128 threads, 4 blocks                                97.9   (64 / 32 threads: 85.6 / 82.8, r02g)
+//   + halo test compiled out of the interior launches, copies issued by
+//     every warp (population q by warp q mod 4) instead of by thread 0      100.2   ncu r02i: a fifth of the issued instructions on
+//                                                                                   the uniform datapath = address arithmetic of the copies
+//   + running line addresses and block-constant pieces                      106.3   ncu r02j: DRAM 5.4 TB/s = 0.84 of the measured
+//                                                                                   peak at 49.4 B/update, fp64 pipe 61 %, issue 65 %
+// Pairs -> triples at the final shape (r02k, GLUPS; fp64 | fp32):
+//   1024^2  BGK 56.7 -> 71.5 | 71.6 -> 89.0    TRT 62.7 -> 81.1 | 83.8 -> 100.6    RR 41.5 -> 47.6 | 48.7 -> 59.0
+//   2048^2  BGK 73.1 -> 87.5 | 106.8 -> 126.6  TRT 70.6 -> 101.7 | 121.8 -> 140.2  RR 53.9 -> 57.5 | 73.2 -> 81.5
+//   4096^2  BGK 77.7 -> 98.4 | 131.4 -> 150.1  TRT 77.6 -> 114.6 | 150.9 -> 168.1  RR 62.4 -> 65.0 | 90.9 -> 96.3
+//   8192^2  BGK 83.2 -> 106.3 | 150.1 -> 164.3 TRT 83.0 -> 123.1 | 162.1 -> 183.7  RR 68.7 -> 69.4 | 102.8 -> 112.8 (scalar collisions)
+//   512^2 TRT fp64: k_lbm2 31.4 -> 41.2;  bench slab 32768 x 4096 BGK fp64: 85.3 -> 105.6
+// PLBM_TRIPLES=0: never (pairs as in round 1); 2: at every size the kernel applies to (tests).
 int lbm_triples_level(const Grid& g)
 {
     if (g.nx < 2 * PLBM_HALO_LINES || !lbm_multi_applicable(g, M_BGK, 3)) return -1;
-    const long long nodes = (long long)g.nx * g.ny;
-    return nodes >= 4096LL * 4096LL ? 2 : (nodes >= 2048LL * 2048LL ? 1 : 0);
+    return (long long)g.nx * g.ny >= 512LL * 512LL ? 1 : 0;
 }
 
 bool lbm_triples_wanted(const Grid& g, int level, int model)
 {
     static const int mode = env_knob("PLBM_TRIPLES", 1);
-    if (mode == 0 || level < 0 || g.variant != 0 || g.prec != PLBM_F64) return false;
-    if (mode >= 2) return model == M_TRT || model == M_BGK;
-    return (model == M_TRT || model == M_BGK) && level >= 1;
+    if (mode == 0 || level < 0 || g.variant != 0 || !(model == M_BGK || model == M_TRT || model == M_RR)) return false;
+    return mode >= 2 || level >= 1;
 }
 
 // `nstep` (2 or 3) fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' nearest lines
@@ -364,16 +448,17 @@ int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end
         return PLBM_ERR_ARG;
     }
 #define PLBM_N(NS, NT, WD) return dispatch_n<T, NS, NT, WD>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s)
+    static const int wide2 = env_knob("PLBM_MULTI_WIDE2", 0);  // two steps per pass in the one-row shape (measurement, variant 9)
+    if (nstep == 2 && wide2) PLBM_N(2, 128, true);
     if (nstep == 2) PLBM_N(2, 128, false);
     static const int nt = env_knob("PLBM_MULTI_NT", 0);  // 0: the default of the shape (128 threads)
     static const int wide = env_knob("PLBM_MULTI_WIDE", PLBM_MULTI_WIDE_DEFAULT);
     // small blocks (measurement knobs): the barriers of a level couple two warps / one warp instead of eight
+    // (measured and dropped, r02g: one row per thread with 64- / 32-thread blocks 85.6 / 82.8 GLUPS, 16 bytes per thread with 64- /
+    // 32-thread blocks 86.1 / 75.1, against 97.9 for the default below -- BGK fp64 8192^2)
     if (wide && nt == 64) PLBM_N(3, 64, true);
-    if (wide && nt == 32) PLBM_N(3, 32, true);
     if (wide && nt == 256) PLBM_N(3, 256, true);
     if (wide) PLBM_N(3, 128, true);  // the default: four blocks of four warps per SM
-    if (nt == 64) PLBM_N(3, 64, false);
-    if (nt == 32) PLBM_N(3, 32, false);
     if (nt == 256) PLBM_N(3, 256, false);
     PLBM_N(3, 128, false);
 #undef PLBM_N

@@ -188,15 +188,15 @@ def test_multi_step_kernel_experimental(plbm, nx, ny, prec):
 @pytest.mark.parametrize("coll_name", ["bgk", "trt"])
 @pytest.mark.parametrize("nsteps", [8, 10, 4])
 def test_fp64_default_takes_three_steps_per_pass_and_stays_bit_identical(plbm, nsteps, coll_name):
-    """Default stepping (variant 0) of collide_bgk / collide_trt in fp64 from 2048^2 nodes up advances THREE steps per pass over
-    HBM (k_lbmn_bulk<3>, csrc/plbm_lbmn.cu lbm_triples_wanted): lattices, indices and lagged macros equal the oracle's bit for
-    bit, and the launch count is the triples schedule's (8 steps: 2 triples + 2 single steps; 10: 3 triples + 1; 4: 1 triple + 1)."""
+    """Default stepping (variant 0) of collide_bgk / collide_trt / collide_rr from 512^2 nodes up advances THREE steps per pass
+    over HBM (k_lbmn_bulk<3>, csrc/plbm_lbmn.cu lbm_triples_wanted): lattices, indices and lagged macros equal the oracle's bit
+    for bit, and the launch count is the triples schedule's (8 steps: 2 triples + 2 single steps; 10: 3 triples + 1; 4: 1 triple + 1)."""
     nx, ny = 2048, 2048
     og, g = make_pair(plbm, nx, ny, "f64")
     coll, ocoll = {"bgk": (plbm.collide_bgk, Oracle.BGK), "trt": (plbm.collide_trt, Oracle.TRT)}[coll_name]
     g.collision, g.streaming = coll, plbm.lbm_stream
-    assert g.steps_per_pass() == 3
-    assert g.steps_per_pass(plbm.collide_rr) == 2
+    assert g.steps_per_pass() == 3 and g.steps_per_pass(plbm.collide_rr) == 3
+    assert g.steps_per_pass(plbm.collide_bgk_split) == 2  # the -DSPLIT operators are instantiated for the two-step kernels only
     l0 = plbm.launch_count()
     plbm.perform_lbm_step(g, nsteps)
     launches = plbm.launch_count() - l0

@@ -117,6 +117,10 @@ def test_pair_kernel_selection(plbm):
         g = plbm.alloc_grid(*shape, precision=prec)
         g.set_variant(variant)
         assert g.pair_kernel() == want, (shape, prec, variant, g.pair_kernel())
+        # plbm_lbm_steps_per_pass: three steps per pass (k_lbmn_bulk) by default from 512^2 nodes, for bgk / trt / rr
+        spp = g.steps_per_pass(plbm.collide_trt)
+        if os.environ.get("PLBM_TRIPLES", "") in ("", "1"):
+            assert spp == (3 if variant == 0 and shape[0] * shape[1] >= 512 * 512 else (1 if want == "k_lbm" else 2)), (shape, prec, variant, spp)
         plbm.dealloc_grid(g)
 
 

@@ -21,15 +21,20 @@ BASE = {3: 0, 6: 1, 7: 2, 0: 3, 2: 5, 4: 7, 1: 9, 5: 12, 8: 15}
 SLOTS = 18
 
 
-def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=None):
-    """One launch of k_lbmn_bulk<NSTEP = nstep, NT = nt, V = v> over columns [x_begin, x_end)."""
+def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=None, va=None, halo_lo=None, halo_hi=None):
+    """One launch of k_lbmn_bulk<NSTEP = nstep, NT = nt, V = v> over columns [x_begin, x_end).  va = rows per 16 bytes (the
+    alignment unit of the bulk copies; va = 2 v is the "wide" shape: half a 16-byte vector per thread).  halo_lo / halo_hi: the
+    ring neighbours' three nearest lines in the order of csrc/plbm_internal.h ([3][9][ld]: lines -2, -1, -3 / nx, nx+1, nx+2)."""
     x_end = nx if x_end is None else x_end
+    va = v if va is None else va
     dst = np.full_like(src, np.nan)
     nr, w = nstep - 1, nt * v
-    ws = w + 2 * v
+    hs = -(-(nr * v + 1) // va) * va   # staged rows beyond the strip on each side (level 1 pulls one row beyond its own)
+    off = hs - nr * v                  # stage row of thread 0's first row
+    ws = w + 2 * off
     ty_max = (nt - 2 * nr) * v
     nstrips = -(-ny // ty_max)
-    ty = -(-(-(-ny // nstrips)) // v) * v
+    ty = -(-(-(-ny // nstrips)) // va) * va
     nstrips = -(-ny // ty)
     ncols = x_end - x_begin
     nseg = -(-ncols // seg_cols)
@@ -54,7 +59,7 @@ def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=No
             xs = x_begin + seg * seglen
             xe = min(xs + seglen, x_end)
             yl = y_lo - nr * v + tt * v
-            r0, r1 = y_lo - nstep * v, y_hi + nstep * v
+            r0, r1 = y_lo - hs, y_hi + hs
             assert r1 - r0 <= ws
             ring = np.full((nr, SLOTS, w), np.nan, dtype=src.dtype)
             stage = np.full((2, 9, ws), np.nan, dtype=src.dtype)
@@ -68,22 +73,29 @@ def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=No
                 assert s not in pending, "stage refilled before it was consumed"
                 for q in range(9):
                     col = xl - CX[q]
-                    col = col + nx if col < 0 else (col - nx if col >= nx else col)
-                    assert 0 <= col < nx
-                    line = src[q, col]
+                    if halo_lo is not None and col < 0:
+                        assert -3 <= col
+                        line = halo_lo[2 if col == -3 else col + 2, q]
+                    elif halo_hi is not None and col >= nx:
+                        assert col - nx < 3
+                        line = halo_hi[col - nx, q]
+                    else:
+                        col = col + nx if col < 0 else (col - nx if col >= nx else col)
+                        assert 0 <= col < nx
+                        line = src[q, col]
                     d = stage[s, q]
                     d[:] = np.nan
                     nbytes = 0
                     if r0 < 0:
-                        assert (ny + r0) % v == 0 and (-r0) % v == 0 and ny + r0 >= 0
+                        assert (ny + r0) % va == 0 and (-r0) % va == 0 and ny + r0 >= 0
                         d[0:-r0] = line[ny + r0:ny]
                         nbytes += -r0
                     m0, m1 = max(r0, 0), min(r1, ny)
-                    assert m1 > m0 and m0 % v == 0 and (m1 - m0) % v == 0 and (m0 - r0) % v == 0
+                    assert m1 > m0 and m0 % va == 0 and (m1 - m0) % va == 0 and (m0 - r0) % va == 0
                     d[m0 - r0:m1 - r0] = line[m0:m1]
                     nbytes += m1 - m0
                     if r1 > ny:
-                        assert (r1 - ny) % v == 0 and r1 - ny <= ny
+                        assert (r1 - ny) % va == 0 and r1 - ny <= ny
                         d[ny - r0:r1 - r0] = line[0:r1 - ny]
                         nbytes += r1 - ny
                     assert nbytes == r1 - r0  # expect_tx of the kernel
@@ -115,7 +127,7 @@ def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=No
                 # level 1
                 assert pending.pop(k & 1) == x + nr, "wrong raw column in the stage"
                 act = active(1)
-                n = pull(lambda q: (stage[k & 1, q], v))
+                n = pull(lambda q: (stage[k & 1, q], off))
                 collide_rows(n, act)
                 rows = (tt[act][:, None] * v + np.arange(v)[None, :]).ravel()
                 for q in range(9):
@@ -173,6 +185,50 @@ def test_schedule_of_the_multi_step_kernels(nstep, nx, ny, nt, v, seg_cols):
         got = emulate(o, collide, f0, nx, ny, nstep, nt, v, seg_cols)
         want = reference(o, collide, f0, nx, ny, nstep)
         assert np.array_equal(got[:, :, :ny], want[:, :, :ny]), (name, nstep)
+
+
+@pytest.mark.parametrize("nstep", [2, 3])
+@pytest.mark.parametrize("nx,ny,nt,v,va,seg_cols", [
+    (7, 16, 16, 1, 2, 64),    # fp64, one row per thread (the default shape of the three-step kernel): 16-byte pieces of two rows
+    (9, 40, 12, 1, 2, 4),     # several strips, ragged last strip
+    (6, 32, 10, 2, 4, 3),     # fp32, two rows per thread, 16-byte pieces of four rows
+    (5, 24, 8, 1, 2, 1),      # one-column segments
+])
+def test_schedule_of_the_wide_shape(nstep, nx, ny, nt, v, va, seg_cols):
+    """half a 16-byte vector per thread: the staged range is rounded out to 16 bytes and thread 0 starts inside it"""
+    o = Oracle("f64")
+    p = o.set_properties(0.02, 1.0, 0.25)
+    f0 = random_state(o, nx, ny)
+    for name, collide in collisions(o, p).items():
+        got = emulate(o, collide, f0, nx, ny, nstep, nt, v, seg_cols, va=va)
+        want = reference(o, collide, f0, nx, ny, nstep)
+        assert np.array_equal(got[:, :, :ny], want[:, :, :ny]), (name, nstep)
+
+
+@pytest.mark.parametrize("nxl", [6, 7, 12])
+def test_three_step_schedule_of_a_slab(nxl):
+    """The slab schedule of a triple: lines [0, 3) and [nxl - 3, nxl) read the neighbours' three halo lines (stored in the order
+    -2, -1, -3 / nx, nx+1, nx+2), the interior [3, nxl - 3) reads the slab alone; together they cover the slab once and equal
+    the middle slab of a three-slab periodic grid stepped as a whole."""
+    o = Oracle("f64")
+    p = o.set_properties(0.02, 1.0, 0.25)
+    ny, nstep = 24, 3
+    nxg = 3 * nxl
+    f0 = random_state(o, nxg, ny)
+    collide = collisions(o, p)["trt"]
+    want = reference(o, collide, f0, nxg, ny, nstep)[:, nxl:2 * nxl]
+    slab = np.ascontiguousarray(f0[:, nxl:2 * nxl])
+    halo_lo = np.stack([f0[:, nxl - 2], f0[:, nxl - 1], f0[:, nxl - 3]])          # lines -2, -1, -3
+    halo_hi = np.stack([f0[:, 2 * nxl], f0[:, 2 * nxl + 1], f0[:, 2 * nxl + 2]])  # lines nx, nx+1, nx+2
+    got = np.full_like(slab, np.nan)
+    ranges = ((0, nxl),) if nxl <= 6 else ((0, 3), (nxl - 3, nxl), (3, nxl - 3))
+    for x0, x1 in ranges:
+        boundary = x0 == 0 or x1 == nxl
+        part = emulate(o, collide, slab, nxl, ny, nstep, 12, 1, 64, x0, x1, va=2,
+                       halo_lo=halo_lo if boundary else None, halo_hi=halo_hi if boundary else None)
+        assert np.isnan(got[:, x0:x1, :ny]).all()
+        got[:, x0:x1] = part[:, x0:x1]
+    assert np.array_equal(got[:, :, :ny], want[:, :, :ny])
 
 
 def test_schedule_on_a_line_sub_range():
