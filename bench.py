@@ -447,10 +447,14 @@ def run_ours(args):
     # GPU sees whose own periodic domain is that slab: after the same call every rank's lattice must have the same 64-bit
     # checksum (plbm_lattice_hash, computed on the device) as that single-GPU run -- which rank 0 performs here, in the same
     # process, on a second grid without a ring.  The hash is therefore also equal across N = 1, 2, 4, 8 of a weak-scaling run.
-    KS = 7 if scheme == "lbm" else 3
+    # Two calls (4 + 5 steps: triple, single | triple, single, single), so that every kind of launch also CONSUMES the halo
+    # message the launch before it produced, across a call boundary too.
+    KS_CALLS = (4, 5) if scheme == "lbm" else (3,)
+    KS = sum(KS_CALLS)
     fill_ic(nxl, 0)
     p.set_pdf_to_equilibrium(g)
-    step(KS)
+    for k in KS_CALLS:
+        step(k)
     h_ring = g.lattice_hash(g.iold)
     hashes = [h_ring]
     if world > 1:
@@ -469,13 +473,14 @@ def run_ours(args):
             if g1 is not None:
                 g1.rho, g1.ux, g1.uy = g.rho, g.ux, g.uy
                 p.set_pdf_to_equilibrium(g1)
-                step(KS, g1)
+                for k in KS_CALLS:
+                    step(k, g1)
                 h_single = g1.lattice_hash(g1.iold)
                 p.dealloc_grid(g1)
         selfcheck = {"hash": f"{h_ring:016x}", "ranks_equal": len(set(hashes)) == 1,
                      "single_gpu_hash": None if h_single is None else f"{h_single:016x}",
                      "equals_single_gpu": None if h_single is None else all(h == h_single for h in hashes), "steps": KS,
-                     "what": f"Taylor-Green periodic over the {nxl} lines of one slab; {KS} steps in one call; plbm_lattice_hash(iold) of every rank "
+                     "what": f"Taylor-Green periodic over the {nxl} lines of one slab; {KS} steps in calls of {KS_CALLS}; plbm_lattice_hash(iold) of every rank "
                              "vs the same slab stepped alone on one GPU in this run"}
 
     if rank == 0:

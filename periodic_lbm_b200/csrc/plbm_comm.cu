@@ -545,6 +545,9 @@ static void finish_steps(Grid& g, int depth)
     g.comm->halo_of_lattice = g.iold;
 }
 
+// lines per side the boundary launches cover = lines of the halo message (slabs too thin for that: two, or the whole slab)
+static int boundary_lines(const Grid& g) { return g.nx >= 2 * PLBM_HALO_LINES ? PLBM_HALO_LINES : (g.nx >= 4 ? 2 : g.nx); }
+
 // How many steps the next launch of a call advances: three while more than three remain and the ring takes triples for this
 // collision, two while more than two remain, else one (the last step stays single so that lattice `inew` ends up holding state
 // n-1 like the reference, see step_lbm_t).  Every rank computes the same sequence.
@@ -596,9 +599,11 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         a.halo_lo = (const T*)c->halo_lo[slot];
         a.halo_hi = (const T*)c->halo_hi[slot];
         a.cp = cp;
-        // boundary lines per side: as many as the launch advances steps, two for a single step (it would need only one; the
-        // message always carries three so that any launch may follow).  They need the halo, and they are what the neighbours get next
-        const int nb = depth == 3 ? 3 : (g.nx >= 4 ? 2 : g.nx);
+        // THREE boundary lines per side whatever the launch advances (one step would need one, a pair two): they need the halo,
+        // and they are what the neighbours get next -- the message always carries three lines so that any launch may follow, and
+        // every line of it must come from the boundary launch, which is all the push waits for (r02n2: with two-line boundaries
+        // after a single step the third line was still the interior launch's to write, and a following triple read it stale)
+        const int nb = boundary_lines(g);
         PLBM_CUDA(cudaStreamWaitEvent(B, c->ev_interior, 0));                  // interior of the previous launch (wrote src, read dst)
         if (!first) PLBM_CUDA(cudaStreamWaitEvent(M, c->ev_boundary, 0));      // boundaries of the previous launch (wrote src)
         if ((rc = p2p_wait(g, e, B))) return rc;                               // the neighbours' lines of lattice `iold` have landed
@@ -641,7 +646,7 @@ template <typename T> int comm_lbm_steps(Grid& g, int model, const CollideParams
         a.halo_lo = (const T*)c->halo_lo[p];
         a.halo_hi = (const T*)c->halo_hi[p];
         a.cp = cp;
-        const int nb = depth == 3 ? 3 : (g.nx >= 4 ? 2 : g.nx);
+        const int nb = boundary_lines(g);
         // the boundary lines of each side first: they need the neighbours' lines, and produce what must be sent
         PLBM_CUDA(cudaStreamWaitEvent(g.stream, c->ev_halo[p], 0));
         if ((rc = lbm_boundaries<T>(g, a, depth, nb, model, g.stream))) return rc;

@@ -388,6 +388,14 @@ int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, cons
     case M_TRT: return launch_n<T, M_TRT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
     case M_RR: return launch_n<T, M_RR, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
     }
+    // the -DSPLIT operators and collide_bgk_improved: the default shape only
+    if constexpr (NSTEP == 3 && NT == 128 && WIDE) {
+        switch (model) {
+        case M_BGK_SPLIT: return launch_n<T, M_BGK_SPLIT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+        case M_TRT_SPLIT: return launch_n<T, M_TRT_SPLIT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+        case M_BGK_IMPROVED: return launch_n<T, M_BGK_IMPROVED, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+        }
+    }
     set_error("launch_lbm_multi: collision model not instantiated for the experimental multi-step kernel");
     return PLBM_ERR_ARG;
 }
@@ -396,11 +404,13 @@ int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, cons
 
 // the experimental kernel is instantiated for the three reference collision operators of the LBM path, on grids the
 // bulk copies can address (every staged piece a multiple of 16 bytes, the wrap pieces inside one line)
+bool lbm_multi_shape_is_default();
 bool lbm_multi_applicable(const Grid& g, int model, int nstep)
 {
     const int v = 16 / (int)g.esize();
-    return (nstep == 2 || nstep == 3) && (model == M_BGK || model == M_TRT || model == M_RR) && g.nx >= 4 && (g.ny % v) == 0 &&
-           g.ny >= 8 * v;
+    const bool reference3 = model == M_BGK || model == M_TRT || model == M_RR;
+    const bool others = (model == M_BGK_SPLIT || model == M_TRT_SPLIT || model == M_BGK_IMPROVED) && nstep == 3 && lbm_multi_shape_is_default();
+    return (nstep == 2 || nstep == 3) && (reference3 || others) && g.nx >= 4 && (g.ny % v) == 0 && g.ny >= 8 * v;
 }
 
 // THREE steps per pass over HBM (k_lbmn_bulk; bit-identical like the pairs) is the default of perform_lbm_step wherever the kernel
@@ -433,8 +443,15 @@ int lbm_triples_level(const Grid& g)
 bool lbm_triples_wanted(const Grid& g, int level, int model)
 {
     static const int mode = env_knob("PLBM_TRIPLES", 1);
-    if (mode == 0 || level < 0 || g.variant != 0 || !(model == M_BGK || model == M_TRT || model == M_RR)) return false;
+    if (mode == 0 || level < 0 || g.variant != 0 || !lbm_multi_applicable(g, model, 3)) return false;
     return mode >= 2 || level >= 1;
+}
+
+bool lbm_multi_shape_is_default()
+{
+    static const bool dflt = env_knob("PLBM_MULTI_WIDE", PLBM_MULTI_WIDE_DEFAULT) != 0 &&
+                             (env_knob("PLBM_MULTI_NT", 0) == 0 || env_knob("PLBM_MULTI_NT", 0) == 128);
+    return dflt;
 }
 
 // `nstep` (2 or 3) fused steps src -> dst for columns [x_begin, x_end).  halo_lo / halo_hi: the ring neighbours' nearest lines

@@ -5,9 +5,10 @@ Rank r owns lines [x_offset, x_offset + nx_local) of every population and forms 
 with its neighbours.  One LBM step needs the last line of q = 1,5,8 (cx = +1) from rank r-1
 and the first line of q = 3,6,7 (cx = -1) from rank r+1; a fused pair of steps (the library's
 two-step kernel) recomputes step 1 on the neighbours' nearest line and therefore needs their TWO
-nearest lines of all nine populations.  The halo message always carries HALO_LINES = 2 lines x 9
-populations per direction, so that either kind of launch can follow; the y shift of the diagonal
-populations is applied locally on the received lines, so no corner exchange exists.
+nearest lines of all nine populations, a fused triple (the three-step kernel, the default) their
+THREE nearest lines.  The halo message always carries HALO_LINES = 3 lines x 9 populations per
+direction, so that any kind of launch can follow; the y shift of the diagonal populations is
+applied locally on the received lines, so no corner exchange exists.
 """
 from __future__ import annotations
 
@@ -50,7 +51,7 @@ def slab_of(rank: int, nranks: int, nx_global: int) -> Slab:
     return Slab(rank, nranks, nx_global, x_offset, nx_local)
 
 
-HALO_LINES = 2  # lines per direction in one halo message
+HALO_LINES = 3  # lines per direction in one halo message
 
 
 def halo_message_bytes(ny: int, itemsize: int) -> int:
@@ -58,13 +59,14 @@ def halo_message_bytes(ny: int, itemsize: int) -> int:
     return HALO_LINES * 9 * ((ny + 15) // 16 * 16) * itemsize
 
 
-def launch_schedule(nsteps: int, pairs: bool = True) -> list:
-    """Steps advanced by each launch of one perform_lbm_step(nsteps) call: fused pairs while at least one
-    single step remains (the last step stays single so that lattice `inew` ends up holding state nsteps-1
+def launch_schedule(nsteps: int, pairs: bool = True, triples: bool = False) -> list:
+    """Steps advanced by each launch of one perform_lbm_step(nsteps) call: fused triples while more than three
+    steps remain (where the ring takes them: every slab at least 2 * HALO_LINES lines wide), fused pairs while
+    more than two remain (the last step stays single so that lattice `inew` ends up holding state nsteps-1
     exactly like the reference), then single steps."""
     out, s = [], 0
     while s < nsteps:
-        n = 2 if pairs and s + 2 < nsteps else 1
+        n = 3 if triples and s + 3 < nsteps else (2 if pairs and s + 2 < nsteps else 1)
         out.append(n)
         s += n
     return out

@@ -163,7 +163,7 @@ def test_multi_step_kernel_experimental(plbm, nx, ny, prec):
     """k_lbmn_bulk: variant 9 = pairs through its NSTEP = 2 instance, variant 10 = triples (+ pairs for the rest);
     the schedule itself is pinned on the CPU by tests/test_multi_step_schedule.py.  (First run on a B200 in round 2, green:
     profiles/r02_a_pytest_experimental.txt; the name is kept.)"""
-    for nsteps, (coll, ocoll) in zip((3, 4, 5, 8, 9, 11), collisions(plbm)[:3] * 2):
+    for nsteps, (coll, ocoll) in zip((3, 4, 5, 8, 9, 11, 7, 10, 13), collisions(plbm)[:3] * 2 + collisions(plbm)[3:]):
         og, g0 = make_pair(plbm, nx, ny, prec)
         f0 = g0.download_f(g0.iold)
         plbm.dealloc_grid(g0)
@@ -196,7 +196,7 @@ def test_fp64_default_takes_three_steps_per_pass_and_stays_bit_identical(plbm, n
     coll, ocoll = {"bgk": (plbm.collide_bgk, Oracle.BGK), "trt": (plbm.collide_trt, Oracle.TRT)}[coll_name]
     g.collision, g.streaming = coll, plbm.lbm_stream
     assert g.steps_per_pass() == 3 and g.steps_per_pass(plbm.collide_rr) == 3
-    assert g.steps_per_pass(plbm.collide_bgk_split) == 2  # the -DSPLIT operators are instantiated for the two-step kernels only
+    assert g.steps_per_pass(plbm.collide_bgk_split) == 3 and g.steps_per_pass(plbm.collide_bgk_improved) == 3
     l0 = plbm.launch_count()
     plbm.perform_lbm_step(g, nsteps)
     launches = plbm.launch_count() - l0

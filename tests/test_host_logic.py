@@ -23,7 +23,7 @@ def test_slab_partition_covers_grid():
         slab_of(0, 8, 15)
     assert [q for q in range(9) if cx[q] == 1] == list(Q_FROM_LO)
     assert [q for q in range(9) if cx[q] == -1] == sorted(Q_FROM_HI)
-    assert halo_message_bytes(32768, 8) == 2 * 9 * 32768 * 8  # two lines of all nine populations (a fused pair of steps may follow)
+    assert halo_message_bytes(32768, 8) == 3 * 9 * 32768 * 8  # three lines of all nine populations (a fused triple of steps may follow)
 
 
 def test_driver_recipe_matches_oracle_recipe():
@@ -61,9 +61,9 @@ def _free_port():
 
 
 def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
-    """One rank of the ring: owns a slab, exchanges the halo message (two lines of all nine populations per
-    direction) with gloo, and advances its slab with the ORACLE kernels on a halo-extended copy -- one step
-    or a fused pair per launch, in the library's own schedule.  This exercises exactly the protocol
+    """One rank of the ring: owns a slab, exchanges the halo message (three lines of all nine populations per
+    direction) with gloo, and advances its slab with the ORACLE kernels on a halo-extended copy -- one step,
+    a fused pair or a fused triple per launch, in the library's own schedule.  This exercises exactly the protocol
     libplbm_b200's ring implements (which lines, which neighbour, what a pair needs) without a GPU."""
     import torch
     import torch.distributed as dist
@@ -83,11 +83,11 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
     nxl = sl.nx_local
     H = HALO_LINES
     collide = {0: lambda a: o.collide_bgk(a, ny, 1.7), 2: lambda a: o.collide_rr(a, ny, 1.7)}[coll]
-    can_pair = torch.tensor([int(nxl >= 4)])
-    dist.all_reduce(can_pair, op=dist.ReduceOp.MIN)  # every rank must issue the same sequence of launches
-    for nfused in launch_schedule(steps, pairs=bool(can_pair.item())):
-        send_lo = torch.from_numpy(f[:, :H].copy())    # my first two lines -> rank lo (its lines nx, nx+1)
-        send_hi = torch.from_numpy(f[:, -H:].copy())   # my last two lines  -> rank hi (its lines -2, -1)
+    can = torch.tensor([int(nxl >= 4), int(nxl >= 2 * H)])
+    dist.all_reduce(can, op=dist.ReduceOp.MIN)  # every rank must issue the same sequence of launches
+    for nfused in launch_schedule(steps, pairs=bool(can[0].item()), triples=bool(can[1].item())):
+        send_lo = torch.from_numpy(f[:, :H].copy())    # my first three lines -> rank lo (its lines nx, nx+1, nx+2)
+        send_hi = torch.from_numpy(f[:, -H:].copy())   # my last three lines  -> rank hi (its lines -3, -2, -1)
         halo_lo, halo_hi = torch.empty_like(send_hi), torch.empty_like(send_lo)
         ops = [dist.P2POp(dist.isend, send_lo, sl.lo), dist.P2POp(dist.isend, send_hi, sl.hi),
                dist.P2POp(dist.irecv, halo_hi, sl.hi), dist.P2POp(dist.irecv, halo_lo, sl.lo)]
@@ -98,7 +98,7 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
         ext[:, :H] = halo_lo.numpy()
         ext[:, -H:] = halo_hi.numpy()
         # every step on the extended slab pollutes one more ghost line from each end (its periodic wrap is
-        # wrong there): two ghost lines per side keep the owned lines exact for up to two steps
+        # wrong there): three ghost lines per side keep the owned lines exact for up to three steps
         for _ in range(nfused):
             dst = np.zeros_like(ext)
             o.lbm_stream(ext, dst, ny)
@@ -120,7 +120,7 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nxg,ny,coll", [(2, 12, 10, 0), (2, 9, 16, 2), (3, 13, 7, 0), (2, 7, 8, 0)])
+@pytest.mark.parametrize("world,nxg,ny,coll", [(2, 12, 10, 0), (2, 9, 16, 2), (3, 13, 7, 0), (2, 7, 8, 0), (3, 19, 8, 2)])
 def test_slab_halo_protocol_world_size_n_gloo(world, nxg, ny, coll):
     import torch.multiprocessing as mp
 
