@@ -447,7 +447,7 @@ def run_ours(args):
     # GPU sees whose own periodic domain is that slab: after the same call every rank's lattice must have the same 64-bit
     # checksum (plbm_lattice_hash, computed on the device) as that single-GPU run -- which rank 0 performs here, in the same
     # process, on a second grid without a ring.  The hash is therefore also equal across N = 1, 2, 4, 8 of a weak-scaling run.
-    # Two calls (4 + 5 steps: triple, single | triple, single, single), so that every kind of launch also CONSUMES the halo
+    # Two calls (4 + 5 steps: triple, single | pair, pair, single), so that every kind of launch also CONSUMES the halo
     # message the launch before it produced, across a call boundary too.
     KS_CALLS = (4, 5) if scheme == "lbm" else (3,)
     KS = sum(KS_CALLS)
@@ -495,10 +495,9 @@ def run_ours(args):
         cfg = config_of(args.workload, world)
         def lbm_schedule(k, depth):
             """launches of one perform_lbm_step(k) call: triples while more than three steps remain (depth 3), pairs while more than two"""
-            n3 = (k - 1) // 3 if depth == 3 else 0
-            rest = k - 3 * n3
-            n2 = (rest - 1) // 2 if depth >= 2 else 0
-            return n3, n2, rest - 2 * n2
+            from periodic_lbm_b200.slab import launch_schedule
+            sched = launch_schedule(k, pairs=depth >= 2, triples=depth == 3)
+            return sched.count(3), sched.count(2), sched.count(1)
         n3, n2, n1 = lbm_schedule(K, dom_steps if scheme == "lbm" else 1)
         stepping = {"lbm": f"one perform_lbm_step(K={K}) call: {n3} three-step launches + {n2} two-step launches + {n1} single-step launches, bit-identical to K single steps",
                     "dugks": f"one perform_dugks_step(K={K}) call: one fused launch per step (collide + face reconstruction + face relaxation + flux update)",

@@ -164,7 +164,8 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
         // triples (three reference swaps = one swap of the indices; the result sits in lattice `inew`), then pairs.
         const CollideParams<T> cp = collide_params<T>(g, model);
         if (triples) {
-            for (; s + 3 < nsteps; s += 3) {
+            const bool pairs_follow = g.variant == 10 || (lbm_pair_variant(g.variant) && lbm_pair_applicable(g));
+            for (; lbm_next_depth(nsteps - 1 - s, true, pairs_follow) == 3; s += 3) {
                 int rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 3, g.stream);
                 if (rc) return rc;
                 swap_lattices(g);

@@ -556,9 +556,8 @@ static int next_depth(const Grid& g, int model, int s, int nsteps)
     const Comm* c = g.comm;
     const bool triples = c->triples_level >= 0 && lbm_multi_applicable(g, model, 3) &&
                          (g.variant == 10 || lbm_triples_wanted(g, c->triples_level, model));
-    if (triples && s + 3 < nsteps) return 3;
     const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
-    return pairs && s + 2 < nsteps ? 2 : 1;
+    return lbm_next_depth(nsteps - 1 - s, triples, pairs);
 }
 
 // p2p transport, two streams per rank:

@@ -146,6 +146,14 @@ __host__ __device__ constexpr int halo_lo_source_line(int l, int nx) { return l 
 // nodes, 1 from 512^2 (a ring agrees on the minimum over its slabs: every rank must issue the same launches);
 // lbm_triples_wanted: does this collision / variant take triples at that level.
 int lbm_triples_level(const Grid& g);
+// Steps the next launch of a call advances when `rem` steps remain BEFORE the closing single step (the last step of a call stays
+// single so that lattice `inew` ends up holding state n-1 like the reference): triples, except that four remaining steps go as two
+// pairs (a triple would leave one more single step: 3.67 + 2.82 ms against 2 x 3.1 ms on the bench slab), then pairs, then singles.
+inline int lbm_next_depth(int rem, bool triples, bool pairs)
+{
+    if (triples && rem >= 3 && !(pairs && rem == 4)) return 3;
+    return pairs && rem >= 2 ? 2 : 1;
+}
 bool lbm_triples_wanted(const Grid& g, int level, int model);
 bool comm_triples_level(const Grid& g, int* level);  // the ring's agreed level
 // TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice

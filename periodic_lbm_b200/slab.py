@@ -66,7 +66,11 @@ def launch_schedule(nsteps: int, pairs: bool = True, triples: bool = False) -> l
     exactly like the reference), then single steps."""
     out, s = [], 0
     while s < nsteps:
-        n = 3 if triples and s + 3 < nsteps else (2 if pairs and s + 2 < nsteps else 1)
+        rem = nsteps - 1 - s  # steps before the closing single step
+        if triples and rem >= 3 and not (pairs and rem == 4):  # four remaining steps go as two pairs, not triple + single
+            n = 3
+        else:
+            n = 2 if pairs and rem >= 2 else 1
         out.append(n)
         s += n
     return out

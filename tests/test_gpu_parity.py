@@ -190,7 +190,7 @@ def test_multi_step_kernel_experimental(plbm, nx, ny, prec):
 def test_fp64_default_takes_three_steps_per_pass_and_stays_bit_identical(plbm, nsteps, coll_name):
     """Default stepping (variant 0) of collide_bgk / collide_trt / collide_rr from 512^2 nodes up advances THREE steps per pass
     over HBM (k_lbmn_bulk<3>, csrc/plbm_lbmn.cu lbm_triples_wanted): lattices, indices and lagged macros equal the oracle's bit
-    for bit, and the launch count is the triples schedule's (8 steps: 2 triples + 2 single steps; 10: 3 triples + 1; 4: 1 triple + 1)."""
+    for bit, and the launch count is the triples schedule's (periodic_lbm_b200/slab.py launch_schedule)."""
     nx, ny = 2048, 2048
     og, g = make_pair(plbm, nx, ny, "f64")
     coll, ocoll = {"bgk": (plbm.collide_bgk, Oracle.BGK), "trt": (plbm.collide_trt, Oracle.TRT)}[coll_name]
@@ -200,7 +200,8 @@ def test_fp64_default_takes_three_steps_per_pass_and_stays_bit_identical(plbm, n
     l0 = plbm.launch_count()
     plbm.perform_lbm_step(g, nsteps)
     launches = plbm.launch_count() - l0
-    assert launches == (nsteps - 1) // 3 + (nsteps - 3 * ((nsteps - 1) // 3)), launches
+    from periodic_lbm_b200.slab import launch_schedule
+    assert launches == len(launch_schedule(nsteps, pairs=True, triples=True)), launches  # 8: 3+2+2+1, 10: 3+3+3+1, 4: 3+1
     og.run(Oracle.SCHEME_LBM, ocoll, nsteps)
     assert (g.iold, g.inew) == (og.iold, og.inew)
     assert_same_lattice(g, og, g.iold, og.iold, ny)
