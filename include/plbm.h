@@ -180,21 +180,28 @@ int plbm_synchronize(plbm_handle grid);
 /* kernels launched by this process through the library since load (for bench accounting) */
 long long plbm_launch_count(void);
 /* select a kernel variant (tuning / A-B measurements); 0 = default everywhere.
- *   perform_lbm_step : 0 direct 128-bit loads, two steps per pass over HBM when nsteps >= 3 (k_lbm2_bulk on large
- *                      grids, k_lbm2 on smaller ones; or the cluster-resident multi-step kernel when the grid fits
- *                      in shared memory; env PLBM_PAIR_BULK=0 / 2: k_lbm2 / k_lbm2_bulk everywhere); one step per launch:
+ *   perform_lbm_step : 0 = default: calls of >= 4 steps advance THREE steps per pass over HBM (k_lbmn_bulk: bgk / trt / rr and
+ *                      the -DSPLIT / improved operators, fp64 and fp32, from 512^2 nodes; env PLBM_TRIPLES=0: never, 2: at every
+ *                      size), the last one to four steps of a call as pairs (k_lbm2_bulk on large grids, k_lbm2 on smaller ones;
+ *                      env PLBM_PAIR_BULK=0 / 2: k_lbm2 / k_lbm2_bulk everywhere) and one closing single step (k_lbm, direct
+ *                      128-bit loads); grids that fit in the shared memory of one cluster: all steps in one launch
+ *                      (cluster-resident kernel).  One step per launch:
  *                      1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints;
  *                      5 = like 0 but never the cluster kernel (tests of the two-step kernel on small grids);
  *                      6 / 7 = like 5 with the two-step kernel's raw columns fetched by per-thread loads (k_lbm2) /
  *                      by bulk async copies (k_lbm2_bulk); 8 = 7 issued as the three line ranges of the slab schedule;
- *                      9 / 10 = EXPERIMENTAL depth-generic kernel k_lbmn_bulk (bgk/trt/rr, one GPU): pairs / triples;
+ *                      9 / 10 = the depth-generic kernel k_lbmn_bulk forced on every grid it applies to: pairs / triples
+ *                      (10 is what variant 0 does from 512^2 nodes);
  *                      11 = EXPERIMENTAL the two-step kernels compiled with FMA contraction (one GPU; within 1e-12 /
  *                      1e-5 relative of the non-FMA result, NOT bit-identical);
  *                      12 = like 5, fp32 collisions in scalar instead of packed (two nodes per FFMA2) form: same bits, A/B only
  *   perform_step (fvm/fdm) : 0 TMA + mbarrier pipelined tile kernel, 2 plain-load tile kernel
  *   perform_dugks_step     : 0 TMA-pipelined fused kernel, 1 the reference's two passes, 2 plain-load fused
- *   both                   : 3 = EXPERIMENTAL the TMA-pipelined kernel compiled with FMA contraction (fewer fp64
- *                            instructions; within 1e-12 / 1e-5 relative of the non-FMA result, NOT bit-identical; one GPU) */
+ *   both                   : 3 = opt-in: the TMA-pipelined kernel compiled with FMA contraction (fewer fp64
+ *                            instructions; within 1e-12 / 1e-5 relative of the non-FMA result, NOT bit-identical; one GPU);
+ *                            4 = opt-in: marching kernel with shared cell faces (k_fv_march / k_fv_march_s, csrc/plbm_fvm_march.cu:
+ *                            every face reconstructed and relaxed once, FMA contraction; same tolerance gate, NOT bit-identical;
+ *                            DUGKS fp64 2048^2 24.4 GLUPS against 14.4 of the default) */
 int plbm_set_variant(plbm_handle grid, int variant);
 /* which kernel perform_lbm_step(nsteps >= 3) advances this grid with: 0 = one step per launch (k_lbm),
  * 1 = two steps per launch, raw columns by per-thread loads (k_lbm2), 2 = two steps per launch, raw columns by

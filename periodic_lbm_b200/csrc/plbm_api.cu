@@ -171,7 +171,8 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
                 swap_lattices(g);
             }
         }
-        for (; (g.variant == 9 || g.variant == 10) && s + 2 < nsteps; s += 2) {
+        // (operators the NSTEP = 2 instance is not built for fall through to the two-step kernels below)
+        for (; (g.variant == 9 || g.variant == 10) && lbm_multi_applicable(g, model, 2) && s + 2 < nsteps; s += 2) {
             int rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 2, g.stream);
             if (rc) return rc;
             std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);

@@ -26,7 +26,7 @@ def run(nx, ny, prec, scheme, coll, variant, steps, warmup=3, dugks=True):
     if scheme == "lbm":
         p.set_properties(g, tp["nu"], 1.0, 0.25)
     else:
-        p.set_properties(g, tp["nu"], 5.0 * float(tp["tau"]), 0.25)
+        p.set_properties(g, tp["nu"], min(5.0 * float(tp["tau"]), 0.5), 0.25)  # dt = 5 tau capped at CFL 0.5 (stable)
     # cheap IC: uniform rho with a small shear (values do not matter for bandwidth)
     g.rho[:] = 1.0
     g.ux[:] = 0.01
