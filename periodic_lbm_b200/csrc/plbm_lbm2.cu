@@ -40,7 +40,9 @@
 // the memory-instruction queue only carries the ring traffic and the result stores (stall_mio_throttle 3.5 ->
 // 0.28 per issue), and the kernel moves 6.2-6.4 TB/s of DRAM traffic = 0.95-0.97 of the measured copy peak:
 // BGK / TRT / RR fp64 83.0 / 82.7 / 68.5 GLUPS at 8192^2 (k_lbm2: 63.9 / 64.1 / 58.5), fp32 BGK 147 (119).
-// k_lbm2_bulk is the default; k_lbm2 serves the launches that read a neighbour's halo lines and tiny ny.
+// k_lbm2_bulk was round 1's default; since round 2 perform_lbm_step advances THREE steps per pass (k_lbmn_bulk, plbm_lbmn.cu) and
+// the kernels of this file serve the pair(s) that may close a call, grids below 512^2 nodes, PLBM_TRIPLES=0, the launches of a pair
+// that read a neighbour's halo lines (k_lbm2<HALO>) and tiny ny.
 #include <climits>
 #include <cstdint>
 #include <cstdlib>

@@ -1,14 +1,13 @@
 // plbm_lbmn.cu -- NSTEP fused stream+collide steps per pass over HBM (temporal blocking of depth NSTEP, sm_100a).
 //
-// EXPERIMENTAL (variants 9 and 10 of perform_lbm_step; never selected by default): the generalisation of
-// k_lbm2_bulk (plbm_lbm2.cu) from two to NSTEP levels.  k_lbm2_bulk moves 73.6 B of DRAM traffic per update at
-// 0.97 of the measured HBM copy rate, i.e. it sits on the HBM roof of a two-step scheme; the only way further up
-// is fewer bytes per update: 144 / NSTEP B (fp64).  Not yet run on a GPU when this was written -- the round's
-// GPU budget was spent; tests/test_gpu_parity.py::test_multi_step_kernel_experimental is the parity gate
-// (set PLBM_TEST_EXPERIMENTAL=1) and tools/pair_ab.py --variants 7,9,10 the A/B.
+// The headline kernel: with NSTEP = 3 it is what perform_lbm_step launches by default from 512^2 nodes (lbm_triples_wanted below;
+// variants 9 / 10 force its NSTEP = 2 / 3 instances on every grid they apply to).  It is the generalisation of k_lbm2_bulk
+// (plbm_lbm2.cu) from two to NSTEP levels: k_lbm2_bulk moves 73.6 B of DRAM traffic per update at 0.97 of the measured HBM copy
+// rate, i.e. it sits on the HBM roof of a two-step scheme, and the only way further up is fewer bytes per update: 144 / NSTEP B
+// (fp64; measured 49.4 B with NSTEP = 3).
 //
 // A block owns a strip of rows and marches along x.  In iteration x, after the raw column x + NSTEP - 1 has
-// landed in shared memory by bulk async copies (issued by one thread two columns ahead, one mbarrier per stage),
+// landed in shared memory by bulk async copies (issued two columns ahead by lane 0 of every warp, one mbarrier per stage),
 //   level 1      collides the streamed raw column x + NSTEP - 1            -> ring 0   (state after step 1)
 //   level l      pulls column x + NSTEP - l from ring l-2 (columns c-1, c, c+1), collides -> ring l-1
 //   level NSTEP  pulls column x from ring NSTEP-2, collides, stores the state after step NSTEP to `dst`.
@@ -16,7 +15,8 @@
 // Every ring keeps a population 1 / 2 / 3 columns (cx = -1 / 0 / +1): 18 column slots, one barrier after each
 // level.  Warm-up: the loop starts 2 (NSTEP - 1) columns before the segment and level l joins 2 (l - 1) iterations
 // later, so NSTEP = 2 is exactly k_lbm2_bulk's schedule.  Same collide<T,MODEL> on the same operands as NSTEP
-// k_lbm launches -> bit-identical results.
+// k_lbm launches -> bit-identical results (tests/test_gpu_parity.py; the schedule itself is restated in numpy and
+// checked against the oracle on the CPU: tests/test_multi_step_schedule.py).
 //   lbm_stream_kernel  src/periodic_lbm.f90:45-127 ;  collisions src/collision_*.F90
 #include <cstdint>
 #include <cstdlib>
