@@ -16,7 +16,7 @@
 // level.  Warm-up: the loop starts 2 (NSTEP - 1) columns before the segment and level l joins 2 (l - 1) iterations
 // later, so NSTEP = 2 is exactly k_lbm2_bulk's schedule.  Same collide<T,MODEL> on the same operands as NSTEP
 // k_lbm launches -> bit-identical results (tests/test_gpu_parity.py; the schedule itself is restated in numpy and
-// checked against the oracle on the CPU: tests/test_multi_step_schedule.py).
+// checked against the CPU restatement of the reference: tests/test_multi_step_schedule.py).
 //   lbm_stream_kernel  src/periodic_lbm.f90:45-127 ;  collisions src/collision_*.F90
 #include <cstdint>
 #include <cstdlib>
