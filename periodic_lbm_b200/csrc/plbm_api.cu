@@ -21,6 +21,37 @@ int cuda_fail(cudaError_t e, const char* what)
     return PLBM_ERR_CUDA;
 }
 
+// The hidden third lattice buffer (Grid::spare).  PLBM_SPARE_LATTICE: 0 never, 1 (default) when the GPU keeps at least a quarter of
+// the buffer's size + 1 GB free after it and the grid has 512^2 nodes or more (no triples below that by default), 2 whenever
+// cudaMalloc succeeds (tests: with PLBM_TRIPLES=2 the closing dual triple then runs on small grids too).
+void* lbm_spare(Grid& g)
+{
+    if (g.spare_state != 0) return g.spare_state > 0 ? g.spare : nullptr;
+    static const int mode = getenv("PLBM_SPARE_LATTICE") && *getenv("PLBM_SPARE_LATTICE") ? atoi(getenv("PLBM_SPARE_LATTICE")) : 1;
+    g.spare_state = -1;
+    if (mode <= 0 || (mode == 1 && (long long)g.nx * g.ny < 512LL * 512LL)) return nullptr;
+    const size_t bytes = g.lattice_elems() * g.esize();
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (mode == 1 && free_b < bytes + bytes / 4 + ((size_t)1 << 30)) return nullptr;
+    if (cudaMalloc(&g.spare, bytes) != cudaSuccess) {
+        cudaGetLastError();  // not an error of the call: the schedule without the spare is used
+        g.spare = nullptr;
+        return nullptr;
+    }
+    g.spare_state = 1;
+    return g.spare;
+}
+
+void lbm_adopt_spare_as_inew(Grid& g)
+{
+    std::swap(g.f[g.inew - 1], g.spare);
+    if (g.tmap_ok) make_tensor_maps(g);  // the descriptors name the buffers
+}
+
 namespace {
 
 int check_noflush(plbm_handle g)
@@ -147,7 +178,7 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
 {
     g.dugks_pending = false;  // lattice inew is overwritten below
     if (g.comm) return comm_lbm_steps<T>(g, model, collide_params<T>(g, model), nsteps);
-    if (g.variant == 0 && nsteps >= 4) {
+    if (g.variant == 0 && nsteps >= 4 && !lbm_triples_forced()) {
         // small grids: all the steps in ONE launch, lattices resident in the shared memory of a cluster
         bool done = false;
         int rc = try_lbm_cluster_steps<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), model, collide_params<T>(g, model), nsteps, &done, g.stream);
@@ -159,6 +190,33 @@ template <typename T> int step_lbm_t(Grid& g, int model, int nsteps)
     }
     int s = 0;
     const bool triples = g.variant == 10 || lbm_triples_wanted(g, lbm_triples_level(g), model);
+    if (g.variant == 0 && triples && nsteps >= 3 && lbm_multi_shape_is_default() && lbm_spare(g)) {
+        // the default schedule when a third lattice buffer is available: triples, closed by a triple that stores the states after
+        // its second and third step (lattice `inew` = state n-1, `iold` = state n, exactly what a closing single step leaves)
+        const CollideParams<T> cp = collide_params<T>(g, model);
+        const bool pairs = lbm_pair_applicable(g);
+        while (s < nsteps) {
+            const LbmLaunch L = lbm_next_launch(nsteps - s, true, pairs, true);
+            int rc;
+            if (L.depth == 3) {
+                rc = launch_lbm_multi<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, model, cp, 3, g.stream, nullptr, nullptr,
+                                         L.dual ? static_cast<T*>(g.spare) : nullptr);
+                if (rc) return rc;
+                swap_lattices(g);
+                if (L.dual) lbm_adopt_spare_as_inew(g);
+            } else if (L.depth == 2) {
+                if ((rc = launch_lbm_pair<T>(g, g.lat<T>(g.iold), g.lat<T>(g.inew), 0, g.nx, nullptr, nullptr, model, cp, g.stream))) return rc;
+                std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
+                for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
+            } else {
+                LbmArgs<T> a = lbm_args<T>(g, g.iold, g.inew, model);
+                if ((rc = launch_lbm<T>(a, model, true, g.variant, g.stream))) return rc;
+                swap_lattices(g);
+            }
+            s += L.depth;
+        }
+        return PLBM_OK;
+    }
     if ((g.variant == 9 || triples) && lbm_multi_applicable(g, model, triples ? 3 : 2)) {
         // the depth-generic multi-step kernel.  9: pairs through its NSTEP = 2 instance (measurement);
         // triples (three reference swaps = one swap of the indices; the result sits in lattice `inew`), then pairs.
@@ -489,6 +547,7 @@ int plbm_dealloc_grid(plbm_handle g)
     if (g->stream) cudaStreamSynchronize(g->stream);
     for (int i = 0; i < 3; ++i)
         if (g->f[i]) cudaFree(g->f[i]);
+    if (g->spare) cudaFree(g->spare);
     if (g->mf) cudaFree(g->mf);
     if (g->aux) cudaFree(g->aux);
     if (g->aux2) cudaFree(g->aux2);
@@ -984,6 +1043,26 @@ int plbm_lbm_steps_per_pass(plbm_handle g, int collision)
     if (level >= 0 && lbm_multi_applicable(*g, collision, 3) && (g->variant == 10 || lbm_triples_wanted(*g, level, collision))) return 3;
     if (g->comm && !comm_pairs_agreed(*g)) return 1;
     return lbm_pair_flavour(*g) ? 2 : 1;
+}
+
+int plbm_lbm_closing_triple(plbm_handle g, int collision)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return -1;
+    }
+    if (plbm_lbm_steps_per_pass(g, collision) != 3 || g->variant != 0 || !lbm_multi_shape_is_default()) return 0;
+    if (g->comm) return comm_dual_agreed(*g) && g->spare ? 1 : 0;
+    return lbm_spare(*g) ? 1 : 0;
+}
+
+int plbm_lbm_triple_kernel(plbm_handle g)
+{
+    if (!g) {
+        set_error("null grid handle");
+        return -1;
+    }
+    return lbm_triple_ws_wanted() ? 1 : 0;
 }
 
 int plbm_comm_unique_id(void* id128) { return comm_unique_id(id128); }

@@ -135,6 +135,7 @@ struct Comm {
     bool halo_valid = false;
     bool pairs_ok = false;  // every slab of the ring can run the two-step kernel (agreed at init)
     int triples_level = -1;  // minimum over the slabs of lbm_triples_level (agreed at init): three steps per pass
+    bool dual_ok = false;    // every rank holds a third lattice buffer (agreed at init): a call may close with a dual triple
     int halo_of_lattice = 0;
 };
 
@@ -281,6 +282,16 @@ static int p2p_setup(Grid& g)
     int level = lbm_triples_level(g) + 1;  // agree_min works on non-negative flags
     if ((rc = agree_min(g, &level))) return rc;
     c->triples_level = level - 1;
+    // a call may close with a triple that stores the states after its second and third step (Grid::spare) only if every rank has
+    // the third buffer: the ranks must issue the same launches
+    int dual = c->p2p && c->triples_level >= 1 && lbm_multi_shape_is_default() && lbm_spare(g) ? 1 : 0;
+    if ((rc = agree_min(g, &dual))) return rc;
+    c->dual_ok = dual != 0;
+    if (!c->dual_ok && g.spare) {
+        cudaFree(g.spare);
+        g.spare = nullptr;
+        g.spare_state = -1;
+    }
     if (c->p2p) {
         for (int p = 0; p < 2; ++p) {  // the halo slots now live inside the exported block
             cudaFree(c->halo_lo[p]);
@@ -326,6 +337,7 @@ int comm_allreduce(Grid& g, double* values, int n, int op)
 
 int comm_transport_is_p2p(const Grid& g) { return g.comm && g.comm->p2p ? 1 : 0; }
 bool comm_pairs_agreed(const Grid& g) { return g.comm && g.comm->pairs_ok; }
+bool comm_dual_agreed(const Grid& g) { return g.comm && g.comm->dual_ok && g.comm->p2p; }
 bool comm_triples_level(const Grid& g, int* level)
 {
     if (!g.comm) return false;
@@ -508,7 +520,7 @@ static int p2p_wait(Grid& g, unsigned e, cudaStream_t s)
 template <typename T> static int lbm_range(Grid& g, LbmArgs<T> a, int depth, int x0, int x1, int model, cudaStream_t s)
 {
     if (x1 <= x0) return PLBM_OK;
-    if (depth == 3) return launch_lbm_multi<T>(g, a.src, a.dst, x0, x1, model, a.cp, 3, s, a.halo_lo, a.halo_hi);
+    if (depth == 3) return launch_lbm_multi<T>(g, a.src, a.dst, x0, x1, model, a.cp, 3, s, a.halo_lo, a.halo_hi, a.mid);
     if (depth == 2) return launch_lbm_pair<T>(g, a.src, a.dst, x0, x1, a.halo_lo, a.halo_hi, model, a.cp, s);
     a.x_begin = x0;
     a.x_end = x1;
@@ -534,9 +546,12 @@ template <typename T> static int lbm_boundaries(Grid& g, LbmArgs<T> a, int depth
 
 // Lattice roles after one step or a fused triple (an odd number of reference swaps = one index swap) or after a fused pair (two
 // reference swaps = the indices stay, the result sits in the buffer that was `inew`: the buffers trade places).
-static void finish_steps(Grid& g, int depth)
+static void finish_steps(Grid& g, int depth, bool dual = false)
 {
-    if (depth == 2) {
+    if (dual) {  // a closing triple that also stored state n-1: `inew` becomes the third buffer, the source becomes the spare
+        std::swap(g.iold, g.inew);
+        lbm_adopt_spare_as_inew(g);
+    } else if (depth == 2) {
         std::swap(g.f[g.iold - 1], g.f[g.inew - 1]);
         for (int b = 0; b < 128; ++b) std::swap(g.tmap[g.iold - 1][b], g.tmap[g.inew - 1][b]);
     } else {
@@ -551,14 +566,16 @@ static int boundary_lines(const Grid& g) { return g.nx >= 2 * PLBM_HALO_LINES ? 
 // How many steps the next launch of a call advances: three while more than three remain and the ring takes triples for this
 // collision, two while more than two remain, else one (the last step stays single so that lattice `inew` ends up holding state
 // n-1 like the reference, see step_lbm_t).  Every rank computes the same sequence.
-static int next_depth(const Grid& g, int model, int s, int nsteps)
+static LbmLaunch next_launch(const Grid& g, int model, int s, int nsteps)
 {
     const Comm* c = g.comm;
     const bool triples = c->triples_level >= 0 && lbm_multi_applicable(g, model, 3) &&
                          (g.variant == 10 || lbm_triples_wanted(g, c->triples_level, model));
     const bool pairs = lbm_pair_variant(g.variant) && c->pairs_ok;
-    return lbm_next_depth(nsteps - 1 - s, triples, pairs);
+    const bool dual = c->dual_ok && c->p2p && g.variant == 0 && g.spare != nullptr;
+    return lbm_next_launch(nsteps - s, triples, pairs, dual);
 }
+static int next_depth(const Grid& g, int model, int s, int nsteps) { return next_launch(g, model, s, nsteps).depth; }
 
 // p2p transport, two streams per rank:
 //   B (high priority): wait(interior of the previous launch) -> wait(neighbours' flags) -> both boundaries, one launch
@@ -586,12 +603,14 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
     PLBM_CUDA(cudaEventRecord(c->ev_interior, M));
     bool first = true;
     for (int s = 0; s < nsteps;) {
-        const int depth = next_depth(g, model, s, nsteps);
+        const LbmLaunch L = next_launch(g, model, s, nsteps);
+        const int depth = L.depth;
         const unsigned e = c->epoch;
         const int slot = (int)(e & 1u);
         LbmArgs<T> a;
         a.src = g.lat<T>(g.iold);
         a.dst = g.lat<T>(g.inew);
+        a.mid = L.dual ? static_cast<T*>(g.spare) : nullptr;
         a.nx = g.nx;
         a.ny = g.ny;
         a.ld = g.ld;
@@ -612,7 +631,7 @@ template <typename T> static int p2p_lbm_steps(Grid& g, int model, const Collide
         a.halo_lo = a.halo_hi = nullptr;
         if ((rc = lbm_range<T>(g, a, depth, nb, g.nx - nb, model, M))) return rc;
         PLBM_CUDA(cudaEventRecord(c->ev_interior, M));
-        finish_steps(g, depth);
+        finish_steps(g, depth, L.dual);
         s += depth;
         first = false;
     }

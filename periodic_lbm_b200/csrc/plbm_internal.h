@@ -65,6 +65,12 @@ struct Grid {
     const void* fv_halo_hi = nullptr;
     // slab decomposition (single GPU: nx_global == nx, x_offset == 0)
     int nx_global = 0, x_offset = 0;
+    // A third, hidden lattice buffer for the launch that CLOSES a perform_lbm_step call (lbm_spare, plbm_api.cu): lattice `inew`
+    // must end up holding state n-1 and lattice `iold` state n, and with two buffers only a single-step launch can produce that
+    // (47 GLUPS against 106 for the triples).  With a third buffer the closing launch is a triple that stores the states after
+    // its second AND third step; the buffer it read becomes the spare.  Allocated on first use when the GPU has room for it.
+    void* spare = nullptr;
+    int spare_state = 0;  // 0 not tried yet, 1 allocated, -1 unavailable (no room, switched off, or the ring did not agree)
 
     size_t lattice_elems() const { return (size_t)ld * nx * 9; }
     size_t esize() const { return prec == PLBM_F64 ? 8 : 4; }
@@ -89,6 +95,7 @@ template <typename T> struct LbmArgs {
     const T* halo_hi;
     CollideParams<T> cp;
     T* pre = nullptr;      // optional: also store the streamed, pre-collision PDFs (perform_triple_step)
+    T* mid = nullptr;      // slab schedule, closing triple: also store the state after its second step here (Grid::spare)
 };
 
 // ---- launchers (all asynchronous on `s`) -------------------------------------------------
@@ -135,7 +142,14 @@ int launch_lbm_pair_fma(const Grid& g, const T* src, T* dst, int x_begin, int x_
 bool lbm_multi_applicable(const Grid& g, int model, int nstep);
 template <typename T>
 int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, int nstep,
-                     cudaStream_t s, const T* halo_lo = nullptr, const T* halo_hi = nullptr);
+                     cudaStream_t s, const T* halo_lo = nullptr, const T* halo_hi = nullptr,
+                     T* dst_mid = nullptr);  // dst_mid (three steps, default shape): the state after step 2 as well
+bool lbm_multi_shape_is_default();
+bool lbm_triple_ws_wanted();  // PLBM_TRIPLE_WS: the triples that read no halo lines go to k_lbm3_ws (plbm_lbm3w.cu)
+// three steps per pass, warp-specialised and skewed (plbm_lbm3w.cu): no halo lines; dst_mid != nullptr: the state after step 2 too
+template <typename T>
+int launch_lbm_triple_ws(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int x_end, int model, const CollideParams<T>& cp,
+                         cudaStream_t s);
 // Halo message of the slab decomposition: the PLBM_HALO_LINES nearest lines of each neighbour, all nine populations,
 // [PLBM_HALO_LINES][9][ld].  halo_lo holds lines -2, -1, -3 in that order (the first two are what one step / a fused pair read --
 // k_lbm, k_lbm2 --, the third was appended for three steps per pass); halo_hi holds lines nx, nx+1, nx+2.
@@ -155,6 +169,29 @@ inline int lbm_next_depth(int rem, bool triples, bool pairs)
     return pairs && rem >= 2 ? 2 : 1;
 }
 bool lbm_triples_wanted(const Grid& g, int level, int model);
+bool lbm_triples_forced();  // PLBM_TRIPLES=2
+// The next launch of a call with `rem` steps left (the closing one included).  dual: a third lattice buffer is available, so the
+// call may close with a triple that also stores the state after its second step (lattice `inew` = state n-1); otherwise the call
+// closes with a single step as lbm_next_depth says.  With a closing dual triple: 3 -> it; 5 -> a pair first; 4 -> triple + single;
+// 6 and more -> a triple.  Every rank of a ring computes the same sequence.
+struct LbmLaunch {
+    int depth;
+    bool dual;
+};
+inline LbmLaunch lbm_next_launch(int rem, bool triples, bool pairs, bool dual)
+{
+    if (dual && triples) {
+        if (rem == 3) return {3, true};
+        if (rem == 5 && pairs) return {2, false};
+        if (rem >= 4) return {3, false};
+        return {1, false};
+    }
+    return {lbm_next_depth(rem - 1, triples, pairs), false};
+}
+// the hidden third lattice buffer of a grid (see Grid::spare): allocates it on first use; nullptr if unavailable
+void* lbm_spare(Grid& g);
+void lbm_adopt_spare_as_inew(Grid& g);  // after a dual triple + index swap: lattice `inew` <- spare (state n-1), spare <- the old source
+
 bool comm_triples_level(const Grid& g, int* level);  // the ring's agreed level
 // TMA + mbarrier pipelined tile kernel (plbm_fvm_tma.cu); `which` = 1-based source lattice
 int make_tensor_maps(Grid& g);
@@ -178,6 +215,7 @@ int comm_init(Grid& g, const void* id128, int rank, int nranks, int nx_global, i
 int comm_finalize(Grid& g);
 int comm_transport_is_p2p(const Grid& g);
 bool comm_pairs_agreed(const Grid& g);  // every slab of the ring can run the two-step kernel
+bool comm_dual_agreed(const Grid& g);   // every rank of the ring holds the third lattice buffer (closing dual triple)
 void comm_invalidate_halo(Grid& g);  // the lattices were modified behind the ring's back
 // ring-wide reduction of n doubles in place (every rank calls it; NaN propagates through max / min as through sum)
 enum { PLBM_REDUCE_SUM = 0, PLBM_REDUCE_MAX = 2, PLBM_REDUCE_MIN = 3 };  // = ncclSum, ncclMax, ncclMin

@@ -52,6 +52,7 @@ template <typename T> struct LbmNArgs {
     const T* halo_lo;
     const T* halo_hi;
     CollideParams<T> cp;
+    T* dst_mid;  // DUAL: the state after step NSTEP - 1 goes here as well (the launch that closes a call, see step_lbm_t)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +107,7 @@ template <typename T, int V, typename ColOf> __device__ __forceinline__ void pul
 // HALO: columns below 0 / beyond nx - 1 come from the ring neighbours' halo lines (the boundary launches of a slab).  A template
 // parameter, not a run-time test: the copies are issued by ONE thread after the first barrier of every column while its warp
 // waits, and with the extra branches in that path the interior launch of the bench slab ran 4.75 ms instead of 4.0 (r02h).
-template <typename T, int MODEL, int V, int NT, int MINB, int NSTEP, bool HALO>
+template <typename T, int MODEL, int V, int NT, int MINB, int NSTEP, bool HALO, bool DUAL = false>
 __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
 {
     static_assert(NSTEP >= 2, "depth of the temporal blocking");
@@ -296,6 +297,15 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
                         for (int v = 0; v < V; ++v) p.v[v] = f[v][q];
                         *reinterpret_cast<VecN<T, V>*>(rout + (rn_base(q) + slot) * W) = p;
                     }
+                    if (DUAL && l == NSTEP - 1 && x + 1 >= xs && x + 1 < xe && active(NSTEP)) {  // column x + 1, the strip's own rows
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) {
+                            VecN<T, V> p;
+#pragma unroll
+                            for (int v = 0; v < V; ++v) p.v[v] = f[v][q];
+                            *reinterpret_cast<VecN<T, V>*>(a.dst_mid + ((size_t)q * a.nx + (x + 1)) * (size_t)a.ld + yp) = p;
+                        }
+                    }
                 }
             }
             __syncthreads();  // ring l-1 complete before level l+1 reads it; after the last level: slots may be rewritten
@@ -308,6 +318,9 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
 #ifndef PLBM_MULTI_WIDE_DEFAULT
 #define PLBM_MULTI_WIDE_DEFAULT 1
 #endif
+#ifndef PLBM_TRIPLE_WS_DEFAULT
+#define PLBM_TRIPLE_WS_DEFAULT 0
+#endif
 int env_knob(const char* name, int dflt)
 {
     const char* e = getenv(name);
@@ -318,9 +331,9 @@ int env_knob(const char* name, int dflt)
 // NT = 256 (NSTEP 3 only, PLBM_MULTI_NT=256): one 222 KB block of eight warps per SM, strips of up to 504 rows (fp64)
 // WIDE: 8 bytes per thread and 256 threads -- the shared memory of the 128-thread shape with twice the warps (NSTEP 3: two blocks
 // = sixteen warps per SM instead of eight)
-template <typename T, int MODEL, int NSTEP, int NT, bool WIDE = false>
+template <typename T, int MODEL, int NSTEP, int NT, bool WIDE = false, bool DUAL = false>
 int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, const CollideParams<T>& cp,
-             cudaStream_t s)
+             cudaStream_t s, T* dst_mid = nullptr)
 {
     constexpr int VA = 16 / (int)sizeof(T);
     constexpr int V = WIDE ? VA / 2 : VA;
@@ -334,7 +347,7 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     constexpr int MINB = by_smem < by_threads ? (by_smem < 24 ? by_smem : 24) : (by_threads < 24 ? by_threads : 24);
     if (x_end <= x_begin) return PLBM_OK;
     const bool halo = halo_lo && halo_hi;
-    auto kern = halo ? k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP, true> : k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP, false>;
+    auto kern = halo ? k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP, true, DUAL> : k_lbmn_bulk<T, MODEL, V, NT, MINB, NSTEP, false, DUAL>;
     static bool configured[64][2] = {{false}};
     if (g.device < 64 && !configured[g.device][halo]) {
         PLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -352,6 +365,7 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     a.halo_lo = halo_lo;
     a.halo_hi = halo_hi;
     a.cp = cp;
+    a.dst_mid = dst_mid;
     // the fewest strips (2 (NSTEP-1) V redundant rows each), 64-column segments (2 (NSTEP-1) warm-up columns each)
     const int ncols = x_end - x_begin;
     const int ty_max = (NT - 2 * (NSTEP - 1)) * V;
@@ -379,24 +393,26 @@ int launch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const 
     return PLBM_OK;
 }
 
-template <typename T, int NSTEP, int NT, bool WIDE = false>
+template <typename T, int NSTEP, int NT, bool WIDE = false, bool DUAL = false>
 int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, const T* halo_lo, const T* halo_hi, int model,
-               const CollideParams<T>& cp, cudaStream_t s)
+               const CollideParams<T>& cp, cudaStream_t s, T* dst_mid = nullptr)
 {
+#define PLBM_M(M) return launch_n<T, M, NSTEP, NT, WIDE, DUAL>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s, dst_mid)
     switch (model) {
-    case M_BGK: return launch_n<T, M_BGK, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_TRT: return launch_n<T, M_TRT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-    case M_RR: return launch_n<T, M_RR, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+    case M_BGK: PLBM_M(M_BGK);
+    case M_TRT: PLBM_M(M_TRT);
+    case M_RR: PLBM_M(M_RR);
     }
     // the -DSPLIT operators and collide_bgk_improved: the default shape only
     if constexpr (NSTEP == 3 && NT == 128 && WIDE) {
         switch (model) {
-        case M_BGK_SPLIT: return launch_n<T, M_BGK_SPLIT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-        case M_TRT_SPLIT: return launch_n<T, M_TRT_SPLIT, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
-        case M_BGK_IMPROVED: return launch_n<T, M_BGK_IMPROVED, NSTEP, NT, WIDE>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, cp, s);
+        case M_BGK_SPLIT: PLBM_M(M_BGK_SPLIT);
+        case M_TRT_SPLIT: PLBM_M(M_TRT_SPLIT);
+        case M_BGK_IMPROVED: PLBM_M(M_BGK_IMPROVED);
         }
     }
-    set_error("launch_lbm_multi: collision model not instantiated for the experimental multi-step kernel");
+#undef PLBM_M
+    set_error("launch_lbm_multi: collision model not instantiated for the multi-step kernel");
     return PLBM_ERR_ARG;
 }
 
@@ -405,6 +421,7 @@ int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, cons
 // the experimental kernel is instantiated for the three reference collision operators of the LBM path, on grids the
 // bulk copies can address (every staged piece a multiple of 16 bytes, the wrap pieces inside one line)
 bool lbm_multi_shape_is_default();
+bool lbm_triple_ws_wanted();
 bool lbm_multi_applicable(const Grid& g, int model, int nstep)
 {
     const int v = 16 / (int)g.esize();
@@ -440,11 +457,25 @@ int lbm_triples_level(const Grid& g)
     return (long long)g.nx * g.ny >= 512LL * 512LL ? 1 : 0;
 }
 
+// PLBM_TRIPLES=2 (tests): triples wherever the kernel applies, also where the cluster-resident kernel would take the whole call
+bool lbm_triples_forced()
+{
+    static const bool forced = env_knob("PLBM_TRIPLES", 1) >= 2;
+    return forced;
+}
+
 bool lbm_triples_wanted(const Grid& g, int level, int model)
 {
     static const int mode = env_knob("PLBM_TRIPLES", 1);
     if (mode == 0 || level < 0 || g.variant != 0 || !lbm_multi_applicable(g, model, 3)) return false;
     return mode >= 2 || level >= 1;
+}
+
+// PLBM_TRIPLE_WS: 1 = the launches of a triple that read no halo lines go to k_lbm3_ws (plbm_lbm3w.cu), 0 = to k_lbmn_bulk
+bool lbm_triple_ws_wanted()
+{
+    static const bool on = env_knob("PLBM_TRIPLE_WS", PLBM_TRIPLE_WS_DEFAULT) != 0;
+    return on;
 }
 
 bool lbm_multi_shape_is_default()
@@ -458,12 +489,16 @@ bool lbm_multi_shape_is_default()
 // under a slab decomposition ([PLBM_HALO_LINES][9][ld]), nullptr = periodic self-wrap.
 template <typename T>
 int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end, int model, const CollideParams<T>& cp, int nstep,
-                     cudaStream_t s, const T* halo_lo, const T* halo_hi)
+                     cudaStream_t s, const T* halo_lo, const T* halo_hi, T* dst_mid)
 {
-    if (!lbm_multi_applicable(g, model, nstep)) {
+    if (!lbm_multi_applicable(g, model, nstep) || (dst_mid && !(nstep == 3 && lbm_multi_shape_is_default()))) {
         set_error("launch_lbm_multi: not applicable to this grid / collision / depth");
         return PLBM_ERR_ARG;
     }
+    // three steps, no halo lines to read: the warp-specialised, skewed form of the kernel (plbm_lbm3w.cu)
+    if (nstep == 3 && !halo_lo && !halo_hi && lbm_triple_ws_wanted()) return launch_lbm_triple_ws<T>(g, src, dst, dst_mid, x_begin, x_end, model, cp, s);
+    // the launch that closes a call: the state after step 2 goes to dst_mid as well
+    if (dst_mid) return dispatch_n<T, 3, 128, true, true>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s, dst_mid);
 #define PLBM_N(NS, NT, WD) return dispatch_n<T, NS, NT, WD>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s)
     static const int wide2 = env_knob("PLBM_MULTI_WIDE2", 0);  // two steps per pass in the one-row shape (measurement, variant 9)
     if (nstep == 2 && wide2) PLBM_N(2, 128, true);
@@ -482,8 +517,8 @@ int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end
 }
 
 template int launch_lbm_multi<double>(const Grid&, const double*, double*, int, int, int, const CollideParams<double>&, int, cudaStream_t,
-                                      const double*, const double*);
+                                      const double*, const double*, double*);
 template int launch_lbm_multi<float>(const Grid&, const float*, float*, int, int, int, const CollideParams<float>&, int, cudaStream_t,
-                                     const float*, const float*);
+                                     const float*, const float*, float*);
 
 }  // namespace plbm

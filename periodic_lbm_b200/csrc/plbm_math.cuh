@@ -42,11 +42,22 @@ template <typename T> struct CollideParams {
     T lambda_d;  // lambda_d(omega, magic)  (TRT only)
 };
 
-// rho, ux, uy with the collision kernels' summation order (f0 added last).
-template <typename T> __device__ __forceinline__ void moments(const T (&f)[9], T& rho, T& ux, T& uy)
+// Density of a node in the collision kernels' summation order (f0 added last).
+template <typename T> __device__ __forceinline__ T node_rho(const T (&f)[9])
 {
-    rho = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
-    T invrho = T(1) / rho;
+    return (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
+}
+
+// The collisions that divide by the density take an optional `inv`: the reciprocal T(1) / node_rho(f), computed by the caller.
+// Same division on the same operand, so nothing changes in the result; a kernel that collides several independent nodes per
+// thread uses it to issue all the divisions first -- the IEEE division expands into a fast path plus a branch to a slow path, and
+// that branch otherwise ends the basic block, so that the instruction streams of the nodes could not be interleaved.
+
+// rho, ux, uy with the collision kernels' summation order (f0 added last).
+template <typename T> __device__ __forceinline__ void moments(const T (&f)[9], T& rho, T& ux, T& uy, const T* inv = nullptr)
+{
+    rho = node_rho(f);
+    T invrho = inv ? *inv : T(1) / rho;
     ux = invrho * (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3]));
     uy = invrho * (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4]));
 }
@@ -79,18 +90,18 @@ template <typename T> __device__ __forceinline__ void equilibrium(T rho, T ux, T
     feq[8] = wd * rho * (indp + T(3) * uxmy + T(4.5) * uxmy * uxmy);
 }
 
-template <typename T> __device__ __forceinline__ void collide_bgk(T (&f)[9], T omega)
+template <typename T> __device__ __forceinline__ void collide_bgk(T (&f)[9], T omega, const T* inv = nullptr)
 {
     T omegabar = T(1) - omega;
     T rho, ux, uy, feq[9];
-    moments(f, rho, ux, uy);
+    moments(f, rho, ux, uy, inv);
     equilibrium(rho, ux, uy, feq);
 #pragma unroll
     for (int q = 0; q < 9; ++q) f[q] = omegabar * f[q] + omega * feq[q];
 }
 
 // Re-associated BGK of kernel_bgk / bgk_kernel_cache (numerically different from collide_bgk).
-template <typename T> __device__ __forceinline__ void collide_bgk_split(T (&f)[9], T omega)
+template <typename T> __device__ __forceinline__ void collide_bgk_split(T (&f)[9], T omega, const T* inv = nullptr)
 {
     const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd();
     T omegabar = T(1) - omega;
@@ -98,7 +109,7 @@ template <typename T> __device__ __forceinline__ void collide_bgk_split(T (&f)[9
     T omega_ws = T(3) * omega * ws;
     T omega_wd = T(3) * omega * wd;
     T rho, ux, uy;
-    moments(f, rho, ux, uy);
+    moments(f, rho, ux, uy, inv);
     T indp = K<T>::one_third() - T(0.5) * (ux * ux + uy * uy);
 
     f[0] = omegabar * f[0] + omega_w0 * rho * indp;
@@ -203,7 +214,7 @@ template <typename T> __device__ __forceinline__ void collide_trt(T (&f)[9], T l
 }
 
 // Recursive-regularized collision with 3rd/4th-order Hermite equilibrium.
-template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T omega)
+template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T omega, const T* inv = nullptr)
 {
     const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd(), csqr = K<T>::csqr();
     T omega_w0 = w0 * (T(1) - omega);
@@ -215,7 +226,7 @@ template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T om
     T feq[9];
 
     T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
-    T invrho = T(1) / rho;
+    T invrho = inv ? *inv : T(1) / rho;
     T ux = invrho * (((vNE - vSW) + (vSE - vNW)) + (vE - vW));
     T uy = invrho * (((vNE - vSW) + (vNW - vSE)) + (vN - vS));
 
@@ -351,7 +362,7 @@ template <typename T> __device__ __forceinline__ void collide_trt_split(T (&f)[9
 // collide_bgk_improved (src/collision_bgk_improved.f90:24-107): product-form BGK with a cubic
 // Galilean-invariance correction.  The reference kernel ignores the padded leading dimension
 // (identical when ny is a multiple of 16); the intended per-node arithmetic is kept.
-template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f)[9], T omega)
+template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f)[9], T omega, const T* inv = nullptr)
 {
     const T one_third = T(1) / T(3), two_thirds = T(2) / T(3);
     T fac = T(4.5) - T(2.25) * omega;
@@ -360,7 +371,7 @@ template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f
     T vNE = f[5], vNW = f[6], vSW = f[7], vSE = f[8];
 
     T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
-    T invrho = T(1) / rho;
+    T invrho = inv ? *inv : T(1) / rho;
     T sumX1 = vE + vNE + vSE;
     T sumXN = vW + vNW + vSW;
     T sumY1 = vN + vNE + vNW;
@@ -394,15 +405,17 @@ template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f
     f[8] = omegabar * vSE + X1 * YN;
 }
 
-template <typename T, int MODEL> __device__ __forceinline__ void collide(T (&f)[9], const CollideParams<T>& p)
+template <typename T, int MODEL> __device__ __forceinline__ void collide(T (&f)[9], const CollideParams<T>& p, const T* inv = nullptr)
 {
-    if (MODEL == M_BGK) collide_bgk(f, p.omega);
+    if (MODEL == M_BGK) collide_bgk(f, p.omega, inv);
     else if (MODEL == M_TRT) collide_trt(f, p.omega, p.lambda_d);
-    else if (MODEL == M_RR) collide_rr(f, p.omega);
-    else if (MODEL == M_BGK_SPLIT) collide_bgk_split(f, p.omega);
+    else if (MODEL == M_RR) collide_rr(f, p.omega, inv);
+    else if (MODEL == M_BGK_SPLIT) collide_bgk_split(f, p.omega, inv);
     else if (MODEL == M_TRT_SPLIT) collide_trt_split(f, p.omega, p.lambda_d);
-    else if (MODEL == M_BGK_IMPROVED) collide_bgk_improved(f, p.omega);
+    else if (MODEL == M_BGK_IMPROVED) collide_bgk_improved(f, p.omega, inv);
 }
+// does collide<T, MODEL> divide by the density (i.e. does it take `inv`)
+__host__ __device__ constexpr bool model_divides(int model) { return model != M_TRT && model != M_TRT_SPLIT && model != M_NONE; }
 
 // Collision of the V vertically adjacent nodes a thread owns.  PACKED (fp32 only, V even): two nodes per instruction
 // through the packed pair type F2 (plbm_f32x2.cuh) -- the same individually rounded operations on the same operands, so
@@ -438,6 +451,39 @@ template <int MODEL, int V> struct CollideNodes<float, MODEL, V, true> {
 template <typename T, int MODEL, int V, bool PACKED> __device__ __forceinline__ void collide_nodes(T (&n)[V][9], const CollideParams<T>& p)
 {
     CollideNodes<T, MODEL, V, PACKED>::run(n, p);
+}
+
+// The same in two parts: node_reciprocals() issues the divisions of the V nodes (nothing for a collision that does not divide),
+// collide_nodes(n, p, inv) does the rest -- bit-identical to collide_nodes(n, p), see the note at node_rho.
+template <typename T, int MODEL, int V> __device__ __forceinline__ void node_reciprocals(const T (&n)[V][9], T (&inv)[V])
+{
+#pragma unroll
+    for (int v = 0; v < V; ++v) inv[v] = model_divides(MODEL) ? T(1) / node_rho(n[v]) : T(0);
+}
+template <typename T, int MODEL, int V, bool PACKED>
+__device__ __forceinline__ void collide_nodes(T (&n)[V][9], const CollideParams<T>& p, const T (&inv)[V])
+{
+    if constexpr (PACKED && sizeof(T) == 4 && (V % 2) == 0) {
+        CollideParams<F2> p2;
+        p2.omega = F2(p.omega);
+        p2.lambda_d = F2(p.lambda_d);
+#pragma unroll
+        for (int v = 0; v < V; v += 2) {
+            F2 f[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) f[q] = F2(n[v][q], n[v + 1][q]);
+            const F2 i2(inv[v], inv[v + 1]);
+            collide<F2, MODEL>(f, p2, &i2);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                n[v][q] = f[q].lo();
+                n[v + 1][q] = f[q].hi();
+            }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], p, &inv[v]);
+    }
 }
 
 // 2nd-order, half-step back-traced face reconstruction of one population from its 3x3

@@ -143,6 +143,22 @@ class LatticeGrid:
             check(k, "lbm_steps_per_pass")
         return k
 
+    def triple_kernel(self):
+        """Kernel of the three-step launches that read no halo lines: 'k_lbmn_bulk' or 'k_lbm3_ws' (PLBM_TRIPLE_WS)."""
+        k = lib.plbm_lbm_triple_kernel(self._h)
+        if k < 0:
+            check(k, "lbm_triple_kernel")
+        return ("k_lbmn_bulk", "k_lbm3_ws")[k]
+
+    def closing_triple(self, collision=None):
+        """True if a many-step perform_lbm_step call on this grid closes with a fused triple that also stores state n-1 (a third,
+        hidden lattice buffer is available), False if it closes with a single-step launch.  Bit-identical either way."""
+        coll = collision if collision is not None else self.collision
+        k = lib.plbm_lbm_closing_triple(self._h, _COLLISION_ID[coll] if callable(coll) else int(coll))
+        if k < 0:
+            check(k, "lbm_closing_triple")
+        return bool(k)
+
     def set_fdm_stencil(self, stencil):
         """Derivative stencil of stream_fdm_bardow; the reference picks it at compile time with -DFDM_WLS,
         -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660)."""

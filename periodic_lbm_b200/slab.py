@@ -59,12 +59,21 @@ def halo_message_bytes(ny: int, itemsize: int) -> int:
     return HALO_LINES * 9 * ((ny + 15) // 16 * 16) * itemsize
 
 
-def launch_schedule(nsteps: int, pairs: bool = True, triples: bool = False) -> list:
+def launch_schedule(nsteps: int, pairs: bool = True, triples: bool = False, dual: bool = False) -> list:
     """Steps advanced by each launch of one perform_lbm_step(nsteps) call: fused triples while more than three
     steps remain (where the ring takes them: every slab at least 2 * HALO_LINES lines wide), fused pairs while
     more than two remain (the last step stays single so that lattice `inew` ends up holding state nsteps-1
-    exactly like the reference), then single steps."""
+    exactly like the reference), then single steps.
+
+    dual (with triples): every rank holds a third lattice buffer, so the call may CLOSE with a triple that stores the states
+    after its second and third step (csrc/plbm_internal.h lbm_next_launch): 3 left -> that triple; 5 left -> a pair first;
+    4 left -> triple + single; 6 or more -> a triple.  The closing dual triple is listed as 3 like any other."""
     out, s = [], 0
+    while dual and triples and s < nsteps:
+        rem = nsteps - s
+        n = 3 if rem == 3 else (2 if rem == 5 and pairs else (3 if rem >= 4 else 1))
+        out.append(n)
+        s += n
     while s < nsteps:
         rem = nsteps - 1 - s  # steps before the closing single step
         if triples and rem >= 3 and not (pairs and rem == 4):  # four remaining steps go as two pairs, not triple + single

@@ -50,17 +50,20 @@ def _worker(rank, world, idq, outq, nxg, ny, steps, coll_id, prec, seed, halo="p
             assert g.pair_kernel() == expect_kernel, (g.pair_kernel(), expect_kernel)
         if expect_steps_per_pass is not None:
             assert g.steps_per_pass() == expect_steps_per_pass, (g.steps_per_pass(), expect_steps_per_pass)
+        if (env or {}).get("EXPECT_CLOSING_TRIPLE"):
+            assert g.closing_triple() and g.triple_kernel() == "k_lbm3_ws", (g.closing_triple(), g.triple_kernel())
         # two calls: exercises the "halo already in flight" path between calls
         p.perform_lbm_step(g, steps // 2)
         p.perform_lbm_step(g, steps - steps // 2)
     got = g.download_f(g.iold)
+    got_inew = g.download_f(g.inew)
     p.update_macros(g, lagged=False)
     # global diagnostics: every rank gets the numbers of the WHOLE grid
     diag = g.diagnostics()
     uxa, uya = _analytic_fields(nxg, ny, g.dtype)
     l2 = g.l2_sums(np.ascontiguousarray(uxa[sl.x_offset:sl.x_end]), np.ascontiguousarray(uya[sl.x_offset:sl.x_end]))
     om2, om4 = p.vorticity_2nd(None, None, grid=g), p.vorticity_4th(None, None, grid=g)  # d(uy)/dx crosses the slab boundaries
-    outq.put((rank, sl.x_offset, got, transport, diag, l2, om2, om4))
+    outq.put((rank, sl.x_offset, got, transport, diag, l2, om2, om4, got_inew))
     check(lib.plbm_comm_finalize(g._h), "comm_finalize")
     p.dealloc_grid(g)
 
@@ -155,6 +158,38 @@ def test_slabs_with_three_steps_per_pass_bitwise_equal_single_gpu(plbm, world, h
     assert np.array_equal(multi[:, :, :ny], single[:, :, :ny])
     for t in parts:
         assert t[4]["max_speed"] == diag["max_speed"]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("nxg,ny,steps,coll_id", [(512, 2048, 10, 0), (64, 64, 12, 1), (48, 132, 16, 2), (24, 36, 6, 0), (96, 516, 11, 2)])
+def test_slabs_closing_dual_triple_bitwise_equal_single_gpu(plbm, world, prec, nxg, ny, steps, coll_id):
+    """A call that closes with a triple storing the states after its second AND third step (third lattice buffer on every rank,
+    csrc/plbm_comm.cu dual_ok): interior launches by k_lbm3_ws, boundary launches by k_lbmn_bulk<HALO, DUAL>.  Two calls per run.
+    Lattice `iold` (state n) and lattice `inew` (state n-1) of the slabs equal the single-GPU lattices bit for bit."""
+    if plbm.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    if nxg // world < 6:
+        pytest.skip("slabs thinner than six lines do not take triples")
+    if prec == "f32" and ny % 4:
+        pytest.skip("fp32 rows come in fours")
+    seed = 23
+    env = {"PLBM_TRIPLES": "2", "PLBM_SPARE_LATTICE": "2", "PLBM_TRIPLE_WS": "1", "EXPECT_CLOSING_TRIPLE": "1"}
+    parts = _run_ring(plbm, world, nxg, ny, steps, coll_id, prec, seed, "p2p", env=env, expect_steps_per_pass=3)
+    assert all(t[3] == 1 for t in parts)
+    from conftest import random_state
+    from oracle.oracle import Oracle
+
+    f0 = np.nan_to_num(random_state(Oracle(prec), nxg, ny, seed=seed), nan=0.0)
+    g = plbm.alloc_grid(nxg, ny, precision=prec)
+    plbm.set_properties(g, 0.02, 1.0, 0.25)
+    g.upload_f(g.iold, f0)
+    g.collision, g.streaming = {0: plbm.collide_bgk, 1: plbm.collide_trt, 2: plbm.collide_rr}[coll_id], plbm.lbm_stream
+    plbm.perform_lbm_step(g, steps)
+    single_iold, single_inew = g.download_f(g.iold), g.download_f(g.inew)
+    plbm.dealloc_grid(g)
+    assert np.array_equal(np.concatenate([t[2] for t in parts], axis=1)[:, :, :ny], single_iold[:, :, :ny])
+    assert np.array_equal(np.concatenate([t[8] for t in parts], axis=1)[:, :, :ny], single_inew[:, :, :ny])
 
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])

@@ -167,3 +167,27 @@ def test_text_writers_use_the_reference_edit_descriptors(tmp_path):
     first = [float(v) for v in txt[0].split()]
     assert first == [0.5, 0.5, 1.0, 0.25, -0.125]
     assert [float(v) for v in txt[ny + 1].split()][:3] == [1.5, 0.5, 3.0]
+
+
+def test_launch_schedule_with_a_closing_dual_triple():
+    """periodic_lbm_b200/slab.py launch_schedule(dual=True) mirrors csrc/plbm_internal.h lbm_next_launch: with a third lattice
+    buffer a call closes with a triple (no single-step launch) unless one step is left over, and never takes more launches."""
+    from periodic_lbm_b200.slab import launch_schedule
+
+    for k in range(1, 60):
+        old = launch_schedule(k, pairs=True, triples=True)
+        new = launch_schedule(k, pairs=True, triples=True, dual=True)
+        assert sum(old) == k and sum(new) == k and old[-1] == 1
+        assert len(new) <= len(old)
+        if k >= 3 and k % 3 != 1:
+            assert new[-1] == 3 and 1 not in new and new.count(2) == (1 if k % 3 == 2 else 0), (k, new)
+        elif k >= 4:
+            assert new == [3] * (k // 3) + [1], (k, new)
+        else:
+            assert new == [1] * k
+        # no pairs on this grid: a call of 3 m + 2 steps ends triple, single, single
+        np_ = launch_schedule(k, pairs=False, triples=True, dual=True)
+        assert sum(np_) == k and 2 not in np_
+    assert launch_schedule(20, True, True, True) == [3, 3, 3, 3, 3, 2, 3]
+    assert launch_schedule(20, True, True, False) == [3, 3, 3, 3, 3, 2, 2, 1]
+    assert launch_schedule(7, True, False, True) == launch_schedule(7, True, False, False)  # dual needs triples

@@ -29,7 +29,7 @@ def run(nx, ny, prec, coll, variant, steps, reps, once=False):
     g.collision, g.streaming = getattr(p, "collide_" + coll), p.lbm_stream
     kernel = g.pair_kernel()  # what variants 5..8 use (9 / 10: k_lbmn_bulk, 11: the FMA build of this one)
     if variant in (9, 10) or (variant == 0 and g.steps_per_pass() == 3):
-        kernel = "k_lbmn_bulk"
+        kernel = g.triple_kernel() if variant == 0 else "k_lbmn_bulk"
     if once:
         p.perform_lbm_step(g, 4)  # one pair + two single steps; variant 10: one triple + one single step
         g.synchronize()
