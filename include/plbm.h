@@ -220,10 +220,11 @@ int plbm_lbm_steps_per_pass(plbm_handle grid, int collision);
  * buffer + 1 GB stays free --, 2 whenever the allocation succeeds); under a slab decomposition every rank must have it.  Results are
  * bit-identical either way.  For bench accounting; -1 on a null handle. */
 int plbm_lbm_closing_triple(plbm_handle grid, int collision);
-/* which kernel runs the three-step launches that read no halo lines (every launch on one GPU, the interior launches of a slab):
- * 0 = k_lbmn_bulk (csrc/plbm_lbmn.cu: levels one after the other, a barrier after each), 1 = k_lbm3_ws (csrc/plbm_lbm3w.cu: a producer
- * warp, levels skewed by two columns, one barrier per column).  Environment PLBM_TRIPLE_WS selects; bit-identical.  -1 on a null handle. */
-int plbm_lbm_triple_kernel(plbm_handle grid);
+/* which kernel runs the three-step launches of this collision that read no halo lines (every launch on one GPU, the interior
+ * launches of a slab): 0 = k_lbmn_bulk (csrc/plbm_lbmn.cu: levels one after the other, a barrier after each), 1 = k_lbm3_ws
+ * (csrc/plbm_lbm3w.cu: a producer warp, levels skewed by two columns, one barrier per column; the default except for the
+ * two-relaxation-time collisions).  Environment PLBM_TRIPLE_WS = 0 / 1 forces one of them; bit-identical.  -1 on a null handle. */
+int plbm_lbm_triple_kernel(plbm_handle grid, int collision);
 /* derivative stencil of stream_fdm_bardow: the reference selects it at compile time with -DFDM_WLS,
  * -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2 or -DFDM_ISO (src/fvm_bardow.F90:591-660); default = none of them. */
 enum plbm_fdm_stencil { PLBM_FDM_DEFAULT = 0, PLBM_FDM_WLS = 1, PLBM_FDM_WLS_GAUSS_V1 = 2, PLBM_FDM_WLS_GAUSS_V2 = 3, PLBM_FDM_ISO = 4 };

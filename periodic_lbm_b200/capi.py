@@ -62,7 +62,7 @@ SIGNATURES = {
     "plbm_lbm_pair_kernel": (_I, [_H]),
     "plbm_lbm_steps_per_pass": (_I, [_H, _I]),
     "plbm_lbm_closing_triple": (_I, [_H, _I]),
-    "plbm_lbm_triple_kernel": (_I, [_H]),
+    "plbm_lbm_triple_kernel": (_I, [_H, _I]),
     "plbm_set_fdm_stencil": (_I, [_H, _I]),
     "plbm_comm_unique_id": (_I, [_P]),
     "plbm_comm_init": (_I, [_H, _P, _I, _I, _I, _I]),

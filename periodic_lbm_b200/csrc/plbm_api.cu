@@ -1056,13 +1056,13 @@ int plbm_lbm_closing_triple(plbm_handle g, int collision)
     return lbm_spare(*g) ? 1 : 0;
 }
 
-int plbm_lbm_triple_kernel(plbm_handle g)
+int plbm_lbm_triple_kernel(plbm_handle g, int collision)
 {
     if (!g) {
         set_error("null grid handle");
         return -1;
     }
-    return lbm_triple_ws_wanted() ? 1 : 0;
+    return lbm_triple_ws_wanted(collision) ? 1 : 0;
 }
 
 int plbm_comm_unique_id(void* id128) { return comm_unique_id(id128); }

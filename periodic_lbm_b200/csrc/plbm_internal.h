@@ -145,7 +145,7 @@ int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end
                      cudaStream_t s, const T* halo_lo = nullptr, const T* halo_hi = nullptr,
                      T* dst_mid = nullptr);  // dst_mid (three steps, default shape): the state after step 2 as well
 bool lbm_multi_shape_is_default();
-bool lbm_triple_ws_wanted();  // PLBM_TRIPLE_WS: the triples that read no halo lines go to k_lbm3_ws (plbm_lbm3w.cu)
+bool lbm_triple_ws_wanted(int model);  // the triples that read no halo lines go to k_lbm3_ws (plbm_lbm3w.cu); PLBM_TRIPLE_WS overrides
 // three steps per pass, warp-specialised and skewed (plbm_lbm3w.cu): no halo lines; dst_mid != nullptr: the state after step 2 too
 template <typename T>
 int launch_lbm_triple_ws(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int x_end, int model, const CollideParams<T>& cp,

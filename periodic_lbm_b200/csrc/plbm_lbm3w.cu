@@ -120,11 +120,15 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k_lbm3_ws(const Lbm3Args<T> a)
     constexpr int HS = (NR * V + 1 + VA - 1) / VA * VA;
     constexpr int OFF = HS - NR * V;
     constexpr int WS = W + 2 * OFF;
-    constexpr int PAD = VA;  // rows behind the last ring slot (the row above the last thread's)
+    // a ring slot = V pad rows, the W rows of the threads, V pad rows: the levels run unpredicated on the halo threads as well, and
+    // thread 0 / the last thread pull the row below / above theirs -- that row is a pad row nobody writes, not a row of the
+    // neighbouring slot (which another thread may be writing in the same iteration: harmless, the halo thread's result is thrown
+    // away, but compute-sanitizer racecheck reports it, r02r)
+    constexpr int WP = W + 2 * V;
     extern __shared__ __align__(128) unsigned char smem_n[];
     T* stage = reinterpret_cast<T*>(smem_n);       // [2][9][WS]
-    T* ring = stage + 2 * 9 * WS;                  // [2][RS_SLOTS][W]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * RS_SLOTS * W + PAD);
+    T* ring = stage + 2 * 9 * WS;                  // [2][RS_SLOTS][WP]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * RS_SLOTS * WP);
     const uint32_t bar0 = smem_addr(bars);
 
     const int strip = blockIdx.x % a.nstrips, seg = blockIdx.x / a.nstrips;
@@ -141,7 +145,8 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k_lbm3_ws(const Lbm3Args<T> a)
     // every shared-memory word a thread may read holds a finite positive number from the start: the levels run unpredicated on
     // the halo threads too (only their stores are predicated), and 1 / rho of an arbitrary bit pattern could take the slow path
     {
-        constexpr int NWORDS = (2 * 9 * WS + 2 * RS_SLOTS * W + PAD) / VA;
+        constexpr int NWORDS = (2 * 9 * WS + 2 * RS_SLOTS * WP) / VA;
+        static_assert((2 * 9 * WS + 2 * RS_SLOTS * WP) % VA == 0, "whole 16-byte words");
         VecN<T, VA> one;
 #pragma unroll
         for (int v = 0; v < VA; ++v) one.v[v] = T(1);
@@ -203,8 +208,8 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k_lbm3_ws(const Lbm3Args<T> a)
     const int yl = y_lo - NR * V + t * V;  // logical first row of this thread
     const bool a1 = yl < y_hi + 2 * V, a2 = yl >= y_lo - V && yl < y_hi + V, a3 = yl >= y_lo && yl < y_hi;
     const T* st0 = stage + OFF + t * V;
-    T* rg0 = ring + t * V;
-    T* rg1 = rg0 + RS_SLOTS * W;
+    T* rg0 = ring + V + t * V;
+    T* rg1 = rg0 + RS_SLOTS * WP;
     const size_t qs = (size_t)a.nx * a.ld;
     T* out3 = a.dst + (size_t)(x_first - 4) * a.ld + yl;  // column j - 4 of population 0, this thread's first row
     T* out2 = DUAL ? a.dst_mid + (size_t)(x_first - 2) * a.ld + yl : nullptr;
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k_lbm3_ws(const Lbm3Args<T> a)
             VecN<T, V> p;
 #pragma unroll
             for (int v = 0; v < V; ++v) p.v[v] = n[v][q];
-            *reinterpret_cast<VecN<T, V>*>(rg + slot_w(q, w2, w3, w4) * W) = p;
+            *reinterpret_cast<VecN<T, V>*>(rg + slot_w(q, w2, w3, w4) * WP) = p;
         }
     };
     auto to_global = [&](T* o, const T (&n)[V][9]) {
@@ -247,8 +252,8 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k_lbm3_ws(const Lbm3Args<T> a)
                 const T* st = st0 + (k & 1) * 9 * WS;
                 pull_rows<T, V>([&](int q) { return st + q * WS; }, n1);
             }
-            pull_rows<T, V>([&](int q) { return rg0 + slot_w(q, r2, r3, r4) * W; }, n2);
-            pull_rows<T, V>([&](int q) { return rg1 + slot_w(q, r2, r3, r4) * W; }, n3);
+            pull_rows<T, V>([&](int q) { return rg0 + slot_w(q, r2, r3, r4) * WP; }, n2);
+            pull_rows<T, V>([&](int q) { return rg1 + slot_w(q, r2, r3, r4) * WP; }, n3);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             stage_read(k);
             T i1[V], i2[V], i3[V];
@@ -279,14 +284,14 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k_lbm3_ws(const Lbm3Args<T> a)
             }
             if (l2) {
                 T n2[V][9];
-                pull_rows<T, V>([&](int q) { return rg0 + slot_w(q, r2, r3, r4) * W; }, n2);
+                pull_rows<T, V>([&](int q) { return rg0 + slot_w(q, r2, r3, r4) * WP; }, n2);
                 collide_nodes<T, MODEL, V, PACKED>(n2, a.cp);
                 if (a2) to_ring(rg1, n2, w2, w3, w4);
                 if (DUAL && a3 && j - 2 >= xs && j - 2 < xe) to_global(out2, n2);
             }
             if (l3) {
                 T n3[V][9];
-                pull_rows<T, V>([&](int q) { return rg1 + slot_w(q, r2, r3, r4) * W; }, n3);
+                pull_rows<T, V>([&](int q) { return rg1 + slot_w(q, r2, r3, r4) * WP; }, n3);
                 collide_nodes<T, MODEL, V, PACKED>(n3, a.cp);
                 if (a3) to_global(out3, n3);
             }
@@ -312,8 +317,8 @@ int launch_3w(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int 
     constexpr int VA = 16 / (int)sizeof(T);
     constexpr int V = VA / 2;  // one row (fp64) / two rows (fp32) per thread, like the default shape of k_lbmn_bulk
     constexpr int HS = (2 * V + 1 + VA - 1) / VA * VA;
-    constexpr int W = NTC * V, WS = W + 2 * (HS - 2 * V);
-    constexpr size_t smem = ((size_t)2 * 9 * WS + 2 * RS_SLOTS * W + VA) * sizeof(T) + 16;
+    constexpr int W = NTC * V, WS = W + 2 * (HS - 2 * V), WP = W + 2 * V;
+    constexpr size_t smem = ((size_t)2 * 9 * WS + 2 * RS_SLOTS * WP) * sizeof(T) + 16;
     constexpr int MINB = (int)((size_t)(228 * 1024) / (smem + 1024));
     static_assert(MINB == (NTC == 128 ? 3 : (NTC == 96 ? 4 : 2)), "three blocks of five warps per SM (NTC = 128)");
     if (x_end <= x_begin) return PLBM_OK;
@@ -341,7 +346,8 @@ int launch_3w(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int 
     a.nstrips = (g.ny + ty_max - 1) / ty_max;
     a.ty = ((g.ny + a.nstrips - 1) / a.nstrips + VA - 1) / VA * VA;
     a.nstrips = (g.ny + a.ty - 1) / a.ty;
-    static const int seg_cols = env_knob3("PLBM_WS_SEGLEN", 64) < 1 ? 64 : env_knob3("PLBM_WS_SEGLEN", 64);
+    // 128-column segments (six ramp iterations each): r02r, 64 / 96 / 128 / 192 / 256 columns within 1 % of each other, 128 best overall
+    static const int seg_cols = env_knob3("PLBM_WS_SEGLEN", 128) < 1 ? 128 : env_knob3("PLBM_WS_SEGLEN", 128);
     int nseg = (ncols + seg_cols - 1) / seg_cols;
     const long long slots = (long long)MINB * g.sm_count;
     const long long blocks64 = (long long)a.nstrips * nseg;

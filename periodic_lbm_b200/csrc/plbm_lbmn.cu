@@ -318,9 +318,7 @@ __global__ void __launch_bounds__(NT, MINB) k_lbmn_bulk(const LbmNArgs<T> a)
 #ifndef PLBM_MULTI_WIDE_DEFAULT
 #define PLBM_MULTI_WIDE_DEFAULT 1
 #endif
-#ifndef PLBM_TRIPLE_WS_DEFAULT
-#define PLBM_TRIPLE_WS_DEFAULT 0
-#endif
+
 int env_knob(const char* name, int dflt)
 {
     const char* e = getenv(name);
@@ -421,7 +419,7 @@ int dispatch_n(const Grid& g, const T* src, T* dst, int x_begin, int x_end, cons
 // the experimental kernel is instantiated for the three reference collision operators of the LBM path, on grids the
 // bulk copies can address (every staged piece a multiple of 16 bytes, the wrap pieces inside one line)
 bool lbm_multi_shape_is_default();
-bool lbm_triple_ws_wanted();
+bool lbm_triple_ws_wanted(int model);
 bool lbm_multi_applicable(const Grid& g, int model, int nstep)
 {
     const int v = 16 / (int)g.esize();
@@ -471,11 +469,19 @@ bool lbm_triples_wanted(const Grid& g, int level, int model)
     return mode >= 2 || level >= 1;
 }
 
-// PLBM_TRIPLE_WS: 1 = the launches of a triple that read no halo lines go to k_lbm3_ws (plbm_lbm3w.cu), 0 = to k_lbmn_bulk
-bool lbm_triple_ws_wanted()
+// Which kernel takes the launches of a triple that read no halo lines: k_lbm3_ws (plbm_lbm3w.cu: producer warp, skewed levels, one
+// barrier per column, three blocks per SM) or k_lbmn_bulk (this file: a barrier after every level, four blocks per SM).  Measured on
+// a B200 (r02q / r02r, 20-step calls closed by a dual triple, GLUPS, k_lbmn_bulk -> k_lbm3_ws with 128-column segments):
+//   bench slab 32768 x 4096 BGK fp64 101.7 -> 103.5     8192^2 BGK fp64 99.9 -> 101.6   RR fp64 68.9 -> 70.8   TRT fp64 110.7 -> 107.8
+//   8192^2 BGK fp32 161.6 -> 164.5   RR fp32 112.0 -> 114.4     2048^2 BGK fp64 82.3 -> 88.2     1024^2 TRT fp64 74.5 -> 76.4
+// k_lbm3_ws wins wherever the collision carries a division (its three independent chains per thread hide the reciprocal); the
+// two-relaxation-time collisions have none and are faster with the sixteen warps per SM of k_lbmn_bulk on large grids.
+// PLBM_TRIPLE_WS: 0 = always k_lbmn_bulk, 1 = always k_lbm3_ws, unset = that rule.
+bool lbm_triple_ws_wanted(int model)
 {
-    static const bool on = env_knob("PLBM_TRIPLE_WS", PLBM_TRIPLE_WS_DEFAULT) != 0;
-    return on;
+    static const int mode = env_knob("PLBM_TRIPLE_WS", -1);
+    if (mode >= 0) return mode != 0;
+    return model != M_TRT && model != M_TRT_SPLIT;
 }
 
 bool lbm_multi_shape_is_default()
@@ -496,7 +502,7 @@ int launch_lbm_multi(const Grid& g, const T* src, T* dst, int x_begin, int x_end
         return PLBM_ERR_ARG;
     }
     // three steps, no halo lines to read: the warp-specialised, skewed form of the kernel (plbm_lbm3w.cu)
-    if (nstep == 3 && !halo_lo && !halo_hi && lbm_triple_ws_wanted()) return launch_lbm_triple_ws<T>(g, src, dst, dst_mid, x_begin, x_end, model, cp, s);
+    if (nstep == 3 && !halo_lo && !halo_hi && lbm_triple_ws_wanted(model)) return launch_lbm_triple_ws<T>(g, src, dst, dst_mid, x_begin, x_end, model, cp, s);
     // the launch that closes a call: the state after step 2 goes to dst_mid as well
     if (dst_mid) return dispatch_n<T, 3, 128, true, true>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s, dst_mid);
 #define PLBM_N(NS, NT, WD) return dispatch_n<T, NS, NT, WD>(g, src, dst, x_begin, x_end, halo_lo, halo_hi, model, cp, s)

@@ -143,9 +143,11 @@ class LatticeGrid:
             check(k, "lbm_steps_per_pass")
         return k
 
-    def triple_kernel(self):
-        """Kernel of the three-step launches that read no halo lines: 'k_lbmn_bulk' or 'k_lbm3_ws' (PLBM_TRIPLE_WS)."""
-        k = lib.plbm_lbm_triple_kernel(self._h)
+    def triple_kernel(self, collision=None):
+        """Kernel of the three-step launches of a collision (default: grid.collision) that read no halo lines: 'k_lbmn_bulk' or
+        'k_lbm3_ws' (the default except for the two-relaxation-time collisions; PLBM_TRIPLE_WS = 0 / 1 forces one)."""
+        coll = collision if collision is not None else self.collision
+        k = lib.plbm_lbm_triple_kernel(self._h, _COLLISION_ID[coll] if callable(coll) else int(coll))
         if k < 0:
             check(k, "lbm_triple_kernel")
         return ("k_lbmn_bulk", "k_lbm3_ws")[k]

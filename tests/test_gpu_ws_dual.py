@@ -14,10 +14,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("ws,spare", [(1, 2), (0, 2), (1, 0)])
+@pytest.mark.parametrize("ws,spare", [(1, 2), (0, 2), (1, 0), (None, 2)])
 def test_three_step_kernels_and_closing_dual_triple(plbm, ws, spare):
-    env = dict(os.environ, PLBM_TRIPLES="2", PLBM_TRIPLE_WS=str(ws), PLBM_SPARE_LATTICE=str(spare))
-    kernel = "k_lbm3_ws" if ws else "k_lbmn_bulk"
+    """ws: 1 / 0 = k_lbm3_ws / k_lbmn_bulk forced for every collision, None = the library's own choice per collision"""
+    env = dict(os.environ, PLBM_TRIPLES="2", PLBM_SPARE_LATTICE=str(spare))
+    env.pop("PLBM_TRIPLE_WS", None)
+    if ws is not None:
+        env["PLBM_TRIPLE_WS"] = str(ws)
+    kernel = "auto" if ws is None else ("k_lbm3_ws" if ws else "k_lbmn_bulk")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ws_dual_worker.py"), kernel, "1" if spare else "0"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

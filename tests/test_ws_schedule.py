@@ -8,7 +8,8 @@ lane, wrap around x), the staged periodic pieces, the stage / mbarrier-phase boo
 iterations, the per-level store predicates, the running output pointers and the optional second output (state after step 2).
 Every ring slot remembers which column it holds, so a slot that is overwritten before its last reader, or read before it is
 written, fails the test; values come out bit for bit equal to three oracle steps.  What it cannot see: barriers, the async proxy,
-named-barrier counts -- those are the -m gpu parity tests' job."""
+named-barrier counts -- those are the -m gpu parity tests' job.  It does see what compute-sanitizer racecheck sees inside an
+iteration: a word that one thread reads and another writes without a barrier in between (the reason for the pad rows of a slot)."""
 import numpy as np
 import pytest
 
@@ -65,9 +66,11 @@ def emulate_ws(o, collide, src, nx, ny, ntc, v, seg_cols, x_begin=0, x_end=None,
             a1 = yl < y_hi + 2 * v
             a2 = (yl >= y_lo - v) & (yl < y_hi + v)
             a3 = (yl >= y_lo) & (yl < y_hi)
-            # shared memory starts as ones (finite, positive): [stage | ring 0 | ring 1 | pad], flat like in the kernel
-            smem = np.full(2 * 9 * ws + 2 * SLOTS * w + va, 1.0, dtype=src.dtype)
-            stage0, ring0 = 0, 2 * 9 * ws
+            # shared memory starts as ones (finite, positive): [stage | ring 0 | ring 1], flat like in the kernel; a ring slot is
+            # v pad rows + the w rows of the threads + v pad rows (wp rows), ring0 = the first thread row of slot 0
+            wp = w + 2 * v
+            smem = np.full(2 * 9 * ws + 2 * SLOTS * wp, 1.0, dtype=src.dtype)
+            stage0, ring0 = 0, 2 * 9 * ws + v
             held = {}     # (ring, slot index) -> column it holds
             pending = {}  # stage -> raw column in flight
             x_first = xs - 2
@@ -107,6 +110,8 @@ def emulate_ws(o, collide, src, nx, ny, ntc, v, seg_cols, x_begin=0, x_end=None,
                 pending[s] = xl
                 issued[0] += 1
 
+            reads = set()  # shared-memory addresses read in the current iteration, by any thread (halo threads included)
+
             def pull(base_of):
                 """f[q, W]: rows t V + vv of population q from flat address base_of(q) + t V + vv - cy (always inside smem)"""
                 f = np.empty((9, w), dtype=src.dtype)
@@ -114,7 +119,14 @@ def emulate_ws(o, collide, src, nx, ny, ntc, v, seg_cols, x_begin=0, x_end=None,
                     idx = base_of(q) + tt[:, None] * v + np.arange(v)[None, :] - CY[q]
                     assert idx.min() >= 0 and idx.max() < smem.size, "a halo thread reads outside the block's shared memory"
                     f[q] = smem[idx].ravel()
+                    reads.update(idx.ravel().tolist())
                 return f
+
+            def store(base, rows, vals):
+                """predicated ring store; no thread may have read these words in this iteration (there is no barrier in between:
+                compute-sanitizer racecheck flags it even when the reader is a halo thread that throws its result away)"""
+                assert reads.isdisjoint((base + rows).tolist()), "a word is read and written in the same iteration"
+                smem[base + rows] = vals
 
             issue_next(0)
             if n_raw > 1:
@@ -128,6 +140,7 @@ def emulate_ws(o, collide, src, nx, ny, ntc, v, seg_cols, x_begin=0, x_end=None,
                 l1, l2, l3 = k < n_raw, xs + 1 <= j <= xe + 2, j >= xs + 4
                 assert l1 or l2 or l3
                 # ---- loads of the iteration (all before any store of it: the levels are independent)
+                reads.clear()
                 n1 = n2 = n3 = None
                 if l1:
                     assert pending.pop(k & 1) == j, "wrong raw column in the stage"
@@ -135,11 +148,11 @@ def emulate_ws(o, collide, src, nx, ny, ntc, v, seg_cols, x_begin=0, x_end=None,
                 if l2:
                     for q in range(9):
                         assert held[(0, rslot(q))] == j - 2 - CX[q], "ring 0 slot does not hold the column level 2 pulls"
-                    n2 = pull(lambda q: ring0 + rslot(q) * w)
+                    n2 = pull(lambda q: ring0 + rslot(q) * wp)
                 if l3:
                     for q in range(9):
                         assert held[(1, rslot(q))] == j - 4 - CX[q], "ring 1 slot does not hold the column level 3 pulls"
-                    n3 = pull(lambda q: ring0 + (SLOTS + rslot(q)) * w)
+                    n3 = pull(lambda q: ring0 + (SLOTS + rslot(q)) * wp)
                 # the producer refills the stage once every consumer has read it
                 if k + 2 < n_raw:
                     issue_next(k & 1)
@@ -148,13 +161,13 @@ def emulate_ws(o, collide, src, nx, ny, ntc, v, seg_cols, x_begin=0, x_end=None,
                     n1 = collide_rows(n1)
                     rows = rows_of(a1)
                     for q in range(9):
-                        smem[ring0 + wslot(q) * w + rows] = n1[q, rows]
+                        store(ring0 + wslot(q) * wp, rows, n1[q, rows])
                         held[(0, wslot(q))] = j
                 if l2:
                     n2 = collide_rows(n2)
                     rows = rows_of(a2)
                     for q in range(9):
-                        smem[ring0 + (SLOTS + wslot(q)) * w + rows] = n2[q, rows]
+                        store(ring0 + (SLOTS + wslot(q)) * wp, rows, n2[q, rows])
                         held[(1, wslot(q))] = j - 2
                     if dual and xs <= j - 2 < xe:
                         rows, ylog = rows_of(a3), (yl[a3][:, None] + np.arange(v)[None, :]).ravel()
