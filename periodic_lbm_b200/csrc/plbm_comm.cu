@@ -284,7 +284,8 @@ static int p2p_setup(Grid& g)
     c->triples_level = level - 1;
     // a call may close with a triple that stores the states after its second and third step (Grid::spare) only if every rank has
     // the third buffer: the ranks must issue the same launches
-    int dual = c->p2p && c->triples_level >= 1 && lbm_multi_shape_is_default() && lbm_spare(g) ? 1 : 0;
+    const bool triples_here = c->triples_level >= 1 || (c->triples_level == 0 && lbm_triples_forced());  // what lbm_triples_wanted says
+    int dual = c->p2p && triples_here && lbm_multi_shape_is_default() && lbm_spare(g) ? 1 : 0;
     if ((rc = agree_min(g, &dual))) return rc;
     c->dual_ok = dual != 0;
     if (!c->dual_ok && g.spare) {

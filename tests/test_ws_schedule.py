@@ -218,6 +218,20 @@ def test_second_output_is_the_state_after_two_steps():
     assert np.array_equal(mid[:, :, :ny], reference(o, collide, f0, nx, ny, 2)[:, :, :ny])
 
 
+@pytest.mark.parametrize("nx,x0,x1", [(8, 3, 5), (7, 3, 4), (12, 3, 9), (30, 3, 27)])
+def test_short_interior_ranges(nx, x0, x1):
+    """thin slabs: the interior between the two three-line boundaries is a column or two -- ramp iterations only"""
+    o = Oracle("f64")
+    p = o.set_properties(0.02, 1.0, 0.25)
+    ny = 24
+    f0 = random_state(o, nx, ny)
+    collide = collisions(o, p)["rr"]
+    want3, want2 = reference(o, collide, f0, nx, ny, 3), reference(o, collide, f0, nx, ny, 2)
+    got, mid = emulate_ws(o, collide, f0, nx, ny, 16, 1, 8, x0, x1, dual=True)
+    assert np.array_equal(got[:, x0:x1, :ny], want3[:, x0:x1, :ny]) and np.array_equal(mid[:, x0:x1, :ny], want2[:, x0:x1, :ny])
+    assert np.isnan(got[:, :x0, :ny]).all() and np.isnan(got[:, x1:, :ny]).all() and np.isnan(mid[:, :x0, :ny]).all()
+
+
 def test_interior_range_of_a_slab():
     """the interior launch of a slab (columns [3, nx - 3)) leaves the boundary columns alone and equals the whole-grid result there"""
     o = Oracle("f64")
