@@ -191,3 +191,48 @@ def test_launch_schedule_with_a_closing_dual_triple():
     assert launch_schedule(20, True, True, True) == [3, 3, 3, 3, 3, 2, 3]
     assert launch_schedule(20, True, True, False) == [3, 3, 3, 3, 3, 2, 2, 1]
     assert launch_schedule(7, True, False, True) == launch_schedule(7, True, False, False)  # dual needs triples
+
+
+def test_python_schedule_mirror_equals_the_library_inline(tmp_path):
+    """csrc/plbm_internal.h lbm_next_launch (what step_lbm_t and the slab schedule call) against periodic_lbm_b200/slab.py
+    launch_schedule, for every combination of (triples, pairs, dual) and calls of 1 ... 64 steps: the header's inline function is
+    compiled into a host-only program (nvcc builds it here without a GPU; nothing of it touches the CUDA runtime)."""
+    import shutil
+    import subprocess
+
+    from periodic_lbm_b200.slab import launch_schedule
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sched.cu"
+    src.write_text('#include <cstdio>\n#include "plbm_internal.h"\n'
+                   "int main() {\n"
+                   "  for (int flags = 0; flags < 8; ++flags)\n"
+                   "    for (int k = 1; k <= 64; ++k) {\n"
+                   '      std::printf("%d %d:", flags, k);\n'
+                   "      for (int s = 0; s < k;) {\n"
+                   "        plbm::LbmLaunch L = plbm::lbm_next_launch(k - s, flags & 1, flags & 2, flags & 4);\n"
+                   '        std::printf(" %d%s", L.depth, L.dual ? "d" : "");\n'
+                   "        s += L.depth;\n"
+                   "      }\n"
+                   '      std::printf("\\n");\n'
+                   "    }\n"
+                   "  return 0;\n}\n")
+    exe = tmp_path / "sched"
+    r = subprocess.run([nvcc, "-std=c++17", "-I", os.path.join(root, "periodic_lbm_b200", "csrc"), "-o", str(exe), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == 8 * 64
+    for line in out:
+        head, seq = line.split(":")
+        flags, k = (int(x) for x in head.split())
+        triples, pairs, dual = bool(flags & 1), bool(flags & 2), bool(flags & 4)
+        got = seq.split()
+        want = launch_schedule(k, pairs=pairs, triples=triples, dual=dual)
+        assert [int(x.rstrip("d")) for x in got] == want, (flags, k, got, want)
+        # the dual flag: only on the closing triple of a schedule with a third buffer, and only when three steps are left
+        assert [x.endswith("d") for x in got] == [dual and triples and n == 3 and i == len(want) - 1 and sum(want[:i]) == k - 3
+                                                  for i, n in enumerate(want)], (flags, k, got)

@@ -21,10 +21,11 @@ BASE = {3: 0, 6: 1, 7: 2, 0: 3, 2: 5, 4: 7, 1: 9, 5: 12, 8: 15}
 SLOTS = 18
 
 
-def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=None, va=None, halo_lo=None, halo_hi=None):
+def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=None, va=None, halo_lo=None, halo_hi=None, mid=None):
     """One launch of k_lbmn_bulk<NSTEP = nstep, NT = nt, V = v> over columns [x_begin, x_end).  va = rows per 16 bytes (the
     alignment unit of the bulk copies; va = 2 v is the "wide" shape: half a 16-byte vector per thread).  halo_lo / halo_hi: the
-    ring neighbours' three nearest lines in the order of csrc/plbm_internal.h ([3][9][ld]: lines -2, -1, -3 / nx, nx+1, nx+2)."""
+    ring neighbours' three nearest lines in the order of csrc/plbm_internal.h ([3][9][ld]: lines -2, -1, -3 / nx, nx+1, nx+2).
+    mid (the DUAL instances, a call's closing launch): an array that receives the state after step nstep - 1 as well."""
     x_end = nx if x_end is None else x_end
     va = v if va is None else va
     dst = np.full_like(src, np.nan)
@@ -149,6 +150,13 @@ def emulate(o, collide, src, nx, ny, nstep, nt, v, seg_cols, x_begin=0, x_end=No
                         else:
                             for q in range(9):
                                 ring[level - 1, BASE[q] + wslot(q), rows] = f[q, rows]
+                            if mid is not None and level == nstep - 1 and xs <= x + 1 < xe:  # column x + 1, the strip's own rows
+                                own = active(nstep)
+                                rows_own = (tt[own][:, None] * v + np.arange(v)[None, :]).ravel()
+                                ylog = (yl[own][:, None] + np.arange(v)[None, :]).ravel()
+                                for q in range(9):
+                                    assert np.isnan(mid[q, x + 1, ylog]).all(), "a node of the second output written twice"
+                                    mid[q, x + 1, ylog] = f[q, rows_own]
                 w2 ^= 1
                 w3 = 0 if w3 == 2 else w3 + 1
             assert not pending, "a bulk copy was still in flight when the block ended"
@@ -229,6 +237,32 @@ def test_three_step_schedule_of_a_slab(nxl):
         assert np.isnan(got[:, x0:x1, :ny]).all()
         got[:, x0:x1] = part[:, x0:x1]
     assert np.array_equal(got[:, :, :ny], want[:, :, :ny])
+
+
+@pytest.mark.parametrize("nxl", [6, 12])
+def test_dual_output_of_the_closing_triple_on_a_slab(nxl):
+    """k_lbmn_bulk<HALO, DUAL>, the boundary launches of a call's closing triple under slabs (and the whole-slab launch of a slab of
+    six lines): besides the state after step 3 they store the state after step 2 -- lattice `inew` of the reference -- for exactly
+    the columns and rows they own."""
+    o = Oracle("f64")
+    p = o.set_properties(0.02, 1.0, 0.25)
+    ny = 24
+    nxg = 3 * nxl
+    f0 = random_state(o, nxg, ny)
+    collide = collisions(o, p)["bgk"]
+    want3, want2 = reference(o, collide, f0, nxg, ny, 3)[:, nxl:2 * nxl], reference(o, collide, f0, nxg, ny, 2)[:, nxl:2 * nxl]
+    slab = np.ascontiguousarray(f0[:, nxl:2 * nxl])
+    halo_lo = np.stack([f0[:, nxl - 2], f0[:, nxl - 1], f0[:, nxl - 3]])
+    halo_hi = np.stack([f0[:, 2 * nxl], f0[:, 2 * nxl + 1], f0[:, 2 * nxl + 2]])
+    got, mid = np.full_like(slab, np.nan), np.full_like(slab, np.nan)
+    ranges = ((0, nxl),) if nxl <= 6 else ((0, 3), (nxl - 3, nxl))
+    for x0, x1 in ranges:
+        part = emulate(o, collide, slab, nxl, ny, 3, 12, 1, 64, x0, x1, va=2, halo_lo=halo_lo, halo_hi=halo_hi, mid=mid)
+        got[:, x0:x1] = part[:, x0:x1]
+    for x0, x1 in ranges:
+        assert np.array_equal(got[:, x0:x1, :ny], want3[:, x0:x1, :ny]) and np.array_equal(mid[:, x0:x1, :ny], want2[:, x0:x1, :ny])
+    if nxl > 6:
+        assert np.isnan(mid[:, 3:nxl - 3, :ny]).all()  # the interior is the other kernel's (tests/test_ws_schedule.py)
 
 
 def test_schedule_on_a_line_sub_range():
