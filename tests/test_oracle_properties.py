@@ -185,3 +185,30 @@ def test_heun_finite_volume_plugin_keeps_a_uniform_state():
     f0 = _simfvm_run(o, nx, ny, p, u, 0.4, 1.5, 0)
     f3 = _simfvm_run(o, nx, ny, p, u, 0.4, 1.5, 3)
     assert np.abs(f3 - f0).max() < 1e-16
+
+
+@pytest.mark.parametrize("coll", ["bgk", "trt", "rr"])
+def test_lbm_taylor_green_decay_matches_the_analytic_solution(coll):
+    """lbm_stream + collide_bgk / collide_trt / collide_rr are the rows of SURVEY 8(c) that no golden file of the reference pins.
+    A pin that needs no restatement at all: the Taylor-Green vortex of app/main_taylor_green.f90 decays as umax exp(-t / td) with
+    td = 1 / (nu (kx^2 + ky^2)) and nu = csqr (tau - dt / 2) -- the streaming directions, the velocity set, the relaxation rates of
+    set_properties and all three collisions must be right for the ORACLE to follow it.  48^2, fp64, one decay half-life."""
+    from oracle.oracle import OracleGrid, taylor_green_setup, taylor_green_steps_to_tmax
+
+    n = 48
+    og = OracleGrid(n, n, "f64")
+    s = taylor_green_setup(og.o, n, dt=1.0)
+    og.set_properties(s["nu"], s["dt"], magic=0.25)
+    pr, ux, uy = og.o.taylor_green_eval(n, n, s["kx"], s["ky"], s["umax"], s["td"], 0.0)
+    og.rho, og.ux, og.uy = pr / og.props["csqr"] + 1.0, ux, uy
+    og.set_pdf_to_equilibrium()
+    steps, t = taylor_green_steps_to_tmax(og.o, s)
+    og.run(Oracle.SCHEME_LBM, {"bgk": Oracle.BGK, "trt": Oracle.TRT, "rr": Oracle.RR}[coll], steps)
+    rho, u, v = og.update_macros(lagged=False)
+    _, uxa, uya = og.o.taylor_green_eval(n, n, s["kx"], s["ky"], s["umax"], s["td"], t)
+    speed, want = np.hypot(u, v).max(), np.hypot(uxa, uya).max()  # both sampled at the cell centres
+    assert abs(want / float(s["umax"]) - 0.5) < 5e-3  # one half-life: exp(-t / td) = 1/2 up to the last step and the sampling
+    assert abs(speed - want) / want < 5e-3, (coll, speed, want)
+    assert og.o.l2_norm(u, v, uxa, uya) < 5e-3  # relative L2 error of the velocity field (second order in 2 pi / n)
+    assert abs(rho.sum() - n * n) / (n * n) < 1e-11  # mass, up to the round-off of 7,299 steps
+    assert abs(u.sum()) < 1e-10 and abs(v.sum()) < 1e-10  # no net momentum
