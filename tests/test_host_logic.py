@@ -60,7 +60,7 @@ def _free_port():
     return port
 
 
-def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
+def _slab_worker(rank, world, port, nxg, ny, steps, coll, out, dual=False):
     """One rank of the ring: owns a slab, exchanges the halo message (three lines of all nine populations per
     direction) with gloo, and advances its slab with the ORACLE kernels on a halo-extended copy -- one step,
     a fused pair or a fused triple per launch, in the library's own schedule.  This exercises exactly the protocol
@@ -85,7 +85,9 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
     collide = {0: lambda a: o.collide_bgk(a, ny, 1.7), 2: lambda a: o.collide_rr(a, ny, 1.7)}[coll]
     can = torch.tensor([int(nxl >= 4), int(nxl >= 2 * H)])
     dist.all_reduce(can, op=dist.ReduceOp.MIN)  # every rank must issue the same sequence of launches
-    for nfused in launch_schedule(steps, pairs=bool(can[0].item()), triples=bool(can[1].item())):
+    sched = launch_schedule(steps, pairs=bool(can[0].item()), triples=bool(can[1].item()), dual=dual)
+    f_prev = None  # lattice `inew` of the reference after the call: state steps - 1
+    for launch, nfused in enumerate(sched):
         send_lo = torch.from_numpy(f[:, :H].copy())    # my first three lines -> rank lo (its lines nx, nx+1, nx+2)
         send_hi = torch.from_numpy(f[:, -H:].copy())   # my last three lines  -> rank hi (its lines -3, -2, -1)
         halo_lo, halo_hi = torch.empty_like(send_hi), torch.empty_like(send_lo)
@@ -99,14 +101,18 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
         ext[:, -H:] = halo_hi.numpy()
         # every step on the extended slab pollutes one more ghost line from each end (its periodic wrap is
         # wrong there): three ghost lines per side keep the owned lines exact for up to three steps
-        for _ in range(nfused):
+        for k in range(nfused):
             dst = np.zeros_like(ext)
             o.lbm_stream(ext, dst, ny)
             collide(dst)
             ext = dst
+            if launch == len(sched) - 1 and k == nfused - 2:
+                # the closing triple of a ring whose ranks all hold a third lattice buffer also stores the state after its
+                # second step: two ghost lines per side are polluted by then, the owned lines are exact
+                f_prev = np.ascontiguousarray(ext[:, H:-H])
         f = np.ascontiguousarray(ext[:, H:-H])
     gathered = [None] * world
-    dist.all_gather_object(gathered, (sl.x_offset, f))
+    dist.all_gather_object(gathered, (sl.x_offset, f, f_prev))
     if rank == 0:
         full = np.concatenate([g[1] for g in sorted(gathered, key=lambda t: t[0])], axis=1)
         # single-domain oracle
@@ -115,7 +121,11 @@ def _slab_worker(rank, world, port, nxg, ny, steps, coll, out):
             o.lbm_stream(a, b, ny)
             collide(b)
             a, b = b, a
-        out.put(bool(np.array_equal(full[:, :, :ny], a[:, :, :ny])))
+        ok = bool(np.array_equal(full[:, :, :ny], a[:, :, :ny]))
+        if dual and sched[-1] == 3:  # after the last swap `b` holds state steps - 1: what the dual triple leaves in `inew`
+            prev = np.concatenate([g[2] for g in sorted(gathered, key=lambda t: t[0])], axis=1)
+            ok = ok and bool(np.array_equal(prev[:, :, :ny], b[:, :, :ny]))
+        out.put(ok)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -135,6 +145,25 @@ def test_slab_halo_protocol_world_size_n_gloo(world, nxg, ny, coll):
         p_.join(timeout=60)
         assert p_.exitcode == 0
     assert ok, "slab-decomposed run differs from the single-domain run"
+
+
+@pytest.mark.parametrize("world,nxg,ny,coll,steps", [(2, 12, 10, 0, 8), (2, 14, 16, 2, 9), (3, 19, 8, 0, 11), (2, 13, 8, 2, 6)])
+def test_slab_halo_protocol_with_a_closing_dual_triple_gloo(world, nxg, ny, coll, steps):
+    """the same protocol when every rank holds a third lattice buffer: the call closes with a triple that also keeps the state
+    after its second step -- the slabs must hold states `steps` AND `steps - 1` of the single-domain run"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, nxg, ny, steps, coll, q, True)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    ok = q.get(timeout=120)
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert ok, "slab-decomposed run (closing dual triple) differs from the single-domain run"
 
 
 def test_text_writers_use_the_reference_edit_descriptors(tmp_path):
