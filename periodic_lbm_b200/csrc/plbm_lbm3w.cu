@@ -311,16 +311,17 @@ int env_knob3(const char* name, int dflt)
     return e && *e ? atoi(e) : dflt;
 }
 
-template <typename T, int MODEL, bool DUAL, int NTC = 128>
+template <typename T, int MODEL, bool DUAL>
 int launch_3w(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int x_end, const CollideParams<T>& cp, cudaStream_t s)
 {
+    constexpr int NTC = 128;  // consumer threads
     constexpr int VA = 16 / (int)sizeof(T);
     constexpr int V = VA / 2;  // one row (fp64) / two rows (fp32) per thread, like the default shape of k_lbmn_bulk
     constexpr int HS = (2 * V + 1 + VA - 1) / VA * VA;
     constexpr int W = NTC * V, WS = W + 2 * (HS - 2 * V), WP = W + 2 * V;
     constexpr size_t smem = ((size_t)2 * 9 * WS + 2 * RS_SLOTS * WP) * sizeof(T) + 16;
     constexpr int MINB = (int)((size_t)(228 * 1024) / (smem + 1024));
-    static_assert(MINB == (NTC == 128 ? 3 : (NTC == 96 ? 4 : 2)), "three blocks of five warps per SM (NTC = 128)");
+    static_assert(MINB == 3, "three blocks of five warps per SM");
     if (x_end <= x_begin) return PLBM_OK;
     auto kern = k_lbm3_ws<T, MODEL, V, NTC, MINB, DUAL>;
     static bool configured[64] = {false};
@@ -366,15 +367,8 @@ int launch_3w(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int 
 template <typename T, bool DUAL>
 int dispatch_3w(const Grid& g, const T* src, T* dst, T* dst_mid, int x_begin, int x_end, int model, const CollideParams<T>& cp, cudaStream_t s)
 {
-    // block shape (measurement knob): 96 consumer threads x 4 blocks per SM, 128 x 3 (default), 192 x 2; bgk / trt / rr only
-    static const int ntc = env_knob3("PLBM_WS_NTC", 128);
-    if (ntc == 96 || ntc == 192) {
-        switch (model) {
-        case M_BGK: return ntc == 96 ? launch_3w<T, M_BGK, DUAL, 96>(g, src, dst, dst_mid, x_begin, x_end, cp, s) : launch_3w<T, M_BGK, DUAL, 192>(g, src, dst, dst_mid, x_begin, x_end, cp, s);
-        case M_TRT: return ntc == 96 ? launch_3w<T, M_TRT, DUAL, 96>(g, src, dst, dst_mid, x_begin, x_end, cp, s) : launch_3w<T, M_TRT, DUAL, 192>(g, src, dst, dst_mid, x_begin, x_end, cp, s);
-        case M_RR: return ntc == 96 ? launch_3w<T, M_RR, DUAL, 96>(g, src, dst, dst_mid, x_begin, x_end, cp, s) : launch_3w<T, M_RR, DUAL, 192>(g, src, dst, dst_mid, x_begin, x_end, cp, s);
-        }
-    }
+    // (block shapes measured and dropped, r02r, bench slab BGK fp64: 96 consumer threads x 4 blocks per SM 102.8 GLUPS, 192 x 2 89.1,
+    // against 103.5 for 128 x 3)
     switch (model) {
     case M_BGK: return launch_3w<T, M_BGK, DUAL>(g, src, dst, dst_mid, x_begin, x_end, cp, s);
     case M_TRT: return launch_3w<T, M_TRT, DUAL>(g, src, dst, dst_mid, x_begin, x_end, cp, s);

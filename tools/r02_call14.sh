@@ -1,5 +1,6 @@
 #!/bin/bash
 # GPU call (one B200): shape of k_lbm3_ws (segment length, consumer threads per block), e2e with / without the third lattice buffer
+# (historical: PLBM_WS_NTC selected 96 / 192 consumer threads per block; both were slower and the instantiations were removed afterwards)
 # (alternating processes, median of three cycles), compute-sanitizer over the new kernel and the closing dual triple.
 R=${1:-r02r}
 cd "${GRAFT_REPO_ROOT:-.}"
