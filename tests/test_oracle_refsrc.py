@@ -1,0 +1,156 @@
+"""The C oracle against the reference's OWN SOURCE, bit for bit.
+
+`tests/golden/refsrc_{f64,f32}.npz` hold inputs and outputs of the reference's Fortran kernels and host procedures, produced by
+EXECUTING the source text of `/root/reference/src/*.f90|F90` statement by statement (oracle/f90_exec.py, a small interpreter with
+Fortran's typing rules on IEEE scalars; oracle/make_refsrc_golden.py is the generating script).  No Fortran compiler exists in
+this image, so this is as close as the oracle can get to "outputs of the reference itself run here": no human transcription sits
+between the Fortran statements and the numbers.  It pins the rows that the reference's two golden files cannot reach:
+lbm_stream, collide_trt, collide_rr, the -DSPLIT collisions, collide_bgk_improved, the finite-difference streaming schemes,
+vorticity_2nd / 4th, update_macros, set_properties, and every fp32 result -- and re-pins Bardow FVM and DUGKS at kernel level.
+
+Every comparison is np.array_equal.  Where /root/reference exists the fixtures are regenerated and must equal the committed ones."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, OracleGrid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRECS = ["f64", "f32"]
+
+
+@pytest.fixture(scope="module", params=PRECS)
+def ref(request):
+    prec = request.param
+    with np.load(os.path.join(ROOT, "tests", "golden", f"refsrc_{prec}.npz")) as z:
+        data = {k: z[k] for k in z.files}
+    return prec, data, Oracle(prec)
+
+
+def poisoned(o, f, ny):
+    """the oracle's own allocation with the stored rows: the padding rows stay NaN, so a kernel that touched them would show"""
+    g = o.alloc_f(f.shape[1], ny)
+    g[:, :, :ny] = f[:, :, :ny]
+    return g
+
+
+def same(a, b, ny):
+    return np.array_equal(a[..., :ny], b[..., :ny])
+
+
+def test_lbm_kernels_on_a_non_square_grid(ref):
+    prec, d, o = ref
+    nx, ny = 7, 5
+    omega, magic, _ = d["params"]
+    f0 = poisoned(o, d["f0"], ny)
+    fs = o.alloc_f(nx, ny)
+    o.lbm_stream(f0, fs, ny)
+    assert same(fs, d["stream"], ny), "lbm_stream_kernel (src/periodic_lbm.f90:45-127)"
+    for name, call in (("bgk", lambda f: o.collide_bgk(f, ny, omega)), ("bgk_cache", lambda f: o.kernel_bgk(f, ny, omega)),
+                       ("trt", lambda f: o.collide_trt(f, ny, omega, magic)), ("trt_split", lambda f: o.collide_trt_split(f, ny, omega, magic)),
+                       ("rr", lambda f: o.collide_rr(f, ny, omega))):
+        f = fs.copy()
+        call(f)
+        assert same(f, d[name], ny), name
+    f = f0.copy()
+    o.kernel_bgk(f, ny, omega)
+    assert same(f, d["dugks_kernel_bgk"], ny), "kernel_bgk (src/periodic_dugks.F90:80-169)"
+    lam = o.lambda_d(omega, magic)
+    assert lam == d["lambda_d"][0] and o.magic_number(omega, lam) == d["lambda_d"][1]
+    rho, ux, uy = o.update_macros(fs, ny)
+    assert np.array_equal(np.stack([rho, ux, uy]), d["macros"]), "update_macros_kernel (src/fvm_bardow.F90:356-388)"
+    assert np.array_equal(o.vorticity(ux, uy, 2), d["vorticity2"]) and np.array_equal(o.vorticity(ux, uy, 4), d["vorticity4"])
+
+
+def test_improved_bgk(ref):
+    prec, d, o = ref
+    f = poisoned(o, d["f16"], 16)
+    o.collide_bgk_improved(f, 16, d["params"][0])
+    assert same(f, d["bgk_improved"], 16), "bgk_improved_kernel (src/collision_bgk_improved.f90:24-107)"
+
+
+def test_finite_volume_and_finite_difference_kernels(ref):
+    prec, d, o = ref
+    n = 6
+    dt = d["params"][2]
+    fq = poisoned(o, d["fq"], n)
+    fnew = o.alloc_f(n, n)
+    o.stream_fvm_bardow(fq, fnew, n, dt)
+    assert same(fnew, d["fvm_bardow"], n), "fvm_bardow_kernel (src/fvm_bardow.F90:410-509)"
+    for stencil in ("default", "wls", "wls_gauss_v1", "wls_gauss_v2", "iso"):
+        fnew = o.alloc_f(n, n)
+        o.stream_fdm_bardow(fq, fnew, n, dt, stencil)
+        assert same(fnew, d[f"fdm_bardow_{stencil}"], n), f"fdm_bardow_kernel, {stencil} build (src/fvm_bardow.F90:526-685)"
+    fnew = o.alloc_f(n, n)
+    o.stream_fdm_sofonea(fq, fnew, n, dt)
+    assert same(fnew, d["fdm_sofonea"], n), "fdm_sofonea_kernel (src/fvm_bardow.F90:703-893)"
+
+
+@pytest.mark.parametrize("dugks", [True, False])
+def test_dugks_stream_kernel(ref, dugks):
+    prec, d, o = ref
+    n = 6
+    fq, fp = poisoned(o, d["fq"], n), poisoned(o, d["dugks_fp_in"], n)
+    o.dugks_stream(fq, fp, n, d["dugks_tau"][0], d["params"][2], dugks)
+    assert same(fp, d["dugks_stream_on" if dugks else "dugks_stream_off"], n), "kernel_stream + update_ew / update_ns (src/periodic_dugks.F90:190-434)"
+
+
+RUNS = {"run_lbm_bgk": (Oracle.SCHEME_LBM, Oracle.BGK), "run_lbm_trt": (Oracle.SCHEME_LBM, Oracle.TRT), "run_lbm_rr": (Oracle.SCHEME_LBM, Oracle.RR),
+        "run_fvm_bgk": (Oracle.SCHEME_FVM_BARDOW, Oracle.BGK), "run_dugks": (Oracle.SCHEME_DUGKS, Oracle.BGK)}
+
+
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_whole_procedures_on_a_lattice_grid(ref, name):
+    """set_properties -> set_pdf_to_equilibrium -> N x perform_*step -> update_macros, as the reference's host procedures ran them in
+    the interpreter (procedure pointers bound like app/main_taylor_green.f90:39-40 binds them) against OracleGrid."""
+    prec, d, o = ref
+    scheme, coll = RUNS[name]
+    nsteps, nu, dt, magic = d[f"{name}.args"]
+    og = OracleGrid(6, 6, prec)
+    og.rho, og.ux, og.uy = (np.ascontiguousarray(a) for a in d[f"{name}.init"])
+    p = og.set_properties(nu, dt, magic)
+    assert np.array_equal(np.array([p["tau"], p["omega"], p["trt_magic"], p["csqr"]], dtype=o.dtype), d[f"{name}.props"]), "set_properties"
+    og.set_pdf_to_equilibrium()
+    og.run(scheme, coll, int(nsteps))
+    assert [og.iold, og.inew] == list(d[f"{name}.idx"][:2])
+    lat = d[f"{name}.lattices"]
+    assert same(og.lattice(1), lat[0], 6) and same(og.lattice(2), lat[1], 6), "lattices after the run"
+    rho, ux, uy = og.update_macros(lagged=True)
+    assert np.array_equal(np.stack([rho, ux, uy]), d[f"{name}.macros"]), "update_macros reads lattice inew (SURVEY F3)"
+
+
+def test_perform_triple_step(ref):
+    """perform_triple_step (src/fvm_bardow.F90:322-340) with lbm_stream + collide_bgk on three lattices: the host logic composed from
+    the oracle's kernels like tests/test_gpu_parity.py::test_perform_triple_step does."""
+    prec, d, o = ref
+    nsteps, nu, dt, magic = d["run_triple_lbm_bgk.args"]
+    n = 6
+    p = o.set_properties(nu, dt, magic)
+    f = [o.alloc_f(n, n) for _ in range(3)]
+    inew, iold, imid = 1, 2, 3
+    init = d["run_triple_lbm_bgk.init"]
+    o.set_pdf_to_equilibrium(*(np.ascontiguousarray(a) for a in init), f[iold - 1])
+    for _ in range(int(nsteps)):
+        o.lbm_stream(f[iold - 1], f[inew - 1], n)
+        f[iold - 1][...] = f[inew - 1]
+        o.collide_bgk(f[inew - 1], n, p["omega"])
+        iold, inew, imid = inew, imid, iold
+    assert [iold, inew, imid] == list(d["run_triple_lbm_bgk.idx"])
+    lat = d["run_triple_lbm_bgk.lattices"]
+    for k in (iold, imid):  # lattice inew is scratch at this point (never written in the first steps: zeros there, NaN here)
+        assert same(f[k - 1], lat[k - 1], n), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the reference's sources are not on this machine")
+@pytest.mark.parametrize("prec", PRECS)
+def test_committed_fixtures_are_what_the_reference_source_produces_today(prec):
+    sys.path.insert(0, os.path.join(ROOT))
+    from oracle.make_refsrc_golden import generate
+
+    fresh = generate(prec)
+    with np.load(os.path.join(ROOT, "tests", "golden", f"refsrc_{prec}.npz")) as z:
+        assert sorted(z.files) == sorted(fresh)
+        for k in z.files:
+            assert np.array_equal(z[k], fresh[k], equal_nan=True), k
