@@ -372,7 +372,10 @@ class Interp:
     def load(self, filename):
         path = os.path.join(self.src, filename)
         with open(path) as fh:
-            stmts = preprocess(fh.read(), self.macros)
+            return self.load_text(fh.read())
+
+    def load_text(self, text):
+        stmts = preprocess(text, self.macros)
         mod, stack, skip_until = None, [], None
         for st in stmts:
             if skip_until:
@@ -710,18 +713,18 @@ class Interp:
             fr["host"] = h
         if fr["host"] is None and proc.parent is not None:
             fr["host"] = {"vars": {}, "proc": proc.parent, "host": None}
-        bound = {}
+        bound, byref = {}, []
         if actuals is not None:
             for n, v in zip(proc.args, actuals):
                 bound[n] = v
         else:
             pos = 0
             for a in args:
-                if a[0] == "kw":
-                    bound[a[1]] = self.actual(a[2], caller)
-                else:
-                    bound[proc.args[pos]] = self.actual(a, caller)
-                    pos += 1
+                name, node = (a[1], a[2]) if a[0] == "kw" else (proc.args[pos], a)
+                pos += a[0] != "kw"
+                bound[name] = self.actual(node, caller)
+                if node[0] == "var":
+                    byref.append((name, node))  # a variable: argument association, a scalar dummy writes through
         # dummies: scalars first (array bounds may depend on them)
         for n in proc.args:
             d = proc.decls.get(n)
@@ -734,7 +737,7 @@ class Interp:
                 fr["vars"][n] = bound[n]  # a derived-type object
                 continue
             if d.dims is None:
-                fr["vars"][n] = self.convert(bound[n], d)
+                fr["vars"][n] = None if bound[n] is None else self.convert(bound[n], d)  # None: an actual that is not defined yet
         for n in proc.args:
             d = proc.decls.get(n)
             if d is not None and d.dims is not None and n in bound:
@@ -762,6 +765,10 @@ class Interp:
             else:
                 fr["vars"][n] = None
         self.exec_block(proc.body, 0, len(proc.body), fr)
+        for n, node in byref:
+            v = fr["vars"].get(n)
+            if v is not None and v is not ABSENT and not isinstance(v, (FArray, dict)):
+                self.assign(node, v, caller)
         if proc.kind == "function":
             v = fr["vars"][proc.result]
             return v.a.copy() if isinstance(v, FArray) else v
@@ -771,7 +778,7 @@ class Interp:
         if a[0] == "paren":
             return self.eval(a, fr)
         if a[0] == "var":
-            return self.lookup(fr, a[1])
+            return self.lookup(fr, a[1])  # may be None: a variable that the callee defines (intent(out))
         if a[0] == "ref":
             try:
                 v = self.lookup(fr, a[1])

@@ -15,9 +15,13 @@
  * which cover equilibrium, set_pdf_to_equilibrium, stream_fvm_bardow,
  * collide_bgk, kernel_bgk, dugks_collide, dugks_stream (+update_ew/ns),
  * update_macros (lagged), the Taylor-Green case and the L2 norm.
- * lbm_stream, collide_trt, collide_rr, vorticity_*, the vortex case and every
- * fp32 result are NOT pinned by any reference artefact ("parity unpinned" for
- * those: restatement + physics checks only).
+ * lbm_stream, collide_trt, collide_rr, vorticity_*, the finite-difference schemes, the
+ * -DSPLIT collisions and every fp32 result are pinned by no reference ARTEFACT; they are
+ * pinned on the reference's SOURCE: oracle/f90_exec.py executes the Fortran statements of
+ * /root/reference/src one by one, and this oracle reproduces the outputs bit for bit in
+ * fp64 and fp32 (tests/golden/refsrc_*.npz, tests/test_oracle_refsrc.py).  The reference
+ * binary itself has never run here; the Taylor-Green / vortex field evaluations
+ * (transcendental functions) rest on the restatement and the golden files only.
  *
  * Build: see oracle/Makefile (-O2 -ffp-contract=off, OpenMP optional).
  */
