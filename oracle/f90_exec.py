@@ -38,18 +38,36 @@ def preprocess(text, macros):
         line = raw.rstrip()
         s = line.strip()
         if s.startswith("#"):
+            if re.match(r"#\s*(warning|error|pragma)\b", s):
+                if all(b[0] for b in stack) and re.match(r"#\s*error", s):
+                    raise FortranError(f"live #error: {s}")
+                continue
             m = re.match(r"#\s*(if|ifdef|ifndef|else|endif|elif|define|include)\b\s*(.*)", s)
             if not m:
                 raise FortranError(f"preprocessor line not understood: {s}")
             kw, rest = m.group(1), m.group(2).strip()
             def cond(rest):
-                if not re.fullmatch(r"!?\s*(defined\s*\(\s*\w+\s*\)|\w+)", rest):
-                    raise FortranError(f"preprocessor condition not understood: {s}")
-                name = re.findall(r"\w+", rest.replace("defined", ""))[0]
-                val = bool(macros.get(name, 0))
-                return (not val) if rest.startswith("!") else val
+                """#if expressions of the reference: names, integers, defined(X), !, &&, ||, parentheses"""
+                toks = re.findall(r"defined\s*\(\s*\w+\s*\)|defined\s+\w+|\w+|\|\||&&|!|\(|\)|\S", rest)
+                py = []
+                for t_ in toks:
+                    if t_.startswith("defined"):
+                        py.append(str(bool(macros.get(re.findall(r"\w+", t_)[1], 0))))
+                    elif t_ in ("||", "&&", "!", "(", ")"):
+                        py.append({"||": "or", "&&": "and", "!": "not"}.get(t_, t_))
+                    elif re.fullmatch(r"\d+", t_):
+                        py.append(str(int(t_) != 0))
+                    elif re.fullmatch(r"\w+", t_):
+                        py.append(str(bool(macros.get(t_, 0))))
+                    else:
+                        raise FortranError(f"preprocessor condition not understood: {s}")
+                expr = " ".join(py)
+                return bool(eval(expr, {"__builtins__": {}}, {}))
 
-            if kw in ("if", "ifdef"):
+            if kw == "ifdef":
+                v = bool(macros.get(rest, 0))
+                stack.append([v, v])
+            elif kw == "if":
                 v = cond(rest)
                 stack.append([v, v])  # [this branch is live, some branch of the chain has been live]
             elif kw == "ifndef":
@@ -62,6 +80,11 @@ def preprocess(text, macros):
                 stack[-1] = [not stack[-1][1], True]
             elif kw == "endif":
                 stack.pop()
+            elif kw == "define" and all(b[0] for b in stack):
+                mm = re.match(r"(\w+)\s*(\S*)", rest)
+                macros[mm.group(1)] = int(mm.group(2)) if re.fullmatch(r"-?\d+", mm.group(2) or "") else 1
+            elif kw == "define":
+                pass
             else:
                 raise FortranError(f"preprocessor directive not supported: {s}")
             continue
@@ -352,7 +375,7 @@ class Decl:
 
 class Module:
     def __init__(self, name):
-        self.name, self.decls, self.procs, self.uses, self.values = name, {}, {}, [], {}
+        self.name, self.decls, self.procs, self.uses, self.values, self.renames = name, {}, {}, [], {}, {}
 
 
 DECL_RE = re.compile(r"^(integer|real|logical|double precision)\b\s*(\(([^)]*)\))?(.*?)::(.*)$")
@@ -369,6 +392,9 @@ class Interp:
         self.nstmt = 0
 
     # ---- parsing --------------------------------------------------------------------------------------------------
+    def _global(self):
+        return self.modules.setdefault("_global", Module("_global"))
+
     def load(self, filename):
         path = os.path.join(self.src, filename)
         with open(path) as fh:
@@ -405,7 +431,9 @@ class Interp:
                 p = Proc(kind, name, [a.strip() for a in (args or "").split(",") if a.strip()], res or (name if kind == "function" else None), parent, mod)
                 if rtype:
                     p.decls[p.result] = Decl("real" if rtype.startswith("real") else rtype, "wp" if rtype.startswith("real") else None, None, None, st)
-                (parent.contains if parent else mod.procs)[name] = p
+                if parent is None and mod is None:
+                    p.module = self._global()  # an external procedure (the bind(c) wrappers of sim/): parsed, not ours to run
+                (parent.contains if parent else p.module.procs)[name] = p
                 stack.append(p)
                 continue
             if re.match(r"^end\s*(subroutine|function)", st) or (st == "end" and stack):
@@ -414,9 +442,11 @@ class Interp:
             target = stack[-1] if stack else mod
             if target is None:
                 continue  # program units we do not run
-            if re.match(r"^use\s", st):
-                m = re.match(r"^use\s+(\w+)", st)
-                mod.uses.append(m.group(1))
+            if re.match(r"^use\b", st):
+                m = re.match(r"^use\s*(?:,\s*\w+\s*)?(?:::)?\s*(\w+)", st)
+                (mod or self._global()).uses.append(m.group(1))
+                for local, remote in re.findall(r"(\w+)\s*=>\s*(\w+)", st):
+                    (mod or self._global()).renames[local] = remote  # use m, only: local => remote
                 continue
             if SKIP_DECL.match(st):
                 continue
@@ -467,8 +497,7 @@ class Interp:
         m = re.fullmatch(r"(\d+\.\d*|\.\d+|\d+)([ed][+-]?\d+)?(?:_(\w+))?", text)
         mant, expo, kind = m.group(1), m.group(2), m.group(3)
         if "." not in mant and expo is None:
-            if kind:
-                raise FortranError("integer kinds are not supported")
+            # an integer literal; with a kind suffix (`90_wp` in sim/sim_lw6.F90: an INTEGER of kind 8, since wp = 8) still an integer
             return int(mant)
         if expo and expo[0] == "d":
             if kind:
@@ -577,6 +606,7 @@ class Interp:
                 return p.contains[name]
             p = p.parent
         mod = frame["proc"].module
+        name = mod.renames.get(name, name)
         for m in [mod] + [self.modules[u] for u in mod.uses if u in self.modules]:
             if name in m.procs:
                 return m.procs[name]
@@ -672,6 +702,14 @@ class Interp:
             return int(arr.a.size) if len(args) == 1 else int(arr.a.shape[int(self.eval(args[1], fr)) - 1])
         if name == "present":
             return self.lookup(fr, args[0][1]) is not ABSENT
+        if name == "real":  # real(x [, kind]): the kind is a name, not a value
+            kind = None
+            if len(args) > 1:
+                k = args[1][2] if args[1][0] == "kw" else args[1]
+                kind = k[1] if k[0] == "var" else str(self.eval(k, fr))
+            t = self.real_kind(kind)
+            v = self.eval(args[0], fr)
+            return v.astype(t) if isinstance(v, np.ndarray) else t(v)
         vals = [self.eval(a[2] if a[0] == "kw" else a, fr) for a in args]
         if name == "mod":
             a, b = vals
@@ -679,10 +717,6 @@ class Interp:
                 r = abs(a) % abs(b)
                 return r if a >= 0 else -r
             raise FortranError("mod() of reals is not supported")
-        if name == "real":
-            kind = args[1][1] if len(args) > 1 and args[1][0] == "var" else (args[1][2][1] if len(args) > 1 else None)
-            t = self.real_kind(kind)
-            return t(vals[0]) if not isinstance(vals[0], np.ndarray) else vals[0].astype(t)
         if name == "sqrt":
             return np.sqrt(vals[0])
         if name == "abs":
@@ -760,6 +794,9 @@ class Interp:
                 continue  # evaluated on demand
             if d.dims is not None:
                 lo, shape = self.dims_of(d.dims, fr)
+                if lo is None:
+                    fr["vars"][n] = None  # allocatable / pointer: nothing until move_alloc gives it something
+                    continue
                 t = int if d.typ == "integer" else (self.real_kind(d.kind) if d.typ == "real" else bool)
                 fr["vars"][n] = FArray(np.full(shape, np.nan if d.typ == "real" else 0, dtype=t), lo)
             else:
@@ -767,7 +804,10 @@ class Interp:
         self.exec_block(proc.body, 0, len(proc.body), fr)
         for n, node in byref:
             v = fr["vars"].get(n)
-            if v is not None and v is not ABSENT and not isinstance(v, (FArray, dict)):
+            if v is None or v is ABSENT or isinstance(v, (FArray, dict)):
+                continue
+            before = bound.get(n)
+            if before is None or type(before) is not type(v) or before != v:  # the callee defined / changed the dummy
                 self.assign(node, v, caller)
         if proc.kind == "function":
             v = fr["vars"][proc.result]
@@ -832,6 +872,22 @@ class Interp:
             arr.a[arr.index(subs)] = value
             return
         raise FortranError("left-hand side not supported")
+
+    def bind_name(self, name, obj, fr):
+        """make a variable or a component NAME the array object `obj` (move_alloc), as opposed to copying values into it"""
+        if "%" in name:
+            base, *fields = name.split("%")
+            o = self.lookup(fr, base)
+            for fld in fields[:-1]:
+                o = o[fld]
+            o[fields[-1]] = obj
+            return
+        f = fr
+        while f is not None and name not in f["vars"]:
+            f = f["host"]
+        if f is None:
+            raise FortranError(f"move_alloc: {name} is not declared")
+        f["vars"][name] = obj
 
     def exec_block(self, body, i, end, fr):
         """executes body[i:end]; returns 'cycle' / 'exit' / 'return' / None"""
@@ -924,6 +980,19 @@ class Interp:
                 if not callable(fn):
                     raise FortranError(f"{m.group(1)} is not callable")
                 fn()
+                i += 1
+                continue
+            m = re.match(r"^call\s+move_alloc\s*\((.*)\)$", st)
+            if m:
+                e = parse_expr(f"move_alloc({m.group(1)})")
+                kw = {a[1]: a[2] for a in e[2] if a[0] == "kw"}
+                pos = [a for a in e[2] if a[0] != "kw"]
+                src, dst = kw.get("from", pos[0] if pos else None), kw.get("to", pos[1] if len(pos) > 1 else None)
+                obj = self.lookup(fr, src[1])
+                if not isinstance(obj, FArray):
+                    raise FortranError("move_alloc: from is not an allocated array")
+                self.bind_name(dst[1], obj, fr)
+                self.bind_name(src[1], None, fr)
                 i += 1
                 continue
             m = re.match(r"^call\s+(\w+)\s*(\((.*)\))?$", st)

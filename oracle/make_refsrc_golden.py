@@ -20,7 +20,8 @@ What runs, per precision (wp = real64 / real32, i.e. the reference built without
   whole procedures on a lattice_grid object (set_properties, set_pdf_to_equilibrium, N x perform_*step, update_macros), with the
   procedure pointers grid%streaming / grid%collision bound like the drivers bind them
     perform_lbm_step  x  collide_bgk / collide_trt / collide_rr;  perform_step (stream_fvm_bardow + collide_bgk);
-    perform_dugks_step (-DDUGKS);  perform_triple_step (lbm_stream + collide_bgk, three lattices)."""
+    perform_dugks_step (-DDUGKS);  perform_triple_step (lbm_stream + collide_bgk, three lattices).
+  and the plugins of sim/ (generate_sim, refsrc_sim_f64.npz): slbm, lw, lw4, lw6, fvm -- init, N x <plugin>_step, lbm_macros."""
 import os
 import sys
 
@@ -187,6 +188,71 @@ def generate(prec):
     return out
 
 
+SIM_FILES = ["sim.F90", "sim_lw.F90", "sim_lw4.F90", "sim_lw6.F90", "sim_fvm.F90", "sim_slbm.F90"]
+
+
+def generate_sim():
+    """The plugins of sim/ (fp64: `wp => dp`), built as gfortran builds them (-D__GFORTRAN__ branches): the init sequence of
+    <plugin>_init without its allocate statements (lbm_eqinit_fields + the halo fill), then <plugin>_step / slbm_step / fvm_step run
+    as whole procedures on the plugin object (associate, keyword arguments, move_alloc swaps), then lbm_macros.  Arrays in the oracle's
+    layout f[q, y, x] with the halo, fields [y, x]."""
+    it = Interp("f64", {"__GFORTRAN__": 1}, src="/root/reference/sim")
+    for f in SIM_FILES:
+        it.load(f)
+    out = {}
+    nx, ny, steps = 7, 6, 3
+    rng = np.random.default_rng(SEED + 11)
+    p = 1e-3 * rng.standard_normal((ny, nx))
+    u = 0.05 * rng.standard_normal((2, ny, nx))
+    out["p"], out["u"] = p, u
+    out["args"] = np.array([nx, ny, steps, 0.4, 1.4])  # nx, ny, steps, dt of the Lax-Wendroff / Heun plugins, omega
+    dt, omega = 0.4, 1.4
+
+    def arr(h):
+        return np.zeros((9, ny + 2 * h, nx + 2 * h))
+
+    def macros(f, h):
+        r, a, b = (np.zeros((ny, nx)) for _ in range(3))
+        it.run("lbm_primitives", "lbm_macros", nx, ny, h, F(f), F(r), F(a), F(b))
+        return np.stack([r, a, b])
+
+    # standard LBM behind c_slbm_* (sim/sim_slbm.F90, sim/sim.F90 lbm_primitives)
+    g1, g2 = arr(1), arr(1)
+    this = {"dt": np.float64(1.0), "flip": 0, "grid": {"nx": nx, "ny": ny, "f1": FArray(F(g1), [0, 0, 0]), "f2": FArray(F(g2), [0, 0, 0])}}
+    it.run("lbm_primitives", "lbm_eqinit_fields", nx, ny, 1, this["grid"]["f1"].a, F(p), F(u[0]), F(u[1]))
+    this["grid"]["f2"].a[...] = this["grid"]["f1"].a
+    out["slbm.init"] = g1.copy()
+    for _ in range(steps):
+        it.run("sim_slbm_class", "slbm_step", this, np.float64(omega))
+    out["slbm.final"] = F(this["grid"]["f1"].a).copy()
+    out["slbm.macros"] = macros(out["slbm.final"], 1)
+    # Lax-Wendroff plugins: lw (2nd order, halo 1), lw4 (halo 2), lw6 (halo 3)
+    for name, h, cls, mod in (("lw", 1, "sim_lw_class", "lbm_lw"), ("lw4", 2, "sim_lw4_class", "lbm_lw4"), ("lw6", 3, "sim_lw6_class", "lbm_lw6")):
+        g1, g2 = arr(h), arr(h)
+        lo = [1 - h, 1 - h, 0]
+        this = {"dt": np.float64(dt), "flip": 0, "grid": {"nx": nx, "ny": ny, "f1": FArray(F(g1), lo), "f2": FArray(F(g2), lo)}}
+        it.run("lbm_primitives", "lbm_eqinit_fields", nx, ny, h, this["grid"]["f1"].a, F(p), F(u[0]), F(u[1]))
+        it.run(mod, f"{name}_bc", nx, ny, this["grid"]["f1"].a)
+        out[f"{name}.init"] = g1.copy()
+        for _ in range(steps):
+            it.run(cls, f"{name}_step", this, np.float64(omega))
+        out[f"{name}.final"] = F(this["grid"]["f1"].a).copy()
+        out[f"{name}.macros"] = macros(out[f"{name}.final"], h)
+    # Heun finite-volume plugin (sim/sim_fvm.F90)
+    g = [arr(2) for _ in range(3)]
+    lo = [-1, -1, 0]
+    this = {"dt": np.float64(0.3), "nx": nx, "ny": ny, "f1": FArray(F(g[0]), lo), "f2": FArray(F(g[1]), lo), "fc": FArray(F(g[2]), lo)}
+    it.run("lbm_primitives", "lbm_eqinit_fields", nx, ny, 2, this["f1"].a, F(p), F(u[0]), F(u[1]))
+    it.run("lbm_fvm", "fvm_bc", nx, ny, this["f1"].a)
+    out["fvm.init"] = g[0].copy()
+    for _ in range(2):
+        it.run("sim_fvm_class", "fvm_step", this, np.float64(1.2))
+    out["fvm.final"] = F(this["f1"].a).copy()
+    out["fvm.args"] = np.array([0.3, 1.2, 2])
+    out["statements_executed"] = np.array([it.nstmt])
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for prec in ("f64", "f32"):
@@ -194,3 +260,7 @@ if __name__ == "__main__":
         path = os.path.join(ROOT, "tests", "golden", f"refsrc_{prec}.npz")
         np.savez_compressed(path, **data)
         print(path, len(data), "arrays,", int(data["statements_executed"][0]), "Fortran statements executed")
+    data = generate_sim()
+    path = os.path.join(ROOT, "tests", "golden", "refsrc_sim_f64.npz")
+    np.savez_compressed(path, **data)
+    print(path, len(data), "arrays,", int(data["statements_executed"][0]), "Fortran statements executed")

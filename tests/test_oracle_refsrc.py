@@ -154,3 +154,95 @@ def test_committed_fixtures_are_what_the_reference_source_produces_today(prec):
         assert sorted(z.files) == sorted(fresh)
         for k in z.files:
             assert np.array_equal(z[k], fresh[k], equal_nan=True), k
+
+
+# ---- the plugins of sim/ (the second sandbox of the reference: c_slbm_*, c_lw_*, c_lw4_*, c_lw6_*, c_fvm_*) --------------------------
+@pytest.fixture(scope="module")
+def sim():
+    with np.load(os.path.join(ROOT, "tests", "golden", "refsrc_sim_f64.npz")) as z:
+        return {k: z[k] for k in z.files}, Oracle("f64")
+
+
+P = lambda a: a.ctypes.data  # noqa: E731
+
+
+def sim_macros(o, f, nx, ny, h):
+    r, a, b = (np.zeros((ny, nx)) for _ in range(3))
+    (o._sim_macros(nx, ny, P(f), P(r), P(a), P(b)) if h == 1 else o._simh_macros(nx, ny, h, P(f), P(r), P(a), P(b)))
+    return np.stack([r, a, b])
+
+
+def test_standard_lbm_plugin(sim):
+    """slbm_step (sim/sim_slbm.F90:81-110) over lbm_collide_and_stream_fused + lbm_periodic_bc_push (sim/sim.F90), DDF-shifted"""
+    d, o = sim
+    nx, ny, steps, _, omega = d["args"]
+    nx, ny = int(nx), int(ny)
+    p, u = np.ascontiguousarray(d["p"]), np.ascontiguousarray(d["u"])
+    f1 = np.zeros((9, ny + 2, nx + 2))
+    o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
+    assert np.array_equal(f1, d["slbm.init"]), "lbm_eqinit_fields"
+    f2 = f1.copy()
+    for _ in range(int(steps)):
+        o._sim_step(nx, ny, P(f1), P(f2), omega)
+        o._sim_bc(nx, ny, P(f2))
+        f1, f2 = f2, f1
+    assert np.array_equal(f1, d["slbm.final"]), "halo included"
+    assert np.array_equal(sim_macros(o, f1, nx, ny, 1), d["slbm.macros"]), "lbm_macros"
+
+
+@pytest.mark.parametrize("name,h,order", [("lw", 1, 2), ("lw4", 2, 4), ("lw6", 3, 6)])
+def test_lax_wendroff_plugins(sim, name, h, order):
+    """<name>_step (sim/sim_lw.F90, sim_lw4.F90, sim_lw6.F90): <name>_stream, <name>_collision, <name>_bc and the move_alloc swap"""
+    d, o = sim
+    nx, ny, steps, dt, omega = d["args"]
+    nx, ny = int(nx), int(ny)
+    p, u = np.ascontiguousarray(d["p"]), np.ascontiguousarray(d["u"])
+    f1 = np.zeros((9, ny + 2 * h, nx + 2 * h))
+    if h == 1:
+        o._sim_eqinit(nx, ny, P(f1), P(p), P(u[0]), P(u[1]))
+        o._lw_bc(nx, ny, P(f1))
+    else:
+        o._simh_eqinit(nx, ny, h, P(f1), P(p), P(u[0]), P(u[1]))
+        o._lwh_bc(nx, ny, h, P(f1))
+    assert np.array_equal(f1, d[f"{name}.init"])
+    f2 = np.zeros_like(f1)
+    for _ in range(int(steps)):
+        if h == 1:
+            o._lw_stream(nx, ny, P(f1), P(f2), dt)
+            o._lw_collision(nx, ny, P(f2), omega)
+            o._lw_bc(nx, ny, P(f2))
+        else:
+            o._lwh_stream(order, nx, ny, P(f1), P(f2), dt)
+            o._lwh_collision(nx, ny, h, P(f2), omega)
+            o._lwh_bc(nx, ny, h, P(f2))
+        f1, f2 = f2, f1
+    assert np.array_equal(f1, d[f"{name}.final"])
+    assert np.array_equal(sim_macros(o, f1, nx, ny, h), d[f"{name}.macros"])
+
+
+def test_heun_finite_volume_plugin(sim):
+    """fvm_step (sim/sim_fvm.F90:285-322): collisions, fvm_predict_hc, fvm_correct_hc, fvm_bc, the three-buffer rotation"""
+    d, o = sim
+    nx, ny = int(d["args"][0]), int(d["args"][1])
+    dt, omega, steps = d["fvm.args"]
+    p, u = np.ascontiguousarray(d["p"]), np.ascontiguousarray(d["u"])
+    f1 = np.zeros((9, ny + 4, nx + 4))
+    f2, fc = np.zeros_like(f1), np.zeros_like(f1)
+    o._simh_eqinit(nx, ny, 2, P(f1), P(p), P(u[0]), P(u[1]))
+    o._lwh_bc(nx, ny, 2, P(f1))
+    assert np.array_equal(f1, d["fvm.init"])
+    for _ in range(int(steps)):
+        o._simfvm_step(nx, ny, P(f1), P(f2), P(fc), dt, omega)
+        f1, fc = fc, f1
+    assert np.array_equal(f1, d["fvm.final"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/sim"), reason="the reference's sources are not on this machine")
+def test_committed_sim_fixtures_are_what_the_reference_source_produces_today():
+    from oracle.make_refsrc_golden import generate_sim
+
+    fresh = generate_sim()
+    with np.load(os.path.join(ROOT, "tests", "golden", "refsrc_sim_f64.npz")) as z:
+        assert sorted(z.files) == sorted(fresh)
+        for k in z.files:
+            assert np.array_equal(z[k], fresh[k]), k
