@@ -18,10 +18,22 @@ and sections, the operators + - * / ** (integer exponent 2 only) and the relatio
 real, sqrt, abs, min, max, hypot, merge.  Literals carry their kind: `1.0_wp`, `1.0d0`, `1.0` (default real = float32, as in
 Fortran), integers; mixed-kind arithmetic promotes like Fortran (integer -> real of the other operand's kind; float32 -> float64).
 """
+import ctypes
+import ctypes.util
 import os
 import re
 
 import numpy as np
+
+# the transcendental intrinsics go to the C library a gfortran binary on this machine would call (libm's sin / sinf ...), not to
+# numpy's own vectorised implementations, whose last bit may differ
+_LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+_LIBM_FUNCS = {}
+for _n in ("sin", "cos", "tan", "exp", "log", "atan", "asin", "acos", "tanh", "sinh", "cosh"):
+    _d, _f = getattr(_LIBM, _n), getattr(_LIBM, _n + "f")
+    _d.restype, _d.argtypes = ctypes.c_double, [ctypes.c_double]
+    _f.restype, _f.argtypes = ctypes.c_float, [ctypes.c_float]
+    _LIBM_FUNCS[_n] = (_d, _f)
 
 REF_SRC = "/root/reference/src"
 
@@ -717,6 +729,13 @@ class Interp:
                 r = abs(a) % abs(b)
                 return r if a >= 0 else -r
             raise FortranError("mod() of reals is not supported")
+        if name in _LIBM_FUNCS:
+            x = vals[0]
+            if isinstance(x, np.float32):
+                return np.float32(_LIBM_FUNCS[name][1](float(x)))
+            if isinstance(x, np.float64):
+                return np.float64(_LIBM_FUNCS[name][0](float(x)))
+            raise FortranError(f"{name}() of {type(x).__name__}: scalars of a real kind only")
         if name == "sqrt":
             return np.sqrt(vals[0])
         if name == "abs":
@@ -801,6 +820,8 @@ class Interp:
                 fr["vars"][n] = FArray(np.full(shape, np.nan if d.typ == "real" else 0, dtype=t), lo)
             else:
                 fr["vars"][n] = None
+        if proc.kind == "function" and proc.result not in proc.decls:
+            fr["vars"][proc.result] = {}  # a derived-type result: an object whose components the body defines
         self.exec_block(proc.body, 0, len(proc.body), fr)
         for n, node in byref:
             v = fr["vars"].get(n)

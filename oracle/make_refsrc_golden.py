@@ -17,6 +17,7 @@ What runs, per precision (wp = real64 / real32, i.e. the reference built without
                               fdm_bardow_kernel (default, -DFDM_WLS, -DFDM_WLS_GAUSS_V1, -DFDM_WLS_GAUSS_V2, -DFDM_ISO), fdm_sofonea_kernel
     periodic_dugks.F90        kernel_bgk, kernel_stream (+ update_ew / update_ns) with and without -DDUGKS
     vorticity.f90             vorticity_2nd, vorticity_4th
+    benchmarks/*.f90          taylor_green_t (constructor, eval), eval_vortex_case -- transcendental functions from this machine's libm
   whole procedures on a lattice_grid object (set_properties, set_pdf_to_equilibrium, N x perform_*step, update_macros), with the
   procedure pointers grid%streaming / grid%collision bound like the drivers bind them
     perform_lbm_step  x  collide_bgk / collide_trt / collide_rr;  perform_step (stream_fvm_bardow + collide_bgk);
@@ -35,7 +36,8 @@ if ROOT not in sys.path:
 from oracle.f90_exec import FArray, Interp  # noqa: E402
 
 FILES = ["precision.F90", "fvm_bardow.F90", "collision_bgk.F90", "collision_trt.F90", "collision_regularized.F90",
-         "collision_bgk_improved.f90", "periodic_lbm.f90", "periodic_dugks.F90", "vorticity.f90"]
+         "collision_bgk_improved.f90", "periodic_lbm.f90", "periodic_dugks.F90", "vorticity.f90",
+         "benchmarks/taylor_green.f90", "benchmarks/barotropic_vortex_case.F90"]
 SEED = 20261018
 
 
@@ -184,6 +186,24 @@ def generate(prec):
         for k, v in r.items():
             out[f"{name}.{k}"] = v
         out[f"{name}.args"] = np.array([nsteps, nu, dt, mg], dtype=np.float64)
+    # ---- the flow cases (src/benchmarks): sin / cos / exp come from this machine's libm, like in a gfortran binary built here ----------
+    n = 12
+    umax = dtype(0.01) / np.sqrt(dtype(3.0))
+    nu_tg = (umax * dtype(n)) / dtype(100.0)
+    kx = dtype(2) * it.constant("taylor_green", "pi") / dtype(n)
+    case = it.run("taylor_green", "taylor_green_t_constructor", n, n, kx, kx, umax, nu_tg)
+    out["tg.params"] = np.array([n, kx, umax, nu_tg, case["td"]], dtype=dtype)
+    for k, t in enumerate((dtype(0.0), dtype(123.5))):
+        p, ux, uy = (np.zeros((n, n), dtype=dtype) for _ in range(3))
+        it.run("taylor_green", "taylor_green_eval", case, t, F(p), F(ux), F(uy))
+        out[f"tg.fields{k}"] = np.stack([p, ux, uy])
+        out[f"tg.t{k}"] = np.array([t], dtype=dtype)
+    vc = {"u0": dtype(0.05), "xc": dtype(6.2), "yc": dtype(5.1), "rc": dtype(2.5), "eps": dtype(0.02), "rho0": dtype(1.0),
+          "csqr": dtype(1) / dtype(3)}
+    r, a, b = (np.zeros((9, 7), dtype=dtype) for _ in range(3))
+    it.run("barotropic_vortex_case", "eval_vortex_case", vc, 9, 7, F(r), F(a), F(b))
+    out["vortex.params"] = np.array([vc["u0"], vc["xc"], vc["yc"], vc["rc"], vc["eps"]], dtype=dtype)
+    out["vortex.fields"] = np.stack([r, a, b])
     out["statements_executed"] = np.array([it.nstmt + it_split.nstmt + it_dugks.nstmt])
     return out
 

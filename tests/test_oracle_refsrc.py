@@ -97,6 +97,23 @@ def test_dugks_stream_kernel(ref, dugks):
     assert same(fp, d["dugks_stream_on" if dugks else "dugks_stream_off"], n), "kernel_stream + update_ew / update_ns (src/periodic_dugks.F90:190-434)"
 
 
+def test_flow_cases(ref):
+    """taylor_green_t / eval_vortex_case (src/benchmarks): the fixtures carry this image's libm in their last bit (sin, cos, exp), the
+    oracle calls the same libm -- equal bits here; two units in the last place are allowed should a machine's libm differ."""
+    prec, d, o = ref
+
+    def close(a, b):
+        return np.array_equal(a, b) or np.all(np.abs(a - b) <= 2 * np.spacing(np.maximum(np.abs(a), np.abs(b))))
+
+    n, kx, umax, nu, td = d["tg.params"]
+    n = int(n)
+    assert o.tg_decay_time(kx, kx, nu) == td
+    for k in (0, 1):
+        assert close(np.stack(o.taylor_green_eval(n, n, kx, kx, umax, td, d[f"tg.t{k}"][0])), d[f"tg.fields{k}"])
+    u0, xc, yc, rc, eps = d["vortex.params"]
+    assert close(np.stack(o.vortex_eval(9, 7, u0, xc, yc, rc, eps)), d["vortex.fields"])
+
+
 RUNS = {"run_lbm_bgk": (Oracle.SCHEME_LBM, Oracle.BGK), "run_lbm_trt": (Oracle.SCHEME_LBM, Oracle.TRT), "run_lbm_rr": (Oracle.SCHEME_LBM, Oracle.RR),
         "run_fvm_bgk": (Oracle.SCHEME_FVM_BARDOW, Oracle.BGK), "run_dugks": (Oracle.SCHEME_DUGKS, Oracle.BGK)}
 
