@@ -139,6 +139,6 @@ def test_out_of_bounds_and_unsupported_constructs_raise():
     it = make("f64")
     with pytest.raises(FortranError):
         it.run("m", "bad_index", np.zeros(3))
-    it.load_text("module u\ncontains\n subroutine s(a)\n real(8), intent(inout) :: a(2)\n a(1) = sin(a(2))\n end subroutine\nend module\n")
+    it.load_text("module u\ncontains\n subroutine s(a)\n real(8), intent(inout) :: a(2)\n a(1) = bessel_j0(a(2))\n end subroutine\nend module\n")
     with pytest.raises(FortranError):
         it.run("u", "s", np.zeros(2))
