@@ -48,16 +48,23 @@ template <typename T> __device__ __forceinline__ T node_rho(const T (&f)[9])
     return (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
 }
 
-// The collisions that divide by the density take an optional `inv`: the reciprocal T(1) / node_rho(f), computed by the caller.
+// The collisions that divide by the density take an optional `inv` (template parameter PRE = true): the reciprocal
+// T(1) / node_rho(f), computed by the caller.
 // Same division on the same operand, so nothing changes in the result; a kernel that collides several independent nodes per
 // thread uses it to issue all the divisions first -- the IEEE division expands into a fast path plus a branch to a slow path, and
 // that branch otherwise ends the basic block, so that the instruction streams of the nodes could not be interleaved.
 
+// PRE is a template parameter, not a run-time test: with PRE = false (every caller but the three-level kernel of plbm_lbm3w.cu)
+// each function instantiates to exactly the statements it had before `inv` existed.
+
 // rho, ux, uy with the collision kernels' summation order (f0 added last).
-template <typename T> __device__ __forceinline__ void moments(const T (&f)[9], T& rho, T& ux, T& uy, const T* inv = nullptr)
+template <typename T, bool PRE = false>
+__device__ __forceinline__ void moments(const T (&f)[9], T& rho, T& ux, T& uy, const T* inv = nullptr)
 {
-    rho = node_rho(f);
-    T invrho = inv ? *inv : T(1) / rho;
+    rho = (((f[5] + f[7]) + (f[6] + f[8])) + ((f[1] + f[3]) + (f[2] + f[4]))) + f[0];
+    T invrho;
+    if constexpr (PRE) invrho = *inv;
+    else invrho = T(1) / rho;
     ux = invrho * (((f[5] - f[7]) + (f[8] - f[6])) + (f[1] - f[3]));
     uy = invrho * (((f[5] - f[7]) + (f[6] - f[8])) + (f[2] - f[4]));
 }
@@ -90,18 +97,18 @@ template <typename T> __device__ __forceinline__ void equilibrium(T rho, T ux, T
     feq[8] = wd * rho * (indp + T(3) * uxmy + T(4.5) * uxmy * uxmy);
 }
 
-template <typename T> __device__ __forceinline__ void collide_bgk(T (&f)[9], T omega, const T* inv = nullptr)
+template <typename T, bool PRE = false> __device__ __forceinline__ void collide_bgk(T (&f)[9], T omega, const T* inv = nullptr)
 {
     T omegabar = T(1) - omega;
     T rho, ux, uy, feq[9];
-    moments(f, rho, ux, uy, inv);
+    moments<T, PRE>(f, rho, ux, uy, inv);
     equilibrium(rho, ux, uy, feq);
 #pragma unroll
     for (int q = 0; q < 9; ++q) f[q] = omegabar * f[q] + omega * feq[q];
 }
 
 // Re-associated BGK of kernel_bgk / bgk_kernel_cache (numerically different from collide_bgk).
-template <typename T> __device__ __forceinline__ void collide_bgk_split(T (&f)[9], T omega, const T* inv = nullptr)
+template <typename T, bool PRE = false> __device__ __forceinline__ void collide_bgk_split(T (&f)[9], T omega, const T* inv = nullptr)
 {
     const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd();
     T omegabar = T(1) - omega;
@@ -109,7 +116,7 @@ template <typename T> __device__ __forceinline__ void collide_bgk_split(T (&f)[9
     T omega_ws = T(3) * omega * ws;
     T omega_wd = T(3) * omega * wd;
     T rho, ux, uy;
-    moments(f, rho, ux, uy, inv);
+    moments<T, PRE>(f, rho, ux, uy, inv);
     T indp = K<T>::one_third() - T(0.5) * (ux * ux + uy * uy);
 
     f[0] = omegabar * f[0] + omega_w0 * rho * indp;
@@ -214,7 +221,7 @@ template <typename T> __device__ __forceinline__ void collide_trt(T (&f)[9], T l
 }
 
 // Recursive-regularized collision with 3rd/4th-order Hermite equilibrium.
-template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T omega, const T* inv = nullptr)
+template <typename T, bool PRE = false> __device__ __forceinline__ void collide_rr(T (&f)[9], T omega, const T* inv = nullptr)
 {
     const T w0 = K<T>::w0(), ws = K<T>::ws(), wd = K<T>::wd(), csqr = K<T>::csqr();
     T omega_w0 = w0 * (T(1) - omega);
@@ -226,7 +233,9 @@ template <typename T> __device__ __forceinline__ void collide_rr(T (&f)[9], T om
     T feq[9];
 
     T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
-    T invrho = inv ? *inv : T(1) / rho;
+    T invrho;
+    if constexpr (PRE) invrho = *inv;
+    else invrho = T(1) / rho;
     T ux = invrho * (((vNE - vSW) + (vSE - vNW)) + (vE - vW));
     T uy = invrho * (((vNE - vSW) + (vNW - vSE)) + (vN - vS));
 
@@ -362,7 +371,7 @@ template <typename T> __device__ __forceinline__ void collide_trt_split(T (&f)[9
 // collide_bgk_improved (src/collision_bgk_improved.f90:24-107): product-form BGK with a cubic
 // Galilean-invariance correction.  The reference kernel ignores the padded leading dimension
 // (identical when ny is a multiple of 16); the intended per-node arithmetic is kept.
-template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f)[9], T omega, const T* inv = nullptr)
+template <typename T, bool PRE = false> __device__ __forceinline__ void collide_bgk_improved(T (&f)[9], T omega, const T* inv = nullptr)
 {
     const T one_third = T(1) / T(3), two_thirds = T(2) / T(3);
     T fac = T(4.5) - T(2.25) * omega;
@@ -371,7 +380,9 @@ template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f
     T vNE = f[5], vNW = f[6], vSW = f[7], vSE = f[8];
 
     T rho = (((vNE + vSW) + (vNW + vSE)) + ((vE + vW) + (vN + vS))) + vC;
-    T invrho = inv ? *inv : T(1) / rho;
+    T invrho;
+    if constexpr (PRE) invrho = *inv;
+    else invrho = T(1) / rho;
     T sumX1 = vE + vNE + vSE;
     T sumXN = vW + vNW + vSW;
     T sumY1 = vN + vNE + vNW;
@@ -405,14 +416,15 @@ template <typename T> __device__ __forceinline__ void collide_bgk_improved(T (&f
     f[8] = omegabar * vSE + X1 * YN;
 }
 
-template <typename T, int MODEL> __device__ __forceinline__ void collide(T (&f)[9], const CollideParams<T>& p, const T* inv = nullptr)
+template <typename T, int MODEL, bool PRE = false>
+__device__ __forceinline__ void collide(T (&f)[9], const CollideParams<T>& p, const T* inv = nullptr)
 {
-    if (MODEL == M_BGK) collide_bgk(f, p.omega, inv);
+    if (MODEL == M_BGK) collide_bgk<T, PRE>(f, p.omega, inv);
     else if (MODEL == M_TRT) collide_trt(f, p.omega, p.lambda_d);
-    else if (MODEL == M_RR) collide_rr(f, p.omega, inv);
-    else if (MODEL == M_BGK_SPLIT) collide_bgk_split(f, p.omega, inv);
+    else if (MODEL == M_RR) collide_rr<T, PRE>(f, p.omega, inv);
+    else if (MODEL == M_BGK_SPLIT) collide_bgk_split<T, PRE>(f, p.omega, inv);
     else if (MODEL == M_TRT_SPLIT) collide_trt_split(f, p.omega, p.lambda_d);
-    else if (MODEL == M_BGK_IMPROVED) collide_bgk_improved(f, p.omega, inv);
+    else if (MODEL == M_BGK_IMPROVED) collide_bgk_improved<T, PRE>(f, p.omega, inv);
 }
 // does collide<T, MODEL> divide by the density (i.e. does it take `inv`)
 __host__ __device__ constexpr bool model_divides(int model) { return model != M_TRT && model != M_TRT_SPLIT && model != M_NONE; }
@@ -473,7 +485,7 @@ __device__ __forceinline__ void collide_nodes(T (&n)[V][9], const CollideParams<
 #pragma unroll
             for (int q = 0; q < 9; ++q) f[q] = F2(n[v][q], n[v + 1][q]);
             const F2 i2(inv[v], inv[v + 1]);
-            collide<F2, MODEL>(f, p2, &i2);
+            collide<F2, MODEL, true>(f, p2, &i2);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 n[v][q] = f[q].lo();
@@ -482,7 +494,7 @@ __device__ __forceinline__ void collide_nodes(T (&n)[V][9], const CollideParams<
         }
     } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) collide<T, MODEL>(n[v], p, &inv[v]);
+        for (int v = 0; v < V; ++v) collide<T, MODEL, true>(n[v], p, &inv[v]);
     }
 }
 
