@@ -273,8 +273,65 @@ def generate_sim():
     return out
 
 
+def lattice_digest(f, ny):
+    """sha256 of the physical rows of a lattice f[q, x, ld] (what a bitwise comparison would compare), as 32 bytes"""
+    import hashlib
+
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(f[:, :, :ny]).tobytes()).digest(), dtype=np.uint8)
+
+
+def generate_tg64():
+    """The configuration of the reference's own golden files (graphs/fvm_*_64.txt): Taylor-Green on 64 x 64, Re = 100,
+    umax = 0.01 / sqrt(3), nu = umax n / Re, fp64 -- initial condition by taylor_green_eval (t = 0) and the density conversion of
+    app/main_taylor_green.f90:133-149, set_properties WITHOUT a magic number (the default branch), set_pdf_to_equilibrium, then a few
+    steps of each scheme, update_macros.  A 64 x 64 DUGKS step is 1.3 million Fortran statements (two and a half minutes in the
+    interpreter), so this fixture is generated on request (`--tg64`) and not regenerated by the tests; lattices are stored as
+    sha256 digests, the macroscopic fields in full."""
+    n = 64
+    out = {}
+    its = {"dugks": interp("f64", DUGKS=1), "plain": interp("f64")}
+    it = its["plain"]
+    umax = np.float64(0.01) / np.sqrt(np.float64(3.0))
+    nu = (umax * np.float64(n)) / np.float64(100.0)
+    tau = np.float64(3.0) * nu
+    kx = np.float64(2) * it.constant("taylor_green", "pi") / np.float64(n)
+    case = it.run("taylor_green", "taylor_green_t_constructor", n, n, kx, kx, umax, nu)
+    out["params"] = np.array([n, umax, nu, tau, kx, case["td"]])
+    cases = {"dugks": ("dugks", "perform_dugks_step", ("periodic_dugks", "dugks_stream"), ("periodic_dugks", "dugks_collide"), 5.0 * tau, 2,
+                       "periodic_dugks"),
+             "fvm_bgk": ("plain", "perform_step", ("fvm_bardow", "stream_fvm_bardow"), ("collision_bgk", "collide_bgk"), 2.0 * tau, 2, "fvm_bardow"),
+             "lbm_bgk": ("plain", "perform_lbm_step", ("periodic_lbm", "lbm_stream"), ("collision_bgk", "collide_bgk"), np.float64(1.0), 3,
+                         "periodic_lbm")}
+    for name, (which, step_proc, streaming, collision, dt, nsteps, mod) in cases.items():
+        interp_ = its[which]
+        g = new_grid(interp_, n, n)
+        interp_.run("taylor_green", "taylor_green_eval", case, np.float64(0.0), g["rho"].a, g["ux"].a, g["uy"].a)
+        interp_.run("fvm_bardow", "set_properties", g, nu, np.float64(dt))
+        g["rho"].a[...] = g["rho"].a / g["csqr"] + np.float64(1.0)  # apply_initial_condition: grid%rho = grid%rho/grid%csqr + rho0
+        out[f"{name}.init"] = g["_mf"].copy()
+        interp_.run("fvm_bardow", "set_pdf_to_equilibrium", g)
+        g["streaming"] = lambda i_=interp_, s_=streaming, g_=g: i_.run(s_[0], s_[1], g_)
+        g["collision"] = lambda i_=interp_, c_=collision, g_=g: i_.run(c_[0], c_[1], g_)
+        for _ in range(nsteps):
+            interp_.run(mod, step_proc, g)
+        interp_.run("fvm_bardow", "update_macros", g)
+        out[f"{name}.args"] = np.array([nsteps, dt])
+        out[f"{name}.props"] = np.array([g["tau"], g["omega"], g["trt_magic"], g["csqr"]])
+        out[f"{name}.idx"] = np.array([g["iold"], g["inew"]])
+        out[f"{name}.macros"] = g["_mf"].copy()
+        out[f"{name}.digests"] = np.stack([lattice_digest(g["_f"][0], n), lattice_digest(g["_f"][1], n)])
+    out["statements_executed"] = np.array([sum(i.nstmt for i in its.values())])
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "--tg64" in sys.argv:
+        data = generate_tg64()
+        path = os.path.join(ROOT, "tests", "golden", "refsrc_tg64_f64.npz")
+        np.savez_compressed(path, **data)
+        print(path, len(data), "arrays,", int(data["statements_executed"][0]), "Fortran statements executed")
+        sys.exit(0)
     for prec in ("f64", "f32"):
         data = generate(prec)
         path = os.path.join(ROOT, "tests", "golden", f"refsrc_{prec}.npz")

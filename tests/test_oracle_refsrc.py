@@ -263,3 +263,35 @@ def test_committed_sim_fixtures_are_what_the_reference_source_produces_today():
         assert sorted(z.files) == sorted(fresh)
         for k in z.files:
             assert np.array_equal(z[k], fresh[k]), k
+
+
+# ---- the configuration of the reference's golden files, a few steps of it ------------------------------------------------------------
+TG64 = os.path.join(ROOT, "tests", "golden", "refsrc_tg64_f64.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(TG64), reason="generated on request: python oracle/make_refsrc_golden.py --tg64 (ten minutes)")
+@pytest.mark.parametrize("name,scheme", [("dugks", Oracle.SCHEME_DUGKS), ("fvm_bgk", Oracle.SCHEME_FVM_BARDOW), ("lbm_bgk", Oracle.SCHEME_LBM)])
+def test_golden_configuration_64x64(name, scheme):
+    """Taylor-Green 64 x 64, Re = 100 -- what graphs/fvm_*_64.txt were produced with -- executed from the reference's source for a few
+    steps (taylor_green_eval, set_properties without a magic number, set_pdf_to_equilibrium, perform_*step, update_macros): the oracle
+    holds the same lattices (sha256 of the physical rows), indices and macroscopic fields."""
+    import hashlib
+
+    with np.load(TG64) as z:
+        d = {k: z[k] for k in z.files}
+    n = 64
+    nsteps, dt = d[f"{name}.args"]
+    og = OracleGrid(n, n, "f64")
+    og.rho, og.ux, og.uy = (np.ascontiguousarray(a) for a in d[f"{name}.init"])
+    p = og.set_properties(d["params"][2], dt, None)
+    assert np.array_equal(np.array([p["tau"], p["omega"], p["trt_magic"], p["csqr"]]), d[f"{name}.props"])
+    og.set_pdf_to_equilibrium()
+    og.run(scheme, Oracle.BGK, int(nsteps))
+    assert [og.iold, og.inew] == list(d[f"{name}.idx"])
+    for k in (1, 2):
+        digest = hashlib.sha256(np.ascontiguousarray(og.lattice(k)[:, :, :n]).tobytes()).digest()
+        assert digest == d[f"{name}.digests"][k - 1].tobytes(), f"lattice {k}"
+    assert np.array_equal(np.stack(og.update_macros(lagged=True)), d[f"{name}.macros"])
+    # and the initial fields are the oracle's own Taylor-Green evaluation + density conversion
+    pr, ux, uy = og.o.taylor_green_eval(n, n, d["params"][4], d["params"][4], d["params"][1], d["params"][5], 0.0)
+    assert np.array_equal(np.stack([pr / p["csqr"] + 1.0, ux, uy]), d[f"{name}.init"])
