@@ -463,7 +463,7 @@ class Interp:
             if SKIP_DECL.match(st):
                 continue
             m = DECL_RE.match(st)
-            if m and (stack == [] or not target.body or True) and self._looks_like_decl(st):
+            if m and self._looks_like_decl(st):
                 self._declare(target, m, st)
                 continue
             if stack:
@@ -851,7 +851,6 @@ class Interp:
         return self.eval(a, fr)
 
     def assign(self, lhs, value, fr):
-        proc = fr["proc"]
         if lhs[0] == "var" and "%" in lhs[1]:
             base, *fields = lhs[1].split("%")
             obj = self.lookup(fr, base)
@@ -876,7 +875,6 @@ class Interp:
             if isinstance(cur, FArray):
                 cur.a[...] = value  # whole-array assignment: numpy converts to the array's type element by element
                 return
-            d = None
             p = f["proc"]
             d = p.decls.get(name)
             if d is None:
