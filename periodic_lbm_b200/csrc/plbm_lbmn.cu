@@ -1,10 +1,13 @@
 // plbm_lbmn.cu -- NSTEP fused stream+collide steps per pass over HBM (temporal blocking of depth NSTEP, sm_100a).
 //
-// The headline kernel: with NSTEP = 3 it is what perform_lbm_step launches by default from 512^2 nodes (lbm_triples_wanted below;
-// variants 9 / 10 force its NSTEP = 2 / 3 instances on every grid they apply to).  It is the generalisation of k_lbm2_bulk
-// (plbm_lbm2.cu) from two to NSTEP levels: k_lbm2_bulk moves 73.6 B of DRAM traffic per update at 0.97 of the measured HBM copy
-// rate, i.e. it sits on the HBM roof of a two-step scheme, and the only way further up is fewer bytes per update: 144 / NSTEP B
-// (fp64; measured 49.4 B with NSTEP = 3).
+// With NSTEP = 3 this was the headline kernel of round 2 until k_lbm3_ws (plbm_lbm3w.cu: the same three steps with the levels skewed
+// and a producer warp) took over the launches that read no halo lines; k_lbmn_bulk<3> remains what perform_lbm_step launches for the
+// two-relaxation-time collisions, for the boundary launches of a slab (HALO) and under PLBM_TRIPLE_WS=0 (lbm_triple_ws_wanted below;
+// variants 9 / 10 force its NSTEP = 2 / 3 instances on every grid they apply to).  DUAL: the launch that closes a call also stores the
+// state after step NSTEP - 1 (Grid::spare, plbm_api.cu step_lbm_t).  It is the generalisation of k_lbm2_bulk (plbm_lbm2.cu) from two to
+// NSTEP levels: k_lbm2_bulk moves 73.6 B of DRAM traffic per update at 0.97 of the measured HBM copy rate, i.e. it sits on the HBM
+// roof of a two-step scheme, and the only way further up is fewer bytes per update: 144 / NSTEP B (fp64; measured 49.4 B with
+// NSTEP = 3).
 //
 // A block owns a strip of rows and marches along x.  In iteration x, after the raw column x + NSTEP - 1 has
 // landed in shared memory by bulk async copies (issued two columns ahead by lane 0 of every warp, one mbarrier per stage),
