@@ -180,10 +180,12 @@ int plbm_synchronize(plbm_handle grid);
 /* kernels launched by this process through the library since load (for bench accounting) */
 long long plbm_launch_count(void);
 /* select a kernel variant (tuning / A-B measurements); 0 = default everywhere.
- *   perform_lbm_step : 0 = default: calls of >= 4 steps advance THREE steps per pass over HBM (k_lbmn_bulk: bgk / trt / rr and
- *                      the -DSPLIT / improved operators, fp64 and fp32, from 512^2 nodes; env PLBM_TRIPLES=0: never, 2: at every
- *                      size), the last one to four steps of a call as pairs (k_lbm2_bulk on large grids, k_lbm2 on smaller ones;
- *                      env PLBM_PAIR_BULK=0 / 2: k_lbm2 / k_lbm2_bulk everywhere) and one closing single step (k_lbm, direct
+ *   perform_lbm_step : 0 = default: calls of >= 3 steps advance THREE steps per pass over HBM (k_lbm3_ws / k_lbmn_bulk, see
+ *                      plbm_lbm_triple_kernel: bgk / trt / rr and the -DSPLIT / improved operators, fp64 and fp32, from 512^2
+ *                      nodes; env PLBM_TRIPLES=0: never, 2: at every size).  With the third lattice buffer (plbm_lbm_closing_triple)
+ *                      a call closes with a triple that stores states n-1 and n, preceded by one pair when two steps are left
+ *                      over; without it the last one to four steps go as pairs (k_lbm2_bulk on large grids, k_lbm2 on smaller
+ *                      ones; env PLBM_PAIR_BULK=0 / 2: k_lbm2 / k_lbm2_bulk everywhere) and one closing single step (k_lbm, direct
  *                      128-bit loads); grids that fit in the shared memory of one cluster: all steps in one launch
  *                      (cluster-resident kernel).  One step per launch:
  *                      1 warp-shuffle shifts, 2 scalar, 3 TMA-staged tile, 4 streaming hints;
