@@ -295,3 +295,32 @@ def test_golden_configuration_64x64(name, scheme):
     # and the initial fields are the oracle's own Taylor-Green evaluation + density conversion
     pr, ux, uy = og.o.taylor_green_eval(n, n, d["params"][4], d["params"][4], d["params"][1], d["params"][5], 0.0)
     assert np.array_equal(np.stack([pr / p["csqr"] + 1.0, ux, uy]), d[f"{name}.init"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the reference's sources are not on this machine")
+@pytest.mark.parametrize("prec", PRECS)
+def test_the_comparison_is_sensitive_to_one_reassociated_statement(prec):
+    """Mutation check of the whole arrangement: re-associate ONE sum in the reference's TRT kernel text (mathematically the same
+    value) and the interpreter's output must no longer equal the fixture the oracle reproduces -- bit-for-bit equality with the
+    unmodified source is therefore a statement about the order of every operation, not a coincidence of loose arithmetic."""
+    from oracle.f90_exec import Interp
+    from oracle.make_refsrc_golden import F, ld_of
+
+    with np.load(os.path.join(ROOT, "tests", "golden", f"refsrc_{prec}.npz")) as z:
+        d = {k: z[k] for k in z.files}
+    text = open("/root/reference/src/collision_trt.F90").read()
+    old = "( vN + vS - fac1 * velY2 - t1x2 * feq_common )"
+    assert text.count(old) == 1
+    outs = []
+    for src in (text, text.replace(old, "( vN + vS - t1x2 * feq_common - fac1 * velY2 )")):
+        it = Interp(prec)
+        for f in ("precision.F90", "fvm_bardow.F90"):
+            it.load(f)
+        it.load_text(src)
+        f = d["stream"].copy()
+        omega = d["params"][0]
+        it.run("collision_trt", "collide_trt/trt_naive", 7, 5, F(f), ld_of(5), omega, d["lambda_d"][0])
+        outs.append(f)
+    assert np.array_equal(outs[0], d["trt"])          # the text as it is: the fixture
+    assert not np.array_equal(outs[1], d["trt"])      # one re-associated sum: different last bits somewhere
+    assert np.allclose(outs[1], d["trt"], rtol=1e-5 if prec == "f32" else 1e-13, atol=0)
